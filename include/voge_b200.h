@@ -1,0 +1,142 @@
+/*
+ * voge_b200.h -- C ABI of libvoge_b200.so, the B200 (sm_100a) implementation of the
+ * VoGE ray-tracing hot path.
+ *
+ * Drop-in boundary: these entry points are what the reference's pybind11 module
+ * `VoGE._C` (reference VoGE/csrc/ext.cpp:7-17) binds for this path, restated as plain
+ * `extern "C"` functions over raw DEVICE pointers, sizes and a CUDA stream -- no torch
+ * types.  The caller owns every buffer (the Python host allocates them with torch so the
+ * caching allocator owns all memory); kernels never allocate or free.  All functions are
+ * stateless and re-entrant, launch asynchronously on `stream` and return 0 on success or
+ * a cudaError_t value (use voge_error_string()).  float = IEEE fp32, indices = int32.
+ *
+ * Conventions:  N Gaussians, B views, P = B*N packed Gaussians,
+ * H x W image, K = max_assign, BH x BW coarse bins of bin_size pixels, M = max points
+ * per bin.  "isigmas" is the 3x3 matrix S (= 2 * inverse covariance) row-major.
+ */
+#ifndef VOGE_B200_H
+#define VOGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* voge_stream_t; /* cudaStream_t */
+
+/* ---- library info ------------------------------------------------------------------ */
+int voge_version(void);                       /* ABI version, currently 1               */
+const char* voge_error_string(int code);      /* cudaGetErrorString for a returned code */
+int voge_device_sm_count(int* sm_count);      /* SMs of the current device              */
+
+/* ---- coarse binning ----------------------------------------------------------------
+ * Replaces `rasterize_points_coarse` (ext.cpp:8 -> RasterizeEllipseCoarseCuda,
+ * rasterize_coarse.cu:254-305; kernels :20-42 and :44-188).
+ * points_ndc (P,3): x,y in VoGE's flipped NDC, z = view-space depth (skip if z < 0);
+ * radius (P,2): bbox half extents.  first_idx/num_per (B) int64 DEVICE arrays;
+ * max_per_cloud >= max(num_per) (host value, sizes the grid).
+ * bin_points (B,BH,BW,M) int32 must be PRE-FILLED with -1 by the caller (the reference's
+ * at::full, rasterize_coarse.cu:222); indices written are PACKED and, unlike the reference, in
+ * deterministic ascending order.  bin_counts (B,BH,BW) int32 receives the TRUE number of
+ * overlapping Gaussians per bin; a count > M means overflow (the reference prints from the
+ * device and drops chunks, :154-170): here the first M indices are kept and the host raises.
+ * scratch: int32 device buffer of voge_rasterize_coarse_scratch_elems(...) elements.
+ * Returns cudaErrorInvalidValue if BH or BW > 65 (the reference refuses >= 66, :213).          */
+int64_t voge_rasterize_coarse_scratch_elems(int B, int max_per_cloud, int H, int W, int bin_size);
+int voge_rasterize_coarse(const float* points_ndc, const float* radius,
+                          const int64_t* first_idx, const int64_t* num_per,
+                          int B, int P, int max_per_cloud, int H, int W, int bin_size, int M,
+                          int32_t* scratch, int32_t* bin_points, int32_t* bin_counts,
+                          voge_stream_t stream);
+
+/* ---- fine ray tracing ----------------------------------------------------------------
+ * Replaces `ray_trace_voge_fine` (ext.cpp:9 -> RayTraceFineVoge, ray_trace_voge.cu:219-280,
+ * kernel :135-217).  Outputs (B,H,W,K) are fully written by the callee-side kernels
+ * (idx init -1, len/act init 1e10, dsd init 0).  Arithmetic reproduces the reference's
+ * fp32 rounding sequence bit for bit (DESIGN.md "rounding contract").  The batch stride of
+ * bin_points is BH*BW*M (the reference's b*BH*BH*M, :185, is a defect for non-square grids).
+ * The _counts variant takes the optional bin_counts (B,BH,BW) of voge_rasterize_coarse so
+ * only the first min(count, M) entries of each list are scanned (NULL = scan all M).       */
+int voge_ray_trace_fine(const float* mus, const float* isigmas, const float* rays,
+                        const int32_t* bin_points, float thr_act, int bin_size,
+                        int B, int H, int W, int BH, int BW, int M, int K, int P,
+                        int32_t* out_idx, float* out_len, float* out_act, float* out_dsd,
+                        voge_stream_t stream);
+int voge_ray_trace_fine_counts(const float* mus, const float* isigmas, const float* rays,
+                               const int32_t* bin_points, const int32_t* bin_counts,
+                               float thr_act, int bin_size,
+                               int B, int H, int W, int BH, int BW, int M, int K, int P,
+                               int32_t* out_idx, float* out_len, float* out_act, float* out_dsd,
+                               voge_stream_t stream);
+
+/* Replaces `ray_trace_voge_fine_backward` (ext.cpp:10 -> RayTraceFineVogeBackward,
+ * ray_trace_voge.cu:334-379, kernel :283-332).  grad_mus (P,3) and grad_isg (P,3,3) must be
+ * ZEROED by the caller (they are accumulated into); grad_rays (B,H,W,3) is written in full
+ * and may be NULL when the ray gradient is not needed.                                     */
+int voge_ray_trace_fine_backward(const float* mus, const float* isigmas, const float* rays,
+                                 const int32_t* idx, const float* grad_len,
+                                 const float* grad_act, const float* grad_dsd,
+                                 int B, int H, int W, int K, int P,
+                                 float* grad_rays, float* grad_mus, float* grad_isg,
+                                 voge_stream_t stream);
+
+/* ---- blend weights (reference: pure PyTorch, VoGE/Aggregation.py:30-107) ---------------
+ * weight[r,m] = exp(-absorptivity * sum_k exp(-act_k)(erf((len_m-len_k)sqrt(dsd_k+1e-10))+1)/2)
+ *               * exp(-act_m) / exp(-0.5);   valid_num[r] = #(idx >= 0) as int64.
+ * R = number of rays (B*H*W).                                                             */
+int voge_aggregation(const int32_t* idx, const float* act, const float* len, const float* dsd,
+                     float absorptivity, int64_t R, int K,
+                     float* weight, int64_t* valid_num, voge_stream_t stream);
+
+/* Analytic backward of voge_aggregation (the reference relies on autograd through
+ * Aggregation.py:30-79).  Writes grad_act/grad_len/grad_dsd (R,K) in full.                */
+int voge_aggregation_backward(const float* act, const float* len, const float* dsd,
+                              const float* grad_weight, float absorptivity, int64_t R, int K,
+                              float* grad_act, float* grad_len, float* grad_dsd,
+                              voge_stream_t stream);
+
+/* ---- gather-blend (merge_final, Aggregation.py:111-141; Renderer.py:153-176) -----------
+ * out[r,:] = sum_{k < valid_num[r]} weight[r,k] * attr[idx[r,k] (or 0 when < 0), :].
+ * If background != NULL (C floats, device) the composite of Renderer.py:162-171 is fused:
+ *   sil = min(sum_k weight[r,k], 1);  mask = (mask_thr > 0) ? (sil > mask_thr) : sil;
+ *   out = min(out + (1 - mask) * background, 1).
+ * idx_mod > 0 maps packed indices (b*N+n) onto attr rows with idx % idx_mod; attr has n_attr
+ * rows and indices >= n_attr are ignored (the reference asserts on the host, :120).        */
+int voge_merge_final(const float* attr, const float* weight, const int32_t* idx,
+                     const int64_t* valid_num, const float* background, float mask_thr,
+                     int64_t R, int K, int C, int idx_mod, int n_attr,
+                     float* out, voge_stream_t stream);
+
+/* Backward of voge_merge_final: grad_attr (n_attr,C) must be ZEROED by the caller and is
+ * accumulated into; grad_weight (R,K) is written in full.  Either may be NULL.            */
+int voge_merge_final_backward(const float* attr, const float* weight, const int32_t* idx,
+                              const int64_t* valid_num, const float* background,
+                              float mask_thr, const float* out, const float* grad_out,
+                              int64_t R, int K, int C, int idx_mod, int n_attr,
+                              float* grad_attr, float* grad_weight, voge_stream_t stream);
+
+/* ---- sampling (inverse rendering) --------------------------------------------------------
+ * Replaces `sample_voge` (ext.cpp:14 -> SampleVoge, sample_voge.cu:95-134, kernel :35-66):
+ * feat[n,:] += w * image[r,:], wsum[n] += w for every (r,k) with idx >= 0.
+ * feat (num_vert,C) and wsum (num_vert) must be ZEROED by the caller.                     */
+int voge_sample(const float* image, const float* weight, const int32_t* idx,
+                int64_t R, int K, int C, int num_vert,
+                float* feat, float* wsum, voge_stream_t stream);
+
+/* Replaces `sample_voge_backward` (ext.cpp:15, sample_voge.cu:173-252): writes
+ * grad_image (R,C) and grad_weight (R,K) in full (no pre-zeroing needed).                 */
+int voge_sample_backward(const float* image, const float* weight, const int32_t* idx,
+                         const float* grad_feat, const float* grad_wsum,
+                         int64_t R, int K, int C,
+                         float* grad_image, float* grad_weight, voge_stream_t stream);
+
+/* Replaces `scatter_max` (ext.cpp:16, sample_voge.cu:69-92,137-170): wmax[n] = max(w).
+ * wmax (num_vert) must be ZEROED by the caller (the reference starts from zeros).         */
+int voge_scatter_max(const float* weight, const int32_t* idx, int64_t R, int K,
+                     int num_vert, float* wmax, voge_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOGE_B200_H */

@@ -1,0 +1,170 @@
+"""GPU parity tests: every C-ABI entry point of libvoge_b200.so against the CPU oracle on the same
+seeded inputs (bit-exact for indices / lengths / activations, tolerance for atomically
+accumulated gradients), and against the committed golden vectors produced by the UNMODIFIED
+reference CUDA kernels (tests/golden/ref_gpu_*.npz, see tools/make_golden_gpu.py)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from scene_utils import small_scene
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _render_oracle(oracle, sc, **kw):
+    kw.setdefault("max_points_per_bin", sc["verts"].shape[0])
+    return oracle.render_reference_cpu(sc["verts"], sc["sigmas"], sc["R"], sc["T"], sc["focal"], sc["principal"],
+                                       sc["image_size"], K=sc["K"], **kw)
+
+
+@pytest.fixture(scope="module")
+def C():
+    from voge_b200 import _C
+    return _C
+
+
+@pytest.mark.parametrize("seed,aniso,views", [(0, False, 1), (1, True, 1), (2, True, 3)])
+def test_fine_forward_bit_exact(oracle, C, seed, aniso, views):
+    sc = small_scene(seed=seed, aniso=aniso, views=views)
+    o = _render_oracle(oracle, sc)
+    idx, tl, ta, td = C.ray_trace_voge_fine(o["mus"].to(DEV), o["isigmas"].to(DEV), o["rays"].to(DEV),
+                                            o["bin_points"].to(DEV), o["thr_act"], o["bin_size"], sc["K"])
+    assert (o["idx"] >= 0).sum() > 100
+    assert torch.equal(idx.cpu(), o["idx"])
+    assert torch.equal(tl.cpu(), o["len"])       # bit-exact: same rounding sequence as the reference
+    assert torch.equal(ta.cpu(), o["act"])
+    assert torch.equal(td.cpu(), o["dsd"])
+
+
+def test_fine_forward_dense_and_large_k(oracle, C):
+    sc = small_scene(seed=3, n=200, K=70, image_size=(24, 20))
+    o = _render_oracle(oracle, sc, max_points_per_bin=-1)
+    idx, tl, ta, td = C.ray_trace_voge_fine_dense(o["mus"].to(DEV), o["isigmas"].to(DEV), o["rays"].to(DEV), 200,
+                                                  o["thr_act"], o["bin_size"], sc["K"])
+    assert torch.equal(idx.cpu(), o["idx"]) and torch.equal(tl.cpu(), o["len"])
+    assert torch.equal(ta.cpu(), o["act"]) and torch.equal(td.cpu(), o["dsd"])
+
+
+def test_fine_forward_empty_and_padding(oracle, C):
+    sc = small_scene(seed=4, n=50, K=4)
+    o = _render_oracle(oracle, sc)
+    bp = torch.full_like(o["bin_points"], -1)
+    idx, tl, ta, td = C.ray_trace_voge_fine(o["mus"].to(DEV), o["isigmas"].to(DEV), o["rays"].to(DEV), bp.to(DEV),
+                                            o["thr_act"], o["bin_size"], sc["K"])
+    assert (idx == -1).all() and (tl == 1e10).all() and (ta == 1e10).all() and (td == 0).all()
+    # -1 entries interleaved anywhere in the list must be skipped (reference :187)
+    bp2 = o["bin_points"].clone()
+    M = bp2.shape[-1]
+    wide = torch.full(bp2.shape[:-1] + (2 * M + 300,), -1, dtype=torch.int32)
+    wide[..., 1:2 * M:2] = bp2
+    got = C.ray_trace_voge_fine(o["mus"].to(DEV), o["isigmas"].to(DEV), o["rays"].to(DEV), wide.to(DEV),
+                                o["thr_act"], o["bin_size"], sc["K"])
+    assert torch.equal(got[0].cpu(), o["idx"]) and torch.equal(got[1].cpu(), o["len"])
+
+
+def test_coarse_matches_oracle(oracle, C):
+    sc = small_scene(seed=5, n=700, views=2, image_size=(50, 72))
+    o = _render_oracle(oracle, sc, bin_size=10, max_points_per_bin=300)
+    ndc, radii = oracle.coarse_inputs(sc["R"], sc["T"], sc["focal"], sc["principal"], sc["image_size"],
+                                      o["mus"].view(2, -1, 3), o["isigmas"].view(2, -1, 3, 3), 0.01)
+    ndc[0, :5, 2] = -1.0      # behind the camera -> skipped
+    radii[0, 5:8] = float("nan")
+    first = torch.arange(2) * 700
+    nper = torch.full((2,), 700)
+    bp_o, bc_o = oracle.rasterize_coarse(ndc.reshape(-1, 3), radii.reshape(-1, 2), first, nper, sc["image_size"], 10, 300)
+    bp, bc = C.rasterize_points_coarse(ndc.reshape(-1, 3).to(DEV), first.to(DEV), nper.to(DEV), sc["image_size"],
+                                       radii.reshape(-1, 2).to(DEV), 10, 300, return_counts=True)
+    assert np.array_equal(bc.cpu().numpy(), bc_o)
+    assert np.array_equal(bp.cpu().numpy(), bp_o)          # deterministic ascending order
+    assert bc_o.max() > 20
+    # overflow: first M kept, error raised
+    with pytest.raises(RuntimeError):
+        C.rasterize_points_coarse(ndc.reshape(-1, 3).to(DEV), first.to(DEV), nper.to(DEV), sc["image_size"],
+                                  radii.reshape(-1, 2).to(DEV), 10, 5)
+    bp5 = C.rasterize_points_coarse(ndc.reshape(-1, 3).to(DEV), first.to(DEV), nper.to(DEV), sc["image_size"],
+                                    radii.reshape(-1, 2).to(DEV), 10, 5, check_overflow=False)
+    assert np.array_equal(bp5.cpu().numpy(), bp_o[..., :5])
+
+
+def test_fine_backward(oracle, C):
+    sc = small_scene(seed=6, views=2)
+    o = _render_oracle(oracle, sc)
+    g = torch.Generator().manual_seed(7)
+    gl, ga, gd = (torch.randn(o["idx"].shape, generator=g) for _ in range(3))
+    gr_o, gm_o, gs_o = oracle.ray_trace_fine_backward(o["mus"], o["isigmas"], o["rays"], o["idx"], gl, ga, gd)
+    gr, gm, gs = C.ray_trace_voge_fine_backward(o["mus"].to(DEV), o["isigmas"].to(DEV), o["rays"].to(DEV),
+                                                o["idx"].to(DEV), gl.to(DEV), ga.to(DEV), gd.to(DEV))
+    for got, want in ((gr, gr_o), (gm, gm_o), (gs, gs_o)):
+        want = torch.from_numpy(want)
+        scale = want.abs().max()
+        assert (got.cpu() - want).abs().max() <= 2e-5 * scale     # fp32 atomics vs fp64-accumulated oracle
+
+
+def test_aggregation_golden(C, golden_dir):
+    z = np.load(os.path.join(golden_dir, "aggregation_cpu.npz"))
+    for tag in ("k5", "k20", "k40_occ"):
+        t = {k: torch.from_numpy(z[tag + "_" + k]).to(DEV) for k in ("idx", "act", "len", "dsd", "gw")}
+        occ = float(z[tag + "_occ"])
+        w, valid = C.aggregation_forward(t["idx"], t["act"], t["len"], t["dsd"], occ)
+        want = torch.from_numpy(z[tag + "_weight"])
+        assert torch.allclose(w.cpu(), want, rtol=1e-5, atol=1e-7)
+        assert np.array_equal(valid.cpu().numpy(), z[tag + "_valid"])
+        ga, gl, gd = C.aggregation_backward(t["act"], t["len"], t["dsd"], t["gw"], occ)
+        for got, name in ((ga, "g_act"), (gl, "g_len"), (gd, "g_dsd")):
+            want = torch.from_numpy(z[tag + "_" + name])
+            assert torch.allclose(got.cpu(), want, rtol=2e-4, atol=1e-5 * float(want.abs().max())), name
+        attr = torch.from_numpy(z[tag + "_attr"]).to(DEV)
+        merged = C.merge_final_forward(attr, w, t["idx"], valid)
+        assert torch.allclose(merged.cpu(), torch.from_numpy(z[tag + "_merged"]), rtol=1e-5, atol=1e-6)
+
+
+def test_merge_background_and_backward(oracle, C):
+    g = torch.Generator().manual_seed(11)
+    R, K, N, Cc = 500, 6, 40, 3
+    idx = torch.randint(0, N, (R, K), generator=g).int()
+    nvalid = torch.randint(0, K + 1, (R,), generator=g)
+    idx[torch.arange(K)[None] >= nvalid[:, None]] = -1
+    w = torch.rand(R, K, generator=g) * 0.4
+    w[idx < 0] = 0
+    attr = torch.rand(N, Cc, generator=g)
+    for thr in (-1, 0.3):
+        wr, ar = w.clone().requires_grad_(True), attr.clone().requires_grad_(True)
+        want = oracle.to_colored_background_torch(wr, idx, nvalid, ar, (1.0, 0.5, 0.25), thr)
+        go = torch.rand(want.shape, generator=g)
+        (want * go).sum().backward()
+        bg = torch.tensor([1.0, 0.5, 0.25], device=DEV)
+        got = C.merge_final_forward(attr.to(DEV), w.to(DEV), idx.to(DEV), nvalid.to(DEV), bg, thr)
+        assert torch.allclose(got.cpu(), want.detach(), rtol=1e-5, atol=1e-6)
+        g_attr, g_w = C.merge_final_backward(attr.to(DEV), w.to(DEV), idx.to(DEV), nvalid.to(DEV), go.to(DEV), bg, thr)
+        assert torch.allclose(g_w.cpu(), wr.grad, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(g_attr.cpu(), ar.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_sample_ops(oracle, C):
+    g = torch.Generator().manual_seed(12)
+    B, H, W, K, N, Cc = 2, 9, 7, 5, 30, 4
+    idx = torch.randint(-1, N, (B, H, W, K), generator=g).int()
+    w = torch.rand(B, H, W, K, generator=g)
+    img = torch.rand(B, H, W, Cc, generator=g)
+    f_o, s_o = oracle.sample(img, w, idx, N)
+    f, s = C.sample_voge(img.to(DEV), w.to(DEV), idx.to(DEV), N)
+    assert np.allclose(f.cpu().numpy(), f_o, rtol=1e-5, atol=1e-6) and np.allclose(s.cpu().numpy(), s_o, rtol=1e-5)
+    # dense-matrix spec of Documentation.md:94-100
+    dense = torch.zeros(B * H * W, N + 1)
+    dense.scatter_add_(1, (idx.view(-1, K).long() + 1), w.view(-1, K))
+    assert np.allclose((dense[:, 1:].T @ img.view(-1, Cc)).numpy(), f.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    gf, gs = torch.rand(N, Cc, generator=g), torch.rand(N, generator=g)
+    gi_o, gw_o = oracle.sample_backward(img, w, idx, gf, gs)
+    gi, gw = C.sample_voge_backward(img.to(DEV), w.to(DEV), idx.to(DEV), gf.to(DEV), gs.to(DEV))
+    assert np.allclose(gi.cpu().numpy(), gi_o, rtol=1e-5, atol=1e-6) and np.allclose(gw.cpu().numpy(), gw_o, rtol=1e-5, atol=1e-6)
+    m = C.scatter_max(w.to(DEV), idx.to(DEV), N)
+    assert np.array_equal(m.cpu().numpy(), oracle.scatter_max(w, idx, N))
+
+
+def test_cpu_tensors_raise(C):
+    with pytest.raises(RuntimeError):
+        C.sample_voge(torch.zeros(1, 2, 2, 3), torch.zeros(1, 2, 2, 4), torch.zeros(1, 2, 2, 4, dtype=torch.int32), 5)

@@ -1,0 +1,235 @@
+"""`VoGE._C`-shaped module: the reference's pybind entry points (reference VoGE/csrc/ext.cpp:7-17)
+re-exposed with the same names, positional arguments, return orders and dtypes, implemented by
+the C-ABI library libvoge_b200.so.  Outputs are allocated here with torch (the reference's
+at::full / at::zeros) so PyTorch's caching allocator owns all memory.
+
+CPU tensors raise RuntimeError, as the reference's CUDAGuard does: there is no CPU path.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, f32c, i32c, lib, ptr, require_cuda, stream_of
+
+# set by rasterize_points_coarse: true per-bin counts of the last call (device tensor); lets
+# callers bound the candidate scan and detect overflow without re-deriving anything.
+last_bin_counts = None
+
+
+class BinOverflowError(RuntimeError):
+    pass
+
+
+def rasterize_points_coarse(points, cloud_to_packed_first_idx, num_points_per_cloud, image_size, radius,
+                            bin_size, max_points_per_bin, return_counts=False, check_overflow=True):
+    """Reference: RasterizeEllipseCoarseCuda, rasterize_coarse.cu:254-305.
+    points (P,3) f32, first_idx (B,) i64, num_per (B,) i64, image_size (H,W), radius (P,2) f32
+    -> bin_points (B,BH,BW,M) int32, -1 padded, packed indices (ascending inside each bin)."""
+    global last_bin_counts
+    require_cuda(points, cloud_to_packed_first_idx, num_points_per_cloud, radius)
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise RuntimeError("points must have dimensions (num_points, 3)")  # rasterize_coarse.cu:262-264
+    points = f32c(points)
+    radius = f32c(radius)
+    first = cloud_to_packed_first_idx.to(torch.int64).contiguous()
+    nper = num_points_per_cloud.to(torch.int64).contiguous()
+    H, W = int(image_size[0]), int(image_size[1])
+    B, P, M = int(nper.shape[0]), int(points.shape[0]), int(max_points_per_bin)
+    BH, BW = 1 + (H - 1) // bin_size, 1 + (W - 1) // bin_size
+    if BH >= 66 or BW >= 66:  # kMaxItemsPerBin, rasterize_coarse.cu:213-219
+        raise RuntimeError("In RasterizeCoarseCuda got num_bins_y: %d, num_bins_x: %d, ; that's too many!" % (BH, BW))
+    with torch.cuda.device(points.device):
+        bin_points = torch.full((B, BH, BW, M), -1, dtype=torch.int32, device=points.device)
+        counts = torch.zeros((B, BH, BW), dtype=torch.int32, device=points.device)
+        if bin_points.numel() == 0 and M != 0:
+            return (bin_points, counts) if return_counts else bin_points
+        max_per = P  # upper bound of max(num_per) without a device sync
+        n_scratch = lib().voge_rasterize_coarse_scratch_elems(B, max_per, H, W, bin_size)
+        scratch = torch.empty((max(int(n_scratch), 1),), dtype=torch.int32, device=points.device)
+        check(lib().voge_rasterize_coarse(ptr(points), ptr(radius), ptr(first), ptr(nper), B, P, max_per, H, W,
+                                          int(bin_size), M, ptr(scratch), ptr(bin_points), ptr(counts),
+                                          stream_of(points)), "rasterize_coarse")
+    last_bin_counts = counts
+    if check_overflow and M > 0:
+        worst = int(counts.max().item())
+        if worst > M:
+            raise BinOverflowError(
+                "Bin size was too small in the coarse rasterization phase: a bin holds %d Gaussians but "
+                "max_points_per_bin is %d. Increase max_point_per_bin or set it to -1." % (worst, M))
+    return (bin_points, counts) if return_counts else bin_points
+
+
+def ray_trace_voge_fine(mus, isigmas, rays, bin_points, thr_act, bin_size, K, bin_counts=None):
+    """Reference: RayTraceFineVoge, ray_trace_voge.cu:219-280.
+    -> (point_idxs i32, total_len, total_act, total_dsd), each (B,H,W,K)."""
+    require_cuda(mus, isigmas, rays, bin_points)
+    mus, isigmas, rays = f32c(mus), f32c(isigmas), f32c(rays)
+    bin_points = i32c(bin_points)
+    B, H, W = int(rays.shape[0]), int(rays.shape[1]), int(rays.shape[2])
+    BH, BW, M = int(bin_points.shape[1]), int(bin_points.shape[2]), int(bin_points.shape[3])
+    P, K = int(isigmas.shape[0]), int(K)
+    dev = mus.device
+    with torch.cuda.device(dev):
+        idx = torch.empty((B, H, W, K), dtype=torch.int32, device=dev)
+        tlen = torch.empty((B, H, W, K), dtype=torch.float32, device=dev)
+        tact = torch.empty((B, H, W, K), dtype=torch.float32, device=dev)
+        tdsd = torch.empty((B, H, W, K), dtype=torch.float32, device=dev)
+        if tlen.numel() == 0:
+            return idx, tlen, tact, tdsd
+        if bin_counts is not None:
+            bin_counts = i32c(bin_counts)
+        check(lib().voge_ray_trace_fine_counts(ptr(mus), ptr(isigmas), ptr(rays), ptr(bin_points), ptr(bin_counts),
+                                               float(thr_act), int(bin_size), B, H, W, BH, BW, M, K, P,
+                                               ptr(idx), ptr(tlen), ptr(tact), ptr(tdsd), stream_of(mus)),
+              "ray_trace_fine")
+    return idx, tlen, tact, tdsd
+
+
+def ray_trace_voge_fine_dense(mus, isigmas, rays, points_per_view, thr_act, bin_size, K):
+    """"No coarse stage" variant (reference RayTracing.py:22-26 builds an arange bin table instead):
+    all `points_per_view` Gaussians of view b (packed b*N .. b*N+N-1) are candidates of every pixel."""
+    require_cuda(mus, isigmas, rays)
+    mus, isigmas, rays = f32c(mus), f32c(isigmas), f32c(rays)
+    B, H, W = int(rays.shape[0]), int(rays.shape[1]), int(rays.shape[2])
+    P, K, N = int(isigmas.shape[0]), int(K), int(points_per_view)
+    BH, BW = 1 + (H - 1) // bin_size, 1 + (W - 1) // bin_size
+    dev = mus.device
+    with torch.cuda.device(dev):
+        idx = torch.empty((B, H, W, K), dtype=torch.int32, device=dev)
+        tlen = torch.empty((B, H, W, K), dtype=torch.float32, device=dev)
+        tact = torch.empty((B, H, W, K), dtype=torch.float32, device=dev)
+        tdsd = torch.empty((B, H, W, K), dtype=torch.float32, device=dev)
+        if tlen.numel() == 0:
+            return idx, tlen, tact, tdsd
+        check(lib().voge_ray_trace_fine_counts(ptr(mus), ptr(isigmas), ptr(rays), None, None, float(thr_act),
+                                               int(bin_size), B, H, W, BH, BW, N, K, P, ptr(idx), ptr(tlen),
+                                               ptr(tact), ptr(tdsd), stream_of(mus)), "ray_trace_fine(dense)")
+    return idx, tlen, tact, tdsd
+
+
+def ray_trace_voge_fine_backward(mus, isigmas, rays, point_idxs, grad_len, grad_act, grad_dsd, need_rays=True):
+    """Reference: RayTraceFineVogeBackward, ray_trace_voge.cu:334-379.
+    -> (grad_ray (B,H,W,3), grad_mus (P,3), grad_isg (P,3,3))."""
+    require_cuda(mus, isigmas, rays, point_idxs, grad_len, grad_act, grad_dsd)
+    mus, isigmas, rays = f32c(mus), f32c(isigmas), f32c(rays)
+    point_idxs = i32c(point_idxs)
+    grad_len, grad_act, grad_dsd = f32c(grad_len), f32c(grad_act), f32c(grad_dsd)
+    B, H, W, K = (int(s) for s in point_idxs.shape)
+    P = int(isigmas.shape[0])
+    dev = mus.device
+    with torch.cuda.device(dev):
+        g_ray = torch.zeros((B, H, W, 3), dtype=torch.float32, device=dev) if need_rays else None
+        g_mus = torch.zeros((P, 3), dtype=torch.float32, device=dev)
+        g_isg = torch.zeros((P, 3, 3), dtype=torch.float32, device=dev)
+        check(lib().voge_ray_trace_fine_backward(ptr(mus), ptr(isigmas), ptr(rays), ptr(point_idxs), ptr(grad_len),
+                                                 ptr(grad_act), ptr(grad_dsd), B, H, W, K, P, ptr(g_ray),
+                                                 ptr(g_mus), ptr(g_isg), stream_of(mus)), "ray_trace_fine_backward")
+    return g_ray, g_mus, g_isg
+
+
+def sample_voge(image, vert_weight, vert_index, num_vert):
+    """Reference: SampleVoge, sample_voge.cu:95-134. -> (vert_feature (N,C), vert_weight_sum (N,))."""
+    require_cuda(image, vert_weight, vert_index)
+    image, vert_weight, vert_index = f32c(image), f32c(vert_weight), i32c(vert_index)
+    C, K, N = int(image.shape[-1]), int(vert_index.shape[-1]), int(num_vert)
+    R = vert_index.numel() // max(K, 1)
+    dev = image.device
+    with torch.cuda.device(dev):
+        feat = torch.zeros((N, C), dtype=torch.float32, device=dev)
+        wsum = torch.zeros((N,), dtype=torch.float32, device=dev)
+        check(lib().voge_sample(ptr(image), ptr(vert_weight), ptr(vert_index), R, K, C, N, ptr(feat), ptr(wsum),
+                                stream_of(image)), "sample")
+    return feat, wsum
+
+
+def sample_voge_backward(image, vert_weight, vert_index, grad_feature, grad_weight_sum):
+    """Reference: SampleVogeBackward, sample_voge.cu:212-252. -> (grad_image, grad_vert_weight)."""
+    require_cuda(image, vert_weight, vert_index, grad_feature, grad_weight_sum)
+    image, vert_weight, vert_index = f32c(image), f32c(vert_weight), i32c(vert_index)
+    grad_feature, grad_weight_sum = f32c(grad_feature), f32c(grad_weight_sum)
+    C, K = int(image.shape[-1]), int(vert_index.shape[-1])
+    R = vert_index.numel() // max(K, 1)
+    dev = image.device
+    with torch.cuda.device(dev):
+        g_image = torch.empty_like(image)
+        g_w = torch.empty_like(vert_weight)
+        check(lib().voge_sample_backward(ptr(image), ptr(vert_weight), ptr(vert_index), ptr(grad_feature),
+                                         ptr(grad_weight_sum), R, K, C, ptr(g_image), ptr(g_w), stream_of(image)),
+              "sample_backward")
+    return g_image, g_w
+
+
+def scatter_max(vert_weight, vert_index, num_vert):
+    """Reference: ScatterMax, sample_voge.cu:137-170. -> vert_weight_max (N,)."""
+    require_cuda(vert_weight, vert_index)
+    vert_weight, vert_index = f32c(vert_weight), i32c(vert_index)
+    K, N = int(vert_index.shape[-1]), int(num_vert)
+    R = vert_index.numel() // max(K, 1)
+    dev = vert_weight.device
+    with torch.cuda.device(dev):
+        wmax = torch.zeros((N,), dtype=torch.float32, device=dev)
+        check(lib().voge_scatter_max(ptr(vert_weight), ptr(vert_index), R, K, N, ptr(wmax), stream_of(vert_weight)),
+              "scatter_max")
+    return wmax
+
+
+# ---- fused blend ops (PyTorch-only in the reference, Aggregation.py) ---------------------------
+def aggregation_forward(sel_idx, sel_act, sel_len, sel_dsd, absorptivity):
+    require_cuda(sel_idx, sel_act, sel_len, sel_dsd)
+    sel_idx, sel_act, sel_len, sel_dsd = i32c(sel_idx), f32c(sel_act), f32c(sel_len), f32c(sel_dsd)
+    K = int(sel_idx.shape[-1])
+    R = sel_idx.numel() // max(K, 1)
+    dev = sel_act.device
+    with torch.cuda.device(dev):
+        weight = torch.empty_like(sel_act)
+        valid = torch.empty(sel_idx.shape[:-1], dtype=torch.int64, device=dev)
+        check(lib().voge_aggregation(ptr(sel_idx), ptr(sel_act), ptr(sel_len), ptr(sel_dsd), float(absorptivity),
+                                     R, K, ptr(weight), ptr(valid), stream_of(sel_act)), "aggregation")
+    return weight, valid
+
+
+def aggregation_backward(sel_act, sel_len, sel_dsd, grad_weight, absorptivity):
+    sel_act, sel_len, sel_dsd, grad_weight = f32c(sel_act), f32c(sel_len), f32c(sel_dsd), f32c(grad_weight)
+    K = int(sel_act.shape[-1])
+    R = sel_act.numel() // max(K, 1)
+    dev = sel_act.device
+    with torch.cuda.device(dev):
+        g_act = torch.empty_like(sel_act)
+        g_len = torch.empty_like(sel_act)
+        g_dsd = torch.empty_like(sel_act)
+        check(lib().voge_aggregation_backward(ptr(sel_act), ptr(sel_len), ptr(sel_dsd), ptr(grad_weight),
+                                              float(absorptivity), R, K, ptr(g_act), ptr(g_len), ptr(g_dsd),
+                                              stream_of(sel_act)), "aggregation_backward")
+    return g_act, g_len, g_dsd
+
+
+def merge_final_forward(attr, weight, idx, valid_num, background=None, mask_thr=-1.0, idx_mod=0):
+    require_cuda(attr, weight, idx, valid_num)
+    attr, weight, idx = f32c(attr), f32c(weight), i32c(idx)
+    valid_num = valid_num.to(torch.int64).contiguous()
+    K, C = int(idx.shape[-1]), int(attr.shape[-1])
+    R = idx.numel() // max(K, 1)
+    dev = attr.device
+    with torch.cuda.device(dev):
+        out = torch.empty(tuple(idx.shape[:-1]) + (C,), dtype=torch.float32, device=dev)
+        bg = f32c(background) if background is not None else None
+        check(lib().voge_merge_final(ptr(attr), ptr(weight), ptr(idx), ptr(valid_num), ptr(bg), float(mask_thr),
+                                     R, K, C, int(idx_mod), int(attr.shape[0]), ptr(out), stream_of(attr)), "merge_final")
+    return out
+
+
+def merge_final_backward(attr, weight, idx, valid_num, grad_out, background=None, mask_thr=-1.0, idx_mod=0,
+                         need_attr=True, need_weight=True):
+    attr, weight, idx, grad_out = f32c(attr), f32c(weight), i32c(idx), f32c(grad_out)
+    valid_num = valid_num.to(torch.int64).contiguous()
+    K, C = int(idx.shape[-1]), int(attr.shape[-1])
+    R = idx.numel() // max(K, 1)
+    dev = attr.device
+    with torch.cuda.device(dev):
+        g_attr = torch.zeros_like(attr) if need_attr else None
+        g_w = torch.empty_like(weight) if need_weight else None
+        bg = f32c(background) if background is not None else None
+        check(lib().voge_merge_final_backward(ptr(attr), ptr(weight), ptr(idx), ptr(valid_num), ptr(bg),
+                                              float(mask_thr), None, ptr(grad_out), R, K, C, int(idx_mod),
+                                              int(attr.shape[0]), ptr(g_attr), ptr(g_w), stream_of(attr)),
+              "merge_final_backward")
+    return g_attr, g_w

@@ -1,0 +1,92 @@
+"""ctypes binding of libvoge_b200.so (the C ABI declared in include/voge_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+The library is located in-tree (voge_b200/libvoge_b200.so, built by voge_b200/build.py).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvoge_b200.so")
+
+_c_float_p = ctypes.c_void_p
+_c_int_p = ctypes.c_void_p
+_I, _L, _F, _P = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); must list EVERY symbol of include/voge_b200.h (tests check this)
+SIGNATURES = {
+    "voge_version": (_I, []),
+    "voge_error_string": (ctypes.c_char_p, [_I]),
+    "voge_device_sm_count": (_I, [_P]),
+    "voge_rasterize_coarse_scratch_elems": (_L, [_I, _I, _I, _I, _I]),
+    "voge_rasterize_coarse": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "voge_ray_trace_fine": (_I, [_P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "voge_ray_trace_fine_counts": (_I, [_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "voge_ray_trace_fine_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "voge_aggregation": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _P, _P]),
+    "voge_aggregation_backward": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _P, _P, _P]),
+    "voge_merge_final": (_I, [_P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _I, _P, _P]),
+    "voge_merge_final_backward": (_I, [_P, _P, _P, _P, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P, _P, _P]),
+    "voge_sample": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P]),
+    "voge_sample_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P]),
+    "voge_scatter_max": (_I, [_P, _P, _L, _I, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises RuntimeError if the .so is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "voge_b200: %s not found. Build it with `python -m voge_b200.build` "
+                "(there is no CPU or PyTorch fallback)." % LIB_PATH)
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().voge_error_string(int(code))
+        raise RuntimeError("voge_b200.%s failed: CUDA error %d (%s)" % (what, code, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_of(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    """The reference raises RuntimeError for CPU tensors (CUDAGuard); so do we."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("voge_b200: expected a CUDA tensor (there is no CPU path), got device %s" % t.device)
+
+
+def f32c(t):
+    require_cuda(t)
+    if t.dtype != torch.float32:
+        raise RuntimeError("voge_b200: expected float32, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def i32c(t):
+    require_cuda(t)
+    if t.dtype != torch.int32:
+        raise RuntimeError("voge_b200: expected int32, got %s" % t.dtype)
+    return t.contiguous()

@@ -1,0 +1,303 @@
+// blend.cu -- occlusion-aware blending weights (aggregation) and the gather-blend
+// (merge_final + background composite), forward and analytic backward.
+//
+// Reference: pure PyTorch, VoGE/Aggregation.py:30-107 (get_cross_activation, assign2weight,
+// aggregation) materialising (R,K,K) tensors in ~15 elementwise kernels, :111-141 (merge_final)
+// and VoGE/Renderer.py:153-176 (interpolate_attr / get_silhouette / to_colored_background).
+// Here the K x K term lives in shared memory / registers of the thread that owns the ray.
+#include "../../include/voge_b200.h"
+#include "common.cuh"
+
+namespace voge {
+
+constexpr float kInvSqrtPi = 0.5641895835477563f;
+constexpr float kInvExpMinusHalf = 1.6487212707001282f;  // 1 / exp(-0.5), Aggregation.py:79
+constexpr float kErfSat = 4.0f;                          // |c| >= 4  =>  erff(c) == +-1 in fp32
+
+// (erf(c) + 1) / 2 with the saturated branches short-cut
+__device__ __forceinline__ float phi(float c) {
+    if (c >= kErfSat) return 1.f;
+    if (c <= -kErfSat) return 0.f;
+    return (erff(c) + 1.f) * 0.5f;
+}
+
+// ---- forward ---------------------------------------------------------------------------------
+// one thread per ray; per-thread arrays [k][thread] in shared memory: len, s=sqrt(dsd+1e-10), E=exp(-act)
+template <int NT>
+__global__ void __launch_bounds__(NT) aggregation_fwd_kernel(const int32_t* __restrict__ idx,
+                                                             const float* __restrict__ act,
+                                                             const float* __restrict__ len,
+                                                             const float* __restrict__ dsd, float omega,
+                                                             int64_t R, int K, float* __restrict__ weight,
+                                                             int64_t* __restrict__ valid_num) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_len = sm;
+    float* s_s = sm + (size_t)K * NT;
+    float* s_E = sm + (size_t)2 * K * NT;
+    const int tid = threadIdx.x;
+    const int64_t r = (int64_t)blockIdx.x * NT + tid;
+    if (r >= R) return;
+    int nvalid = 0;
+    for (int k = 0; k < K; ++k) {
+        const int64_t o = r * K + k;
+        s_len[k * NT + tid] = len[o];
+        s_s[k * NT + tid] = sqrtf(dsd[o] + 1e-10f);
+        s_E[k * NT + tid] = expf(-act[o]);
+        if (idx != nullptr) nvalid += (idx[o] >= 0);
+    }
+    if (valid_num != nullptr) valid_num[r] = nvalid;
+    for (int m = 0; m < K; ++m) {
+        const float Em = s_E[m * NT + tid];
+        float w = 0.f;
+        if (Em != 0.f) {
+            const float lm = s_len[m * NT + tid];
+            float D = 0.f;
+            for (int k = 0; k < K; ++k) {
+                const float Ek = s_E[k * NT + tid];
+                if (Ek == 0.f) continue;
+                const float c = (lm - s_len[k * NT + tid]) * s_s[k * NT + tid];
+                D += Ek * phi(c);
+            }
+            w = expf(-(D * omega)) * Em * kInvExpMinusHalf;
+        }
+        weight[r * K + m] = w;
+    }
+}
+
+// ---- backward --------------------------------------------------------------------------------
+// w_m = e^{.5} exp(-omega D_m) E_m,  D_m = sum_k E_k Phi(c_mk),  c_mk = (len_m - len_k) s_k
+template <int NT>
+__global__ void __launch_bounds__(NT) aggregation_bwd_kernel(const float* __restrict__ act,
+                                                             const float* __restrict__ len,
+                                                             const float* __restrict__ dsd,
+                                                             const float* __restrict__ g_w, float omega,
+                                                             int64_t R, int K, float* __restrict__ g_act,
+                                                             float* __restrict__ g_len,
+                                                             float* __restrict__ g_dsd) {
+    extern __shared__ __align__(16) float sm[];
+    const size_t A = (size_t)K * NT;
+    float* s_len = sm;
+    float* s_s = sm + A;
+    float* s_E = sm + 2 * A;
+    float* s_gl = sm + 3 * A;
+    float* s_gd = sm + 4 * A;
+    float* s_gE = sm + 5 * A;
+    const int tid = threadIdx.x;
+    const int64_t r = (int64_t)blockIdx.x * NT + tid;
+    if (r >= R) return;
+    for (int k = 0; k < K; ++k) {
+        const int64_t o = r * K + k;
+        s_len[k * NT + tid] = len[o];
+        s_s[k * NT + tid] = sqrtf(dsd[o] + 1e-10f);
+        s_E[k * NT + tid] = expf(-act[o]);
+        s_gl[k * NT + tid] = 0.f;
+        s_gd[k * NT + tid] = 0.f;
+        s_gE[k * NT + tid] = 0.f;
+    }
+    for (int m = 0; m < K; ++m) {
+        const float Em = s_E[m * NT + tid];
+        if (Em == 0.f) continue;
+        const float lm = s_len[m * NT + tid];
+        float D = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float Ek = s_E[k * NT + tid];
+            if (Ek == 0.f) continue;
+            D += Ek * phi((lm - s_len[k * NT + tid]) * s_s[k * NT + tid]);
+        }
+        const float w = expf(-(D * omega)) * Em * kInvExpMinusHalf;
+        const float gw = g_w[r * K + m];
+        const float gD = -omega * w * gw;
+        // direct path d w_m / d act_m = -w_m  (through the trailing exp(-act_m))
+        s_gE[m * NT + tid] += w * gw / Em;   // expressed as a gradient on E_m: dw/dE_m = w/E_m
+        if (gD == 0.f) continue;
+        float glm = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float Ek = s_E[k * NT + tid];
+            if (Ek == 0.f) continue;
+            const float sk = s_s[k * NT + tid];
+            const float dl = lm - s_len[k * NT + tid];
+            const float c = dl * sk;
+            s_gE[k * NT + tid] += gD * phi(c);
+            if (fabsf(c) < 10.f) {  // exp(-c^2) underflows to 0 beyond |c| ~ 9.3
+                const float gc = gD * Ek * expf(-c * c) * kInvSqrtPi;
+                glm += gc * sk;
+                s_gl[k * NT + tid] -= gc * sk;
+                s_gd[k * NT + tid] += gc * dl / (2.f * sk);
+            }
+        }
+        s_gl[m * NT + tid] += glm;
+    }
+    for (int k = 0; k < K; ++k) {
+        const int64_t o = r * K + k;
+        g_act[o] = -s_E[k * NT + tid] * s_gE[k * NT + tid];
+        g_len[o] = s_gl[k * NT + tid];
+        g_dsd[o] = s_gd[k * NT + tid];
+    }
+}
+
+// ---- gather-blend ----------------------------------------------------------------------------
+// one thread per (ray, channel); channel fastest => coalesced attribute-row reads and output writes
+__global__ void __launch_bounds__(256) merge_fwd_kernel(const float* __restrict__ attr,
+                                                        const float* __restrict__ weight,
+                                                        const int32_t* __restrict__ idx,
+                                                        const int64_t* __restrict__ valid_num,
+                                                        const float* __restrict__ background, float mask_thr,
+                                                        int64_t R, int K, int C, int idx_mod, int n_attr,
+                                                        float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R * C) return;
+    const int64_t r = t / C;
+    const int c = (int)(t - r * C);
+    const int nv = valid_num != nullptr ? (int)min((int64_t)K, valid_num[r]) : K;
+    float acc = 0.f, wsum = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float w = weight[r * K + k];
+        wsum += w;
+        if (k < nv) {
+            int g = idx[r * K + k];
+            if (g < 0) g = 0;  // Aggregation.py:131  vert_assign += (vert_assign < 0)
+            if (idx_mod > 0) g %= idx_mod;
+            if (g < n_attr) acc = fmaf(w, __ldg(attr + (int64_t)g * C + c), acc);
+        }
+    }
+    if (background != nullptr) {
+        const float sil = fminf(wsum, 1.f);                                  // Renderer.py:157-159
+        const float mask = mask_thr > 0.f ? (sil > mask_thr ? 1.f : 0.f) : sil;  // :167-168
+        acc = fminf(acc + (1.f - mask) * background[c], 1.f);                // :171
+    }
+    out[t] = acc;
+}
+
+// torch.minimum-style subgradient of min(x, 1): 1 below, 1/2 at the tie, 0 above
+__device__ __forceinline__ float min1_grad(float x) { return x < 1.f ? 1.f : (x == 1.f ? 0.5f : 0.f); }
+
+constexpr int kMaxBgChannels = 32;  // background composite backward supports C <= 32
+
+// one thread per ray
+__global__ void __launch_bounds__(256) merge_bwd_kernel(const float* __restrict__ attr,
+                                                        const float* __restrict__ weight,
+                                                        const int32_t* __restrict__ idx,
+                                                        const int64_t* __restrict__ valid_num,
+                                                        const float* __restrict__ background, float mask_thr,
+                                                        const float* __restrict__ g_out, int64_t R, int K,
+                                                        int C, int idx_mod, int n_attr, float* __restrict__ g_attr,
+                                                        float* __restrict__ g_weight) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int nv = valid_num != nullptr ? (int)min((int64_t)K, valid_num[r]) : K;
+    const bool bg = background != nullptr;
+    float gol[kMaxBgChannels];
+    float g_sumw = 0.f;
+    if (bg) {
+        // upstream gradient after the two clamps of Renderer.py:157-171 (needs the un-clamped colour)
+        float wsum = 0.f;
+        for (int k = 0; k < K; ++k) wsum += weight[r * K + k];
+        const float sil = fminf(wsum, 1.f);
+        const float mask = mask_thr > 0.f ? (sil > mask_thr ? 1.f : 0.f) : sil;
+        for (int c = 0; c < C; ++c) {
+            float acc = 0.f;
+            for (int k = 0; k < nv; ++k) {
+                int g = idx[r * K + k];
+                if (g < 0) g = 0;
+                if (idx_mod > 0) g %= idx_mod;
+                if (g < n_attr) acc = fmaf(weight[r * K + k], __ldg(attr + (int64_t)g * C + c), acc);
+            }
+            const float go = g_out[r * C + c] * min1_grad(acc + (1.f - mask) * background[c]);
+            gol[c] = go;
+            if (!(mask_thr > 0.f)) g_sumw -= go * background[c];
+        }
+        g_sumw *= min1_grad(wsum);
+    }
+    for (int k = 0; k < K; ++k) {
+        float gw = g_sumw;
+        if (k < nv) {
+            int g = idx[r * K + k];
+            if (g < 0) g = 0;
+            if (idx_mod > 0) g %= idx_mod;
+            const float w = weight[r * K + k];
+            for (int c = 0; c < C && g < n_attr; ++c) {
+                const float go = bg ? gol[c] : g_out[r * C + c];
+                gw = fmaf(go, __ldg(attr + (int64_t)g * C + c), gw);
+                if (g_attr != nullptr && w != 0.f && go != 0.f) atomicAdd(g_attr + (int64_t)g * C + c, w * go);
+            }
+        }
+        if (g_weight != nullptr) g_weight[r * K + k] = gw;
+    }
+}
+
+template <int NT>
+static int launch_agg_fwd(const int32_t* idx, const float* act, const float* len, const float* dsd,
+                          float omega, int64_t R, int K, float* weight, int64_t* valid_num,
+                          cudaStream_t s) {
+    const size_t smem = (size_t)3 * K * NT * 4;
+    if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+    VOGE_CUDA_TRY(cudaFuncSetAttribute(aggregation_fwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    aggregation_fwd_kernel<NT><<<(unsigned)((R + NT - 1) / NT), NT, smem, s>>>(idx, act, len, dsd, omega, R, K, weight, valid_num);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int NT>
+static int launch_agg_bwd(const float* act, const float* len, const float* dsd, const float* g_w,
+                          float omega, int64_t R, int K, float* g_act, float* g_len, float* g_dsd,
+                          cudaStream_t s) {
+    const size_t smem = (size_t)6 * K * NT * 4;
+    if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+    VOGE_CUDA_TRY(cudaFuncSetAttribute(aggregation_bwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    aggregation_bwd_kernel<NT><<<(unsigned)((R + NT - 1) / NT), NT, smem, s>>>(act, len, dsd, g_w, omega, R, K, g_act, g_len, g_dsd);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace voge
+
+extern "C" int voge_aggregation(const int32_t* idx, const float* act, const float* len, const float* dsd,
+                                float absorptivity, int64_t R, int K, float* weight, int64_t* valid_num,
+                                voge_stream_t stream) {
+    using namespace voge;
+    if (R <= 0 || K <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (K <= 48) return launch_agg_fwd<128>(idx, act, len, dsd, absorptivity, R, K, weight, valid_num, s);
+    if (K <= 200) return launch_agg_fwd<64>(idx, act, len, dsd, absorptivity, R, K, weight, valid_num, s);
+    return launch_agg_fwd<32>(idx, act, len, dsd, absorptivity, R, K, weight, valid_num, s);
+}
+
+extern "C" int voge_aggregation_backward(const float* act, const float* len, const float* dsd,
+                                         const float* grad_weight, float absorptivity, int64_t R, int K,
+                                         float* grad_act, float* grad_len, float* grad_dsd,
+                                         voge_stream_t stream) {
+    using namespace voge;
+    if (R <= 0 || K <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (K <= 32) return launch_agg_bwd<128>(act, len, dsd, grad_weight, absorptivity, R, K, grad_act, grad_len, grad_dsd, s);
+    if (K <= 110) return launch_agg_bwd<64>(act, len, dsd, grad_weight, absorptivity, R, K, grad_act, grad_len, grad_dsd, s);
+    return launch_agg_bwd<32>(act, len, dsd, grad_weight, absorptivity, R, K, grad_act, grad_len, grad_dsd, s);
+}
+
+extern "C" int voge_merge_final(const float* attr, const float* weight, const int32_t* idx,
+                                const int64_t* valid_num, const float* background, float mask_thr,
+                                int64_t R, int K, int C, int idx_mod, int n_attr, float* out,
+                                voge_stream_t stream) {
+    using namespace voge;
+    if (R <= 0 || C <= 0) return 0;
+    const int64_t total = R * C;
+    merge_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        attr, weight, idx, valid_num, background, mask_thr, R, K, C, idx_mod, n_attr, out);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int voge_merge_final_backward(const float* attr, const float* weight, const int32_t* idx,
+                                         const int64_t* valid_num, const float* background,
+                                         float mask_thr, const float* out, const float* grad_out,
+                                         int64_t R, int K, int C, int idx_mod, int n_attr, float* grad_attr,
+                                         float* grad_weight, voge_stream_t stream) {
+    using namespace voge;
+    (void)out;
+    if (R <= 0 || C <= 0) return 0;
+    if (background != nullptr && C > kMaxBgChannels) return (int)cudaErrorInvalidValue;
+    merge_bwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        attr, weight, idx, valid_num, background, mask_thr, grad_out, R, K, C, idx_mod, n_attr, grad_attr, grad_weight);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}

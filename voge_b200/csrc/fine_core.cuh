@@ -1,0 +1,139 @@
+// fine_core.cuh -- the per-pixel ray-tracing core shared by the API-compatible fine kernel
+// (bin_points candidate lists) and the fused renderer kernel (per-tile CSR lists).
+//
+// Algorithm per CTA (= a set of NT pixels that share one candidate list):
+//   1. candidates are staged through shared memory in chunks of CH: one thread per candidate
+//      loads (mu, S) and derives 10 floats of "filter data" (q = S^T mu, symmetric part of S,
+//      u' = msm - thr - margin);
+//   2. every pixel thread runs the FILTER over the chunk: ksk~ = d^T S d (6 FMA on per-pixel
+//      monomials), msk~ = q.d (3 FMA), f = u'*ksk~ - msk~^2; "f >= 0" proves
+//      act >= thr + margin and rejects the pair (this is the hot loop: broadcast LDS.128 + FFMA);
+//   3. survivors are queued per thread and REFINED with the bit-faithful reference arithmetic
+//      (exact_pair, common.cuh) from the original (mu, S); only the exact act < thr_act and the
+//      exact len decide, so results are bit-identical to the reference kernel
+//      (ray_trace_voge.cu:188-213) no matter how loose the filter is;
+//   4. top-K smallest (len, idx) kept in per-thread sorted lists in shared memory
+//      ([k][thread] layout, conflict-free).  Lexicographic (len, idx) order equals the
+//      reference's "strict <, earlier candidate wins" rule (:197,:203) for ascending candidate
+//      lists and makes the result independent of candidate order.
+#pragma once
+#include "common.cuh"
+
+namespace voge {
+
+constexpr int kStageFloats = 12;  // floats of filter data per staged candidate (3 x float4)
+constexpr int kQueueCap = 8;      // per-thread survivor queue depth
+
+// Filter data for one candidate, computed by the staging thread.
+//   v0 = (q0, q1, q2, u')   v1 = (S00, S11, S22, S01+S10)   v2 = (S02+S20, S12+S21, idx, 0)
+__device__ __forceinline__ void stage_candidate(float* __restrict__ dst, int g, const float* mu,
+                                                const float* S, float thr_act) {
+    float4 v0, v1, v2;
+    const float m0 = mu[0], m1 = mu[1], m2 = mu[2];
+    const float q0 = m0 * S[0] + m1 * S[3] + m2 * S[6];
+    const float q1 = m0 * S[1] + m1 * S[4] + m2 * S[7];
+    const float q2 = m0 * S[2] + m1 * S[5] + m2 * S[8];
+    const float msm = q0 * m0 + q1 * m1 + q2 * m2;
+    const float a = S[0], b = S[4], c = S[8];
+    const float e01 = S[1] + S[3], e02 = S[2] + S[6], e12 = S[5] + S[7];
+    const float s01 = 0.5f * e01, s02 = 0.5f * e02, s12 = 0.5f * e12;
+    const float minor2 = a * b - s01 * s01;
+    const float det = a * (b * c - s12 * s12) - s01 * (s01 * c - s12 * s02) + s02 * (s01 * s12 - b * s02);
+    const float sabs = fabsf(S[0]) + fabsf(S[1]) + fabsf(S[2]) + fabsf(S[3]) + fabsf(S[4]) +
+                       fabsf(S[5]) + fabsf(S[6]) + fabsf(S[7]) + fabsf(S[8]);
+    const float tr = a + b + c;
+    // kappa >= sum|S_ij| / lambda_min(sym S):  lambda_min >= det / (tr/2)^2
+    const float kappa = sabs * (0.25f * tr * tr) / det;
+    // |act_ref - act_filter| <= 2^-17 * kappa * msm (DESIGN.md "filter margin"); factor 2 slack
+    const float margin = 1.52587890625e-5f * kappa * (fabsf(msm) + fabsf(thr_act)) + 1e-30f;
+    const float u = msm - thr_act - margin;
+    const bool pd = (a > 0.f) && (minor2 > 0.f) && (det > 0.f) && (fabsf(u) < 3.0e38f) &&
+                    (fabsf(q0) + fabsf(q1) + fabsf(q2) < 3.0e38f);
+    if (pd) {
+        v0 = make_float4(q0, q1, q2, u);
+        v1 = make_float4(a, b, c, e01);
+        v2 = make_float4(e02, e12, __int_as_float(g), 0.f);
+    } else {
+        // not provably safe to filter: ksk~ = |d|^2 > 0 and u' = -inf => never rejected
+        v0 = make_float4(0.f, 0.f, 0.f, -INFINITY);
+        v1 = make_float4(1.f, 1.f, 1.f, 0.f);
+        v2 = make_float4(0.f, 0.f, __int_as_float(g), 0.f);
+    }
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    d4[0] = v0; d4[1] = v1; d4[2] = v2;
+}
+
+__device__ __forceinline__ void stage_invalid(float* __restrict__ dst) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    d4[0] = make_float4(0.f, 0.f, 0.f, INFINITY);   // u' = +inf => always rejected
+    d4[1] = make_float4(1.f, 1.f, 1.f, 0.f);
+    d4[2] = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
+}
+
+// Per-thread sorted top-K list living in shared memory with [k][thread] layout.
+template <int NT>
+struct TopK {
+    float* s_len;  // [K][NT]
+    int* s_idx;    // [K][NT]
+    int K, tid, cnt;
+    float kth_len;
+    int kth_idx;
+
+    __device__ __forceinline__ void init(float* lens, int* idxs, int K_, int tid_) {
+        s_len = lens; s_idx = idxs; K = K_; tid = tid_; cnt = 0;
+        kth_len = kEmptyLen; kth_idx = 0x7fffffff;
+    }
+    // quick reject against the current K-th entry (exact semantics)
+    __device__ __forceinline__ bool admits(float len, int g) const {
+        return (len < kth_len) || (cnt == K && len == kth_len && g < kth_idx);
+    }
+    __device__ __forceinline__ void insert(float len, int g) {
+        if (!admits(len, g)) return;   // also rejects NaN and len >= 1e10 (reference :197)
+        int pos;
+        if (cnt == K) pos = K - 1; else pos = cnt++;
+        while (pos > 0) {
+            const float pl = s_len[(pos - 1) * NT + tid];
+            const int pi = s_idx[(pos - 1) * NT + tid];
+            if (pl < len || (pl == len && pi < g)) break;
+            s_len[pos * NT + tid] = pl;
+            s_idx[pos * NT + tid] = pi;
+            --pos;
+        }
+        s_len[pos * NT + tid] = len;
+        s_idx[pos * NT + tid] = g;
+        if (cnt == K) {
+            kth_len = s_len[(K - 1) * NT + tid];
+            kth_idx = s_idx[(K - 1) * NT + tid];
+        }
+    }
+};
+
+// Per-pixel state of the filter.
+struct RayMono {
+    float d0, d1, d2;
+    float dxx, dyy, dzz, dxy, dxz, dyz;
+    __device__ __forceinline__ void set(float x, float y, float z) {
+        d0 = x; d1 = y; d2 = z;
+        dxx = x * x; dyy = y * y; dzz = z * z; dxy = x * y; dxz = x * z; dyz = y * z;
+    }
+};
+
+// true  => pair may satisfy act < thr_act and must be refined; false => provably rejected.
+__device__ __forceinline__ bool filter_pass(const float* __restrict__ st, const RayMono& r) {
+    const float4 v0 = *reinterpret_cast<const float4*>(st);
+    const float4 v1 = *reinterpret_cast<const float4*>(st + 4);
+    const float2 v2 = *reinterpret_cast<const float2*>(st + 8);
+    float ksk = v1.x * r.dxx;
+    ksk = fmaf(v1.y, r.dyy, ksk);
+    ksk = fmaf(v1.z, r.dzz, ksk);
+    ksk = fmaf(v1.w, r.dxy, ksk);
+    ksk = fmaf(v2.x, r.dxz, ksk);
+    ksk = fmaf(v2.y, r.dyz, ksk);
+    float msk = v0.x * r.d0;
+    msk = fmaf(v0.y, r.d1, msk);
+    msk = fmaf(v0.z, r.d2, msk);
+    const float f = fmaf(v0.w, ksk, -msk * msk);
+    return !(f >= 0.f);
+}
+
+}  // namespace voge
