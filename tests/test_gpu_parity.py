@@ -68,16 +68,16 @@ def test_fine_forward_empty_and_padding(oracle, C):
 
 def test_coarse_matches_oracle(oracle, C):
     sc = small_scene(seed=5, n=700, views=2, image_size=(50, 72))
-    o = _render_oracle(oracle, sc, bin_size=10, max_points_per_bin=300)
+    o = _render_oracle(oracle, sc, bin_size=10, max_points_per_bin=700)
     ndc, radii = oracle.coarse_inputs(sc["R"], sc["T"], sc["focal"], sc["principal"], sc["image_size"],
                                       o["mus"].view(2, -1, 3), o["isigmas"].view(2, -1, 3, 3), 0.01)
     ndc[0, :5, 2] = -1.0      # behind the camera -> skipped
     radii[0, 5:8] = float("nan")
     first = torch.arange(2) * 700
     nper = torch.full((2,), 700)
-    bp_o, bc_o = oracle.rasterize_coarse(ndc.reshape(-1, 3), radii.reshape(-1, 2), first, nper, sc["image_size"], 10, 300)
+    bp_o, bc_o = oracle.rasterize_coarse(ndc.reshape(-1, 3), radii.reshape(-1, 2), first, nper, sc["image_size"], 10, 700)
     bp, bc = C.rasterize_points_coarse(ndc.reshape(-1, 3).to(DEV), first.to(DEV), nper.to(DEV), sc["image_size"],
-                                       radii.reshape(-1, 2).to(DEV), 10, 300, return_counts=True)
+                                       radii.reshape(-1, 2).to(DEV), 10, 700, return_counts=True)
     assert np.array_equal(bc.cpu().numpy(), bc_o)
     assert np.array_equal(bp.cpu().numpy(), bp_o)          # deterministic ascending order
     assert bc_o.max() > 20
@@ -168,3 +168,28 @@ def test_sample_ops(oracle, C):
 def test_cpu_tensors_raise(C):
     with pytest.raises(RuntimeError):
         C.sample_voge(torch.zeros(1, 2, 2, 3), torch.zeros(1, 2, 2, 4), torch.zeros(1, 2, 2, 4, dtype=torch.int32), 5)
+
+
+def test_against_reference_gpu_golden(C, golden_dir):
+    """libvoge_b200 vs outputs of the UNMODIFIED reference CUDA kernels (tools/make_golden_gpu.py)."""
+    z = np.load(os.path.join(golden_dir, "ref_gpu_golden.npz"))
+    for tag in ("iso", "aniso", "multi"):
+        B, H, W, K, bin_size, n = (int(v) for v in z[tag + "_meta"])
+        t = lambda k: torch.from_numpy(z["%s_%s" % (tag, k)]).to(DEV)
+        first = (torch.arange(B) * n).to(DEV)
+        nper = torch.full((B,), n, dtype=torch.long, device=DEV)
+        bp = C.rasterize_points_coarse(t("ndc"), first, nper, (H, W), t("radii"), bin_size, n)
+        assert torch.equal(bp, t("coarse_ref_sorted"))
+        idx, tl, ta, td = C.ray_trace_voge_fine(t("mus"), t("isigmas"), t("rays"), t("bin_points"),
+                                                float(z[tag + "_thr_act"]), bin_size, K)
+        assert torch.equal(idx, t("idx")) and torch.equal(tl, t("len"))
+        assert torch.equal(ta, t("act")) and torch.equal(td, t("dsd"))
+        gr, gm, gs = C.ray_trace_voge_fine_backward(t("mus"), t("isigmas"), t("rays"), t("idx"), t("gl"), t("ga"), t("gd"))
+        for got, name in ((gr, "grad_rays"), (gm, "grad_mus"), (gs, "grad_isg")):
+            want = t(name)
+            assert (got - want).abs().max() <= 2e-5 * want.abs().max(), name
+        feat, wsum = C.sample_voge(t("img"), t("w"), t("idx"), B * n)
+        assert torch.allclose(feat, t("feat"), rtol=1e-5, atol=1e-6) and torch.allclose(wsum, t("wsum"), rtol=1e-5, atol=1e-6)
+        gi, gw = C.sample_voge_backward(t("img"), t("w"), t("idx"), t("gf"), t("gs"))
+        assert torch.allclose(gi, t("g_image"), rtol=1e-5, atol=1e-6) and torch.allclose(gw, t("g_weight"), rtol=1e-5, atol=1e-6)
+        assert torch.equal(C.scatter_max(t("w"), t("idx"), B * n), t("wmax"))
