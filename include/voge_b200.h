@@ -136,6 +136,44 @@ int voge_sample_backward(const float* image, const float* weight, const int32_t*
 int voge_scatter_max(const float* weight, const int32_t* idx, int64_t R, int K,
                      int num_vert, float* wmax, voge_stream_t stream);
 
+/* ---- fused renderer path (GaussianRenderer.forward, reference VoGE/Renderer.py:102-150) ------
+ * Same results as rasterize_coarse -> ray_trace_voge_fine -> aggregation on the renderer's own
+ * call pattern, without the per-view (B,N,.) copies, the (B,BH,BW,M) bin table or the (R,K,K)
+ * blend tensors.  verts (N,3); sigmas compact: sigma_kind 1 = (N,), 3 = (N,3), 9 = (N,3,3)
+ * (inverse covariances, S = 2*sigma, Renderer.py:137); cameras as R (B,3,3) row-vector
+ * convention, T (B,3), focal (B,2), principal (B,2) in pixels; origins (B,3) = ray origins;
+ * rays (B,H,W,3) unit directions.
+ *
+ * voge_bin_count: per (view, Gaussian) tile rectangle = [reference coarse-bin test of
+ *   RayTracing.py:33-57 + rasterize_coarse.cu:20-42,:116-130 at `bin_size` px, if use_ref_bins]
+ *   AND [conservative projected-ellipsoid bound]; tiles are `tile` x `tile` px (tile <= 16, divides
+ *   bin_size).  rects (B,N,2) uint32 out; tile_counts (B,TY,TX) int32 must be ZEROED by the caller.
+ * voge_bin_fill: scatters Gaussian indices into tile_list using tile_offsets (B*TY*TX+1, int64,
+ *   exclusive scan of tile_counts); cursor (B*TY*TX) int32 must be ZEROED by the caller.
+ * voge_render_forward: fragments.  out_idx (B,H,W,K) packed b*N+n / -1, out_weight, out_len
+ *   (1e10 padded), out_valid (B,H,W) int64; out_act/out_dsd optional (NULL to skip);
+ *   stats optional 2 x uint64 (pairs filtered, pairs refined), must be zeroed by the caller.
+ * voge_render_backward: d(len,act,dsd) (B,H,W,K) -> grad_verts (N,3), grad_sigmas (compact, NULL to
+ *   skip); both ZEROED by the caller and accumulated into.                                    */
+int voge_bin_count(const float* verts, const float* sigmas, int sigma_kind, const float* R,
+                   const float* T, const float* origins, const float* focal, const float* principal,
+                   int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins,
+                   int bin_size, int tile, uint32_t* rects, int32_t* tile_counts,
+                   voge_stream_t stream);
+int voge_bin_fill(const uint32_t* rects, const int64_t* tile_offsets, int32_t* cursor, int B, int N,
+                  int H, int W, int tile, int32_t* tile_list, voge_stream_t stream);
+int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind,
+                        const float* origins, const float* rays, const int64_t* tile_offsets,
+                        const int32_t* tile_list, float thr_act, float absorptivity,
+                        int B, int N, int H, int W, int K, int tile,
+                        int32_t* out_idx, float* out_weight, float* out_len, int64_t* out_valid,
+                        float* out_act, float* out_dsd, uint64_t* stats, voge_stream_t stream);
+int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind,
+                         const float* origins, const float* rays, const int32_t* idx,
+                         const float* grad_len, const float* grad_act, const float* grad_dsd,
+                         int B, int N, int H, int W, int K,
+                         float* grad_verts, float* grad_sigmas, voge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

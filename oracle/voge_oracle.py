@@ -333,7 +333,7 @@ def ray_trace_fine_torch(mus, isigmas, rays, bin_points, thr_act, bin_size, K, c
 
 
 def render_reference_cpu(verts, sigmas, R, T, focal, principal, image_size, K=20, thr=0.01, absorptivity=1.0,
-                         max_points_per_bin=None, bin_size=None, use_c=True):
+                         max_points_per_bin=None, bin_size=None, use_c=True, rays=None, origin=None):
     """GaussianRenderer.forward (Renderer.py:102-150) end to end on the CPU for the closed-form
     camera: returns dict(weight, idx, valid_num, len, act, dsd, rays, bin_points, mus, isigmas)."""
     H, W = image_size
@@ -341,7 +341,10 @@ def render_reference_cpu(verts, sigmas, R, T, focal, principal, image_size, K=20
     S_in = expend_sigma_torch(sigmas.detach().float().cpu())
     R, T = R.float().cpu(), T.float().cpu()
     B, N = R.shape[0], verts.shape[0]
-    rays, origin = camera_rays(R, T, focal, principal, image_size)
+    if rays is None:
+        rays, origin = camera_rays(R, T, focal, principal, image_size)
+    else:   # rays / origins produced by the device-side generator under test (inputs of the hot path)
+        rays, origin = rays.detach().float().cpu().contiguous(), origin.detach().float().cpu()
     mus = verts[None] - origin[:, None]                                                            # :130
     isig = (2 * S_in)[None].expand(B, -1, -1, -1)                                                  # :131-137
     if bin_size is None:

@@ -8,7 +8,9 @@ import torch.nn as nn
 
 from .Aggregation import aggregation, expend_sigma, merge_final
 from .RayTracing import ray_tracing
-from .cameras import generate_rays
+from .cameras import camera_params, generate_rays
+from .fused import render_fused
+from .RayTracing import default_bin_size
 
 
 class Fragments(object):
@@ -88,6 +90,33 @@ class GaussianRenderer(nn.Module):
         self.device = device
         return self
 
+    # The fused CUDA path (voge_b200/fused.py) is used whenever it applies; set False to force the
+    # op-by-op chain ray_tracing -> aggregation (same results, reference-shaped intermediates).
+    use_fused = True
+
+    def _fusable(self, verts, sigmas, rays, origins):
+        if not (verts.is_cuda and verts.dim() == 3 and verts.shape[0] == 1 and verts.dtype == torch.float32):
+            return False
+        if rays.requires_grad or origins.requires_grad:   # camera gradients: op-by-op path
+            return False
+        return sigmas.dim() in (1, 2, 3)
+
+    def _forward_fused(self, verts, sigmas, rays, origins):
+        st = self.render_settings
+        map_size = st['image_size']
+        sig = sigmas
+        if st['inverse_sigma']:
+            sig = torch.inverse(expend_sigma(sigmas))
+        R, T, focal, principal = camera_params(self.cameras, map_size)
+        n_views = rays.shape[0]
+        R, T = R.expand(n_views, -1, -1), T.expand(n_views, -1)
+        focal, principal = focal.expand(n_views, -1), principal.expand(n_views, -1)
+        M = st['max_point_per_bin']
+        w, idx, valid, ln = render_fused(verts[0], sig, origins, rays, R, T, focal, principal, map_size,
+                                         st['thr_activation'], st['absorptivity'], st['max_assign'],
+                                         use_ref_bins=(M != -1), bin_size=default_bin_size(map_size))
+        return Fragments(vert_weight=w, vert_index=idx, valid_num=valid, vert_hit_length=ln)
+
     def _rays(self, image_size):
         """(directions (B,H,W,3), origins (B,3)).  Real pytorch3d cameras go through pytorch3d's own
         ray sampler exactly like the reference (:124-128); the built-in camera uses the closed form."""
@@ -109,11 +138,13 @@ class GaussianRenderer(nn.Module):
         st = self.render_settings
         verts, sigmas, _radians = gmeshes()
         map_size = st['image_size']
-        sigmas = expend_sigma(sigmas)
         if verts.dim() == 2:
             verts = verts[None]
 
         rays, ray_origins = self._rays(map_size)
+        if self.use_fused and self._fusable(verts, sigmas, rays, ray_origins):
+            return self._forward_fused(verts, sigmas, rays, ray_origins)
+        sigmas = expend_sigma(sigmas)
         verts_transformed = verts - ray_origins[:, None]
         if sigmas.dim() == 3:
             sigmas = sigmas.unsqueeze(0).expand(verts_transformed.shape[0], -1, -1, -1)

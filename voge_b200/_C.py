@@ -233,3 +233,76 @@ def merge_final_backward(attr, weight, idx, valid_num, grad_out, background=None
                                               int(attr.shape[0]), ptr(g_attr), ptr(g_w), stream_of(attr)),
               "merge_final_backward")
     return g_attr, g_w
+
+
+# ---- fused renderer path (no counterpart in the reference's _C: replaces the PyTorch glue +
+# ---- rasterize_points_coarse + ray_trace_voge_fine + Aggregation.py chain) ---------------------
+def sigma_kind(sigmas):
+    if sigmas.dim() == 1:
+        return 1
+    if sigmas.dim() == 2 and sigmas.shape[1] == 3:
+        return 3
+    if sigmas.dim() == 3 and sigmas.shape[1] == 3 and sigmas.shape[2] == 3:
+        return 9
+    raise Exception('Got unexpected sigma, which has shape: ' + str(sigmas.shape))
+
+
+def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act, use_ref_bins, bin_size,
+              tile):
+    """-> (tile_offsets (B*TY*TX+1,) int64, tile_list (total,) int32).  One host sync (the total)."""
+    verts, sigmas = f32c(verts), f32c(sigmas)
+    R, T, origins, focal, principal = f32c(R), f32c(T), f32c(origins), f32c(focal), f32c(principal)
+    B, N = int(R.shape[0]), int(verts.shape[0])
+    H, W = int(image_size[0]), int(image_size[1])
+    TX, TY = (W + tile - 1) // tile, (H + tile - 1) // tile
+    dev = verts.device
+    with torch.cuda.device(dev):
+        rects = torch.empty((B, N, 2), dtype=torch.int32, device=dev)
+        counts = torch.zeros((B * TY * TX + 1,), dtype=torch.int32, device=dev)
+        check(lib().voge_bin_count(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(R), ptr(T), ptr(origins),
+                                   ptr(focal), ptr(principal), B, N, H, W, float(thr), float(thr_act),
+                                   int(bool(use_ref_bins)), int(bin_size), int(tile), ptr(rects), ptr(counts),
+                                   stream_of(verts)), "bin_count")
+        offsets = torch.cumsum(counts, 0, dtype=torch.int64)
+        total = int(offsets[-1].item())
+        offsets = torch.cat([offsets.new_zeros(1), offsets[:-1]])   # exclusive scan, B*TY*TX+1 entries
+        tile_list = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
+        cursor = torch.zeros((B * TY * TX,), dtype=torch.int32, device=dev)
+        check(lib().voge_bin_fill(ptr(rects), ptr(offsets), ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
+                                  stream_of(verts)), "bin_fill")
+    return offsets, tile_list
+
+
+def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, thr_act, absorptivity, K, tile,
+                   need_act=True, stats=None):
+    verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
+    B, H, W = int(rays.shape[0]), int(rays.shape[1]), int(rays.shape[2])
+    N, K = int(verts.shape[0]), int(K)
+    dev = verts.device
+    with torch.cuda.device(dev):
+        idx = torch.empty((B, H, W, K), dtype=torch.int32, device=dev)
+        weight = torch.empty((B, H, W, K), dtype=torch.float32, device=dev)
+        tlen = torch.empty((B, H, W, K), dtype=torch.float32, device=dev)
+        valid = torch.empty((B, H, W), dtype=torch.int64, device=dev)
+        act = torch.empty((B, H, W, K), dtype=torch.float32, device=dev) if need_act else None
+        dsd = torch.empty((B, H, W, K), dtype=torch.float32, device=dev) if need_act else None
+        check(lib().voge_render_forward(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(origins), ptr(rays),
+                                        ptr(tile_offsets), ptr(tile_list), float(thr_act), float(absorptivity),
+                                        B, N, H, W, K, int(tile), ptr(idx), ptr(weight), ptr(tlen), ptr(valid),
+                                        ptr(act), ptr(dsd), ptr(stats), stream_of(verts)), "render_forward")
+    return idx, weight, tlen, valid, act, dsd
+
+
+def render_backward(verts, sigmas, origins, rays, idx, g_len, g_act, g_dsd, need_sigma=True):
+    verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
+    idx, g_len, g_act, g_dsd = i32c(idx), f32c(g_len), f32c(g_act), f32c(g_dsd)
+    B, H, W, K = (int(s) for s in idx.shape)
+    N = int(verts.shape[0])
+    dev = verts.device
+    with torch.cuda.device(dev):
+        g_verts = torch.zeros_like(verts)
+        g_sig = torch.zeros_like(sigmas) if need_sigma else None
+        check(lib().voge_render_backward(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(origins), ptr(rays),
+                                         ptr(idx), ptr(g_len), ptr(g_act), ptr(g_dsd), B, N, H, W, K, ptr(g_verts),
+                                         ptr(g_sig), stream_of(verts)), "render_backward")
+    return g_verts, g_sig

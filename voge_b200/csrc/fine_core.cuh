@@ -37,22 +37,52 @@ __device__ __forceinline__ void stage_candidate(float* __restrict__ dst, int g, 
     const float a = S[0], b = S[4], c = S[8];
     const float e01 = S[1] + S[3], e02 = S[2] + S[6], e12 = S[5] + S[7];
     const float s01 = 0.5f * e01, s02 = 0.5f * e02, s12 = 0.5f * e12;
-    const float minor2 = a * b - s01 * s01;
-    const float det = a * (b * c - s12 * s12) - s01 * (s01 * c - s12 * s02) + s02 * (s01 * s12 - b * s02);
-    const float sabs = fabsf(S[0]) + fabsf(S[1]) + fabsf(S[2]) + fabsf(S[3]) + fabsf(S[4]) +
-                       fabsf(S[5]) + fabsf(S[6]) + fabsf(S[7]) + fabsf(S[8]);
-    const float tr = a + b + c;
-    // kappa >= sum|S_ij| / lambda_min(sym S):  lambda_min >= det / (tr/2)^2
-    const float kappa = sabs * (0.25f * tr * tr) / det;
-    // |act_ref - act_filter| <= 2^-17 * kappa * msm (DESIGN.md "filter margin"); factor 2 slack
-    const float margin = 1.52587890625e-5f * kappa * (fabsf(msm) + fabsf(thr_act)) + 1e-30f;
+    // smallest / largest eigenvalue of the symmetric part (closed form, Smith 1961)
+    float lmin, lmax;
+    {
+        const float p1 = s01 * s01 + s02 * s02 + s12 * s12;
+        if (p1 == 0.f) {
+            lmin = fminf(a, fminf(b, c));
+            lmax = fmaxf(a, fmaxf(b, c));
+        } else {
+            const float qq = (a + b + c) * (1.f / 3.f);
+            const float aa = a - qq, bb = b - qq, cc = c - qq;
+            const float p = sqrtf((aa * aa + bb * bb + cc * cc + 2.f * p1) * (1.f / 6.f));
+            const float ip = 1.f / p;
+            const float b00 = aa * ip, b11 = bb * ip, b22 = cc * ip, b01 = s01 * ip, b02 = s02 * ip, b12 = s12 * ip;
+            float r = 0.5f * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+            r = fminf(1.f, fmaxf(-1.f, r));
+            const float phi = acosf(r) * (1.f / 3.f);
+            lmax = qq + 2.f * p * cosf(phi);
+            lmin = qq + 2.f * p * cosf(phi + 2.0943951023931953f);
+        }
+        lmin -= 1e-5f * fabsf(lmax);   // rounding of the closed form itself
+    }
+    // Worst-case |act_reference - act_filter| for this Gaussian over all unit rays
+    // (forward error analysis of both evaluation orders, DESIGN.md "filter margin"):
+    //   eps * [16 Tmm + (Qn/l)(26 Um2 + 8 Qn) + (17 Us/l + 3) Qn^2/l + 4 msm],  eps = 2^-24, x1.25 slack
+    const float am0 = fabsf(m0), am1 = fabsf(m1), am2 = fabsf(m2);
+    const float c0 = am0 * fabsf(S[0]) + am1 * fabsf(S[3]) + am2 * fabsf(S[6]);   // (|S|^T |mu|)_j
+    const float c1 = am0 * fabsf(S[1]) + am1 * fabsf(S[4]) + am2 * fabsf(S[7]);
+    const float c2 = am0 * fabsf(S[2]) + am1 * fabsf(S[5]) + am2 * fabsf(S[8]);
+    const float Tmm = c0 * am0 + c1 * am1 + c2 * am2;
+    const float Um2 = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
+    const float Qn = sqrtf(q0 * q0 + q1 * q1 + q2 * q2);
+    const float r0 = fabsf(S[0]) + fabsf(S[1]) + fabsf(S[2]), r1 = fabsf(S[3]) + fabsf(S[4]) + fabsf(S[5]),
+                r2 = fabsf(S[6]) + fabsf(S[7]) + fabsf(S[8]);
+    const float k0 = fabsf(S[0]) + fabsf(S[3]) + fabsf(S[6]), k1 = fabsf(S[1]) + fabsf(S[4]) + fabsf(S[7]),
+                k2 = fabsf(S[2]) + fabsf(S[5]) + fabsf(S[8]);
+    const float Us = fmaxf(fmaxf(fmaxf(r0, r1), r2), fmaxf(fmaxf(k0, k1), k2));
+    const float il = 1.f / lmin;
+    const float bound = 16.f * Tmm + (Qn * il) * (26.f * Um2 + 8.f * Qn) + (17.f * Us * il + 3.f) * (Qn * Qn * il) +
+                        4.f * fabsf(msm) + 8.f * fabsf(thr_act);
+    const float margin = 7.4505806e-8f * bound;   // 1.25 * 2^-24
     const float u = msm - thr_act - margin;
-    const bool pd = (a > 0.f) && (minor2 > 0.f) && (det > 0.f) && (fabsf(u) < 3.0e38f) &&
-                    (fabsf(q0) + fabsf(q1) + fabsf(q2) < 3.0e38f);
+    const bool pd = (lmin > 0.f) && (fabsf(u) < 3.0e38f) && (fabsf(q0) + fabsf(q1) + fabsf(q2) < 3.0e38f);
     if (pd) {
         v0 = make_float4(q0, q1, q2, u);
         v1 = make_float4(a, b, c, e01);
-        v2 = make_float4(e02, e12, __int_as_float(g), 0.f);
+        v2 = make_float4(e02, e12, __int_as_float(g), margin);
     } else {
         // not provably safe to filter: ksk~ = |d|^2 > 0 and u' = -inf => never rejected
         v0 = make_float4(0.f, 0.f, 0.f, -INFINITY);
@@ -115,6 +145,9 @@ struct RayMono {
     __device__ __forceinline__ void set(float x, float y, float z) {
         d0 = x; d1 = y; d2 = z;
         dxx = x * x; dyy = y * y; dzz = z * z; dxy = x * y; dxz = x * z; dyz = y * z;
+        // the filter margin assumes unit rays (the renderer's always are); for anything else the
+        // monomials are poisoned with NaN so that the filter never rejects (f = NaN => refine).
+        if (!(fabsf(dxx + dyy + dzz - 1.f) <= 1e-3f)) dxx = __int_as_float(0x7fc00000);
     }
 };
 

@@ -1,0 +1,590 @@
+// render.cu -- the fused renderer path behind GaussianRenderer.forward:
+//   voge_bin_count / voge_bin_fill : per-view screen-space culling into per-tile CSR lists
+//   voge_render_forward            : tile-staged filter -> bit-faithful refine -> top-K -> blend weights
+//   voge_render_backward           : recompute + chain rule straight into (N,.) parameter gradients
+//
+// Replaces, for the renderer's own call pattern, the chain
+//   rasterize_coarse (PyTorch maths RayTracing.py:42-57 + kernels rasterize_coarse.cu:20-188)
+//   -> RayTraceFineVogeKernel (ray_trace_voge.cu:135-217) -> aggregation (Aggregation.py:82-107)
+// without materialising (B,N,3)/(B,N,3,3) per-view copies, the (B,BH,BW,M) bin table or the
+// (R,K,K) blend tensors.  Candidate semantics are the reference's: a Gaussian is a candidate of a
+// pixel iff the reference's bbox test puts it in the pixel's coarse bin (bin_size pixels); the
+// tile lists here are that set AND-ed with a provably conservative projected-ellipsoid bound, so
+// the fragments equal the unfused path's bit for bit (same exact_pair arithmetic decides).
+#include "../../include/voge_b200.h"
+#include "blend_core.cuh"
+#include "fine_core.cuh"
+
+namespace voge {
+
+// ---- parameter access ----------------------------------------------------------------------------
+// sigma kinds: 1 = (N,) isotropic, 3 = (N,3) diagonal, 9 = (N,3,3) full.  S = 2 * sigma (Renderer.py:137)
+template <int KIND>
+__device__ __forceinline__ void load_S(const float* __restrict__ sig, int g, float* S) {
+    if (KIND == 1) {
+        const float s = 2.f * __ldg(sig + g);
+        S[0] = s; S[1] = 0.f; S[2] = 0.f; S[3] = 0.f; S[4] = s; S[5] = 0.f; S[6] = 0.f; S[7] = 0.f; S[8] = s;
+    } else if (KIND == 3) {
+        S[0] = 2.f * __ldg(sig + 3 * (int64_t)g); S[4] = 2.f * __ldg(sig + 3 * (int64_t)g + 1);
+        S[8] = 2.f * __ldg(sig + 3 * (int64_t)g + 2);
+        S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) S[i] = 2.f * __ldg(sig + 9 * (int64_t)g + i);
+    }
+}
+
+__device__ __forceinline__ void load_S_dyn(int kind, const float* __restrict__ sig, int g, float* S) {
+    if (kind == 1) load_S<1>(sig, g, S);
+    else if (kind == 3) load_S<3>(sig, g, S);
+    else load_S<9>(sig, g, S);
+}
+
+// exact_pair specialised for a diagonal S: identical bits to exact_pair with explicit zeros
+// (fma(0, c, acc) == acc), at a third of the work.
+__device__ __forceinline__ Hit exact_pair_diag(float m0, float m1, float m2, float s0, float s1, float s2,
+                                               float d0, float d1, float d2) {
+    const float t0 = __fmul_rn(d0, s0), t1 = __fmul_rn(d1, s1), t2 = __fmul_rn(d2, s2);
+    const float u0 = __fmul_rn(m0, s0), u1 = __fmul_rn(m1, s1), u2 = __fmul_rn(m2, s2);
+    const float ksk = __fmaf_rn(t2, d2, __fmaf_rn(t1, d1, __fmul_rn(t0, d0)));
+    const float msk = __fmaf_rn(u2, d2, __fmaf_rn(u1, d1, __fmul_rn(u0, d0)));
+    const float msm = __fmaf_rn(u2, m2, __fmaf_rn(u1, m1, __fmul_rn(u0, m0)));
+    Hit h;
+    h.len = __fdiv_rn(msk, ksk);
+    h.act = __fsub_rn(msm, __fdiv_rn(__fmul_rn(msk, msk), ksk));
+    h.dsd = ksk;
+    return h;
+}
+
+template <int KIND>
+__device__ __forceinline__ Hit exact_hit(const float* __restrict__ verts, const float* __restrict__ sig, int g,
+                                         float c0, float c1, float c2, float d0, float d1, float d2) {
+    const float m0 = __fsub_rn(__ldg(verts + 3 * (int64_t)g), c0);       // verts - ray_origin, Renderer.py:130
+    const float m1 = __fsub_rn(__ldg(verts + 3 * (int64_t)g + 1), c1);
+    const float m2 = __fsub_rn(__ldg(verts + 3 * (int64_t)g + 2), c2);
+    if (KIND == 1) {
+        const float s = 2.f * __ldg(sig + g);
+        return exact_pair_diag(m0, m1, m2, s, s, s, d0, d1, d2);
+    } else if (KIND == 3) {
+        return exact_pair_diag(m0, m1, m2, 2.f * __ldg(sig + 3 * (int64_t)g), 2.f * __ldg(sig + 3 * (int64_t)g + 1),
+                               2.f * __ldg(sig + 3 * (int64_t)g + 2), d0, d1, d2);
+    } else {
+        float S[9];
+        load_S<9>(sig, g, S);
+        return exact_pair(m0, m1, m2, S, d0, d1, d2);
+    }
+}
+
+// ---- binning ---------------------------------------------------------------------------------------
+struct BinArgs {
+    const float* verts;
+    const float* sigmas;
+    int kind;
+    const float* Rm;         // (B,3,3) row-vector convention X_view = X_world @ R + T
+    const float* Tv;         // (B,3)
+    const float* origins;    // (B,3) ray origins (camera centres) used for mu' = verts - origin
+    const float* focal;      // (B,2) pixels
+    const float* principal;  // (B,2) pixels
+    int B, N, H, W;
+    float neg_log_thr, thr_act;
+    int use_ref_bins, bin_size, BH, BW, tile, TX, TY;
+    uint2* rects;            // (B,N): x = x0 | x1 << 16, y = y0 | y1 << 16 in tile units; empty if x0 > x1
+    int32_t* tile_counts;    // (B, TY*TX)
+};
+
+__device__ __forceinline__ float edge_min(int i, int bin, int S1, int S2, float half) {
+    return __fsub_rn(pix_to_ndc(i * bin, S1, S2), half);
+}
+__device__ __forceinline__ float edge_max(int i, int bin, int S1, int S2, float half) {
+    return __fadd_rn(pix_to_ndc((i + 1) * bin - 1, S1, S2), half);
+}
+
+// contiguous range of reference bins along one axis accepted by the reference predicate
+// (lo <= bin_max) && (bin_min < hi)   (rasterize_coarse.cu:116-130)
+__device__ __forceinline__ void ref_bin_range(float lo, float hi, int nb, int bin, int S1, int S2, float half,
+                                              float scale, int& b0, int& b1) {
+    const float c = 0.5f * (float)S1;
+    int e0 = (int)floorf(fminf(fmaxf((lo * scale + c) / (float)bin, -1.f), (float)nb));
+    int e1 = (int)floorf(fminf(fmaxf((hi * scale + c) / (float)bin, -1.f), (float)nb));
+    e0 = min(max(e0, 0), nb - 1);
+    e1 = min(max(e1, 0), nb - 1);
+    // first bin with lo <= bin_max
+    while (e0 > 0 && (lo <= edge_max(e0 - 1, bin, S1, S2, half))) --e0;
+    while (e0 < nb && !(lo <= edge_max(e0, bin, S1, S2, half))) ++e0;
+    // last bin with bin_min < hi
+    while (e1 < nb - 1 && (edge_min(e1 + 1, bin, S1, S2, half) < hi)) ++e1;
+    while (e1 >= 0 && !(edge_min(e1, bin, S1, S2, half) < hi)) --e1;
+    b0 = e0; b1 = e1;
+}
+
+// Per-Gaussian worst-case bound on |act_reference - act_true| + filter error (same formula as
+// stage_candidate) and PD check; returns false if the Gaussian must not be culled analytically.
+__device__ __forceinline__ bool gaussian_margin(const float* mu, const float* S, float thr_act, float& margin) {
+    __align__(16) float tmp[kStageFloats];
+    stage_candidate(tmp, 0, mu, S, thr_act);
+    if (!(tmp[3] > -3.0e38f)) return false;   // flagged "never reject"
+    margin = tmp[11];
+    return margin >= 0.f;
+}
+
+__global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
+    const int b = blockIdx.y;
+    const float* R = a.Rm + 9 * b;
+    const float fx = a.focal[2 * b], fy = a.focal[2 * b + 1];
+    const float px = a.principal[2 * b], py = a.principal[2 * b + 1];
+    const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
+    const float sc = 0.5f * (float)min(a.H, a.W);
+    const float half_x = __fdiv_rn(ndc_range(a.W, a.H) / 2.0f, (float)a.W);
+    const float half_y = __fdiv_rn(ndc_range(a.H, a.W) / 2.0f, (float)a.H);
+    const int tpb = a.use_ref_bins ? a.bin_size / a.tile : 1;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < a.N; g += gridDim.x * blockDim.x) {
+        float mu[3], S[9];
+        mu[0] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
+        mu[1] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
+        mu[2] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
+        load_S_dyn(a.kind, a.sigmas, g, S);
+        // view space (X_v = mu' @ R since the origin is the camera centre)
+        const float xv = mu[0] * R[0] + mu[1] * R[3] + mu[2] * R[6];
+        const float yv = mu[0] * R[1] + mu[1] * R[4] + mu[2] * R[7];
+        const float zv = mu[0] * R[2] + mu[1] * R[5] + mu[2] * R[8];
+        int tx0 = 0, tx1 = a.TX - 1, ty0 = 0, ty1 = a.TY - 1;
+        bool empty = false;
+        if (a.use_ref_bins) {
+            if (zv < 0.f) empty = true;   // rasterize_coarse.cu:35
+            // S_view[:2,:2] = (R^T S R)[:2,:2]
+            float SR0[3], SR1[3];   // columns 0,1 of S R
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                SR0[i] = S[3 * i] * R[0] + S[3 * i + 1] * R[3] + S[3 * i + 2] * R[6];
+                SR1[i] = S[3 * i] * R[1] + S[3 * i + 1] * R[4] + S[3 * i + 2] * R[7];
+            }
+            const float v00 = R[0] * SR0[0] + R[3] * SR0[1] + R[6] * SR0[2];
+            const float v01 = R[0] * SR1[0] + R[3] * SR1[1] + R[6] * SR1[2];
+            const float v10 = R[1] * SR0[0] + R[4] * SR0[1] + R[7] * SR0[2];
+            const float v11 = R[1] * SR1[0] + R[4] * SR1[1] + R[7] * SR1[2];
+            const float idet = 1.f / (v00 * v11 - v01 * v10);
+            const float i00 = v11 * idet, i01 = -v01 * idet, i10 = -v10 * idet, i11 = v00 * idet;
+            const float F0 = fx / sc, F1 = fy / sc;
+            // radii = sqrt(colsum(-ln(thr) F inv F)) / z   (RayTracing.py:33-39)
+            const float col0 = a.neg_log_thr * F0 * (F0 * i00 + F1 * i10);
+            const float col1 = a.neg_log_thr * F1 * (F0 * i01 + F1 * i11);
+            const float iz = 1.f / zv;
+            const float rx = sqrtf(col0) * iz, ry = sqrtf(col1) * iz;
+            const float xn = ((px - fx * xv * iz) - 0.5f * (float)a.W) / sc;
+            const float yn = ((py - fy * yv * iz) - 0.5f * (float)a.H) / sc;
+            int bx0, bx1, by0, by1;
+            ref_bin_range(xn - rx, xn + rx, a.BW, a.bin_size, a.W, a.H, half_x, sc, bx0, bx1);
+            ref_bin_range(yn - ry, yn + ry, a.BH, a.bin_size, a.H, a.W, half_y, sc, by0, by1);
+            if (bx0 > bx1 || by0 > by1) empty = true;
+            tx0 = bx0 * tpb; tx1 = min((bx1 + 1) * tpb - 1, a.TX - 1);
+            ty0 = by0 * tpb; ty1 = min((by1 + 1) * tpb - 1, a.TY - 1);
+        }
+        // conservative projected-ellipsoid bound (exact tangent lines of {act < thr + margin})
+        float margin;
+        if (!empty && zv > 0.f && gaussian_margin(mu, S, a.thr_act, margin)) {
+            const float a00 = S[0], a11 = S[4], a22 = S[8];
+            const float a01 = 0.5f * (S[1] + S[3]), a02 = 0.5f * (S[2] + S[6]), a12 = 0.5f * (S[5] + S[7]);
+            // inverse of the symmetric part (adjugate / det)
+            const float j00 = a11 * a22 - a12 * a12, j01 = a02 * a12 - a01 * a22, j02 = a01 * a12 - a02 * a11;
+            const float j11 = a00 * a22 - a02 * a02, j12 = a01 * a02 - a00 * a12, j22 = a00 * a11 - a01 * a01;
+            const float det = a00 * j00 + a01 * j01 + a02 * j02;
+            const float t = (a.thr_act + margin) * 1.0001f / det;
+            // Q = t * R^T J R ; need Q00 Q11 Q22 Q02 Q12
+            float JR[3][3];
+            const float J[9] = {j00, j01, j02, j01, j11, j12, j02, j12, j22};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) JR[i][k] = J[3 * i] * R[k] + J[3 * i + 1] * R[3 + k] + J[3 * i + 2] * R[6 + k];
+            const float Q00 = t * (R[0] * JR[0][0] + R[3] * JR[1][0] + R[6] * JR[2][0]);
+            const float Q11 = t * (R[1] * JR[0][1] + R[4] * JR[1][1] + R[7] * JR[2][1]);
+            const float Q22 = t * (R[2] * JR[0][2] + R[5] * JR[1][2] + R[8] * JR[2][2]);
+            const float Q02 = t * (R[0] * JR[0][2] + R[3] * JR[1][2] + R[6] * JR[2][2]);
+            const float Q12 = t * (R[1] * JR[0][2] + R[4] * JR[1][2] + R[7] * JR[2][2]);
+            const float C22 = zv * zv - Q22;
+            if (C22 > 1e-6f * zv * zv && det > 0.f) {
+                // disc = C02^2 - C00 C22 expanded to avoid cancellation
+                const float dx = xv * xv * Q22 + zv * zv * Q00 - 2.f * xv * zv * Q02 + (Q02 * Q02 - Q00 * Q22);
+                const float dy = yv * yv * Q22 + zv * zv * Q11 - 2.f * yv * zv * Q12 + (Q12 * Q12 - Q11 * Q22);
+                const float sx = sqrtf(fmaxf(dx, 0.f)) * 1.001f, sy = sqrtf(fmaxf(dy, 0.f)) * 1.001f;
+                const float C02 = xv * zv - Q02, C12 = yv * zv - Q12;
+                const float ic = 1.f / C22;
+                const float u_lo = (C02 - sx) * ic, u_hi = (C02 + sx) * ic;
+                const float v_lo = (C12 - sy) * ic, v_hi = (C12 + sy) * ic;
+                // pixel centre xi+.5 = px - fx*u  (u = X/Z); slack 0.05 px
+                const float xs_lo = px - fx * u_hi - 0.55f, xs_hi = px - fx * u_lo - 0.45f;
+                const float ys_lo = py - fy * v_hi - 0.55f, ys_hi = py - fy * v_lo - 0.45f;
+                if (xs_lo == xs_lo && xs_hi == xs_hi && ys_lo == ys_lo && ys_hi == ys_hi) {
+                    const float fW = (float)a.W, fH = (float)a.H;
+                    if (xs_hi < 0.f || ys_hi < 0.f || xs_lo > fW - 1.f || ys_lo > fH - 1.f) {
+                        empty = true;
+                    } else {
+                        const int pxl = (int)ceilf(fmaxf(xs_lo, 0.f)), pxh = (int)floorf(fminf(xs_hi, fW - 1.f));
+                        const int pyl = (int)ceilf(fmaxf(ys_lo, 0.f)), pyh = (int)floorf(fminf(ys_hi, fH - 1.f));
+                        if (pxl > pxh || pyl > pyh) empty = true;
+                        tx0 = max(tx0, pxl / a.tile); tx1 = min(tx1, pxh / a.tile);
+                        ty0 = max(ty0, pyl / a.tile); ty1 = min(ty1, pyh / a.tile);
+                    }
+                }
+            }
+        }
+        if (tx0 > tx1 || ty0 > ty1) empty = true;
+        uint2 rc;
+        if (empty) {
+            rc = make_uint2(1u, 0u);
+        } else {
+            rc = make_uint2((unsigned)tx0 | ((unsigned)tx1 << 16), (unsigned)ty0 | ((unsigned)ty1 << 16));
+            int32_t* cnt = a.tile_counts + (int64_t)b * a.TX * a.TY;
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt + ty * a.TX + tx, 1);
+        }
+        a.rects[(int64_t)b * a.N + g] = rc;
+    }
+}
+
+__global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__ rects,
+                                                       const int64_t* __restrict__ tile_offsets,
+                                                       int32_t* __restrict__ cursor, int B, int N, int TX, int TY,
+                                                       int32_t* __restrict__ tile_list) {
+    const int b = blockIdx.y;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
+        const uint2 rc = rects[(int64_t)b * N + g];
+        const int tx0 = rc.x & 0xffff, tx1 = rc.x >> 16, ty0 = rc.y & 0xffff, ty1 = rc.y >> 16;
+        if (tx0 > tx1) continue;
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                const int64_t t = ((int64_t)b * TY + ty) * TX + tx;
+                const int slot = atomicAdd(cursor + t, 1);
+                tile_list[tile_offsets[t] + slot] = g;
+            }
+    }
+}
+
+// ---- fused forward -----------------------------------------------------------------------------------
+struct RenderArgs {
+    const float* verts;
+    const float* sigmas;
+    const float* origins;   // (B,3)
+    const float* rays;      // (B,H,W,3)
+    const int64_t* tile_offsets;  // (B*TY*TX + 1)
+    const int32_t* tile_list;     // local Gaussian indices
+    float thr_act, omega;
+    int B, N, H, W, K, tile, TX, TY;
+    int32_t* out_idx;       // (B,H,W,K) packed b*N+g, -1 padded
+    float* out_weight;      // (B,H,W,K)
+    float* out_len;         // (B,H,W,K), 1e10 padded
+    int64_t* out_valid;     // (B,H,W)
+    float* out_act;         // optional (B,H,W,K)
+    float* out_dsd;         // optional (B,H,W,K)
+    unsigned long long* stats;  // optional: [0] pairs filtered, [1] pairs refined
+};
+
+constexpr int kRChunk = 128;
+
+template <int NT, int KIND>
+__global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_stage = reinterpret_cast<float*>(smem_raw);                        // [kRChunk][12]
+    float* s_len = s_stage + kRChunk * kStageFloats;                            // [K][NT]
+    int* s_idx = reinterpret_cast<int*>(s_len + (size_t)a.K * NT);              // [K][NT]  (later: s_k)
+    float* s_E = reinterpret_cast<float*>(s_idx + (size_t)a.K * NT);            // [K][NT]
+    unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_E + (size_t)a.K * NT);   // [kQueueCap][NT]
+
+    const int tid = threadIdx.x;
+    int blk = blockIdx.x;
+    const int tx = blk % a.TX; blk /= a.TX;
+    const int ty = blk % a.TY;
+    const int b = blk / a.TY;
+
+    // pixel of this thread: 16x16 tiles give every warp an 8x4 block (locality for culling and
+    // atomics); other tile sizes use the linear order
+    int lx, ly;
+    bool in_tile;
+    if (a.tile == 16 && NT == 256) {
+        const int w = tid >> 5, l = tid & 31;
+        lx = (w & 1) * 8 + (l & 7);
+        ly = (w >> 1) * 4 + (l >> 3);
+        in_tile = true;
+    } else {
+        lx = tid % a.tile; ly = tid / a.tile;
+        in_tile = tid < a.tile * a.tile;
+    }
+    const int xi = tx * a.tile + lx, yi = ty * a.tile + ly;
+    const bool live = in_tile && xi < a.W && yi < a.H;
+    const int64_t ray = ((int64_t)b * a.H + yi) * a.W + xi;
+    const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
+
+    RayMono r;
+    r.set(0.f, 0.f, 0.f);
+    if (live) r.set(a.rays[ray * 3 + 0], a.rays[ray * 3 + 1], a.rays[ray * 3 + 2]);
+
+    TopK<NT> top;
+    top.init(s_len, s_idx, a.K, tid);
+
+    const int64_t tile_id = ((int64_t)b * a.TY + ty) * a.TX + tx;
+    const int64_t beg = a.tile_offsets[tile_id];
+    const int n = (int)(a.tile_offsets[tile_id + 1] - beg);
+    const int32_t* list = a.tile_list + beg;
+
+    int qn = 0;
+    unsigned n_ref = 0;
+    auto drain = [&]() {
+        for (int j = 0; j < qn; ++j) {
+            const int c = s_queue[j * NT + tid];
+            const int g = __float_as_int(s_stage[c * kStageFloats + 10]);
+            if (g < 0) continue;
+            const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r.d0, r.d1, r.d2);
+            if (h.act < a.thr_act) top.insert(h.len, g);
+        }
+        n_ref += qn;
+        qn = 0;
+    };
+
+    for (int base = 0; base < n; base += kRChunk) {
+        __syncthreads();
+        for (int t = tid; t < kRChunk; t += NT) {
+            const int m = base + t;
+            if (m < n) {
+                const int g = list[m];
+                float mu[3], S[9];
+                mu[0] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
+                mu[1] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
+                mu[2] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
+                load_S<KIND>(a.sigmas, g, S);
+                stage_candidate(s_stage + t * kStageFloats, g, mu, S, a.thr_act);
+            } else {
+                stage_invalid(s_stage + t * kStageFloats);
+            }
+        }
+        __syncthreads();
+        if (live) {
+            const int cn = min(kRChunk, n - base);
+#pragma unroll 4
+            for (int c = 0; c < cn; ++c) {
+                if (filter_pass(s_stage + c * kStageFloats, r)) {
+                    s_queue[qn * NT + tid] = (unsigned short)c;
+                    if (++qn == kQueueCap) drain();
+                }
+            }
+            drain();
+        }
+    }
+    if (a.stats != nullptr) {
+        // warp-aggregated counters (diagnostics only; NULL in timed runs)
+        unsigned long long f = live ? (unsigned long long)n : 0ull, e = n_ref;
+        for (int o = 16; o > 0; o >>= 1) {
+            f += __shfl_down_sync(0xffffffffu, f, o);
+            e += __shfl_down_sync(0xffffffffu, e, o);
+        }
+        if ((tid & 31) == 0) { atomicAdd(a.stats, f); atomicAdd(a.stats + 1, (unsigned long long)e); }
+    }
+    if (!live) return;
+
+    // ---- epilogue: exact (len, act, dsd) of the survivors, blend weights, fragment write-out ----
+    const int cnt = top.cnt;
+    int32_t* o_idx = a.out_idx + ray * a.K;
+    float* o_len = a.out_len + ray * a.K;
+    float* o_w = a.out_weight + ray * a.K;
+    for (int k = 0; k < cnt; ++k) {
+        const int g = s_idx[k * NT + tid];
+        const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r.d0, r.d1, r.d2);
+        o_idx[k] = b * a.N + g;
+        o_len[k] = h.len;
+        if (a.out_act != nullptr) { a.out_act[ray * a.K + k] = h.act; a.out_dsd[ray * a.K + k] = h.dsd; }
+        s_len[k * NT + tid] = h.len;
+        reinterpret_cast<float*>(s_idx)[k * NT + tid] = sqrtf(h.dsd + 1e-10f);   // Aggregation.py:49
+        s_E[k * NT + tid] = expf(-h.act);
+    }
+    const float* s_s = reinterpret_cast<const float*>(s_idx);
+    for (int m = 0; m < cnt; ++m) {
+        const float lm = s_len[m * NT + tid];
+        float D = 0.f;
+        for (int k = 0; k < cnt; ++k) {
+            const float Ek = s_E[k * NT + tid];
+            if (Ek == 0.f) continue;
+            D += Ek * phi((lm - s_len[k * NT + tid]) * s_s[k * NT + tid]);
+        }
+        const float Em = s_E[m * NT + tid];
+        o_w[m] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
+    }
+    for (int k = cnt; k < a.K; ++k) {
+        o_idx[k] = -1; o_len[k] = kEmptyLen; o_w[k] = 0.f;
+        if (a.out_act != nullptr) { a.out_act[ray * a.K + k] = kEmptyLen; a.out_dsd[ray * a.K + k] = 0.f; }
+    }
+    a.out_valid[ray] = cnt;
+}
+
+template <int NT, int KIND>
+static int launch_render(const RenderArgs& a, cudaStream_t stream) {
+    const size_t smem = (size_t)kRChunk * kStageFloats * 4 + (size_t)a.K * NT * 12 + (size_t)kQueueCap * NT * 2;
+    if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+    VOGE_CUDA_TRY(cudaFuncSetAttribute(render_fwd_kernel<NT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long grid = (long long)a.B * a.TX * a.TY;
+    if (grid <= 0 || grid > 2147483647LL) return (int)cudaErrorInvalidValue;
+    render_fwd_kernel<NT, KIND><<<(unsigned)grid, NT, smem, stream>>>(a);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int KIND>
+static int dispatch_render(const RenderArgs& a, cudaStream_t s) {
+    const int px = a.tile * a.tile;
+    if (px > 256) return (int)cudaErrorInvalidValue;
+    if (px > 128) {
+        if ((size_t)a.K * 256 * 12 > 200 * 1024) return (int)cudaErrorInvalidValue;
+        return launch_render<256, KIND>(a, s);
+    }
+    if (px > 64) return launch_render<128, KIND>(a, s);
+    return launch_render<64, KIND>(a, s);
+}
+
+// ---- backward of the geometry: d(len, act, dsd) -> d(verts), d(sigmas) ----------------------------------
+struct RenderBwdArgs {
+    const float* verts;
+    const float* sigmas;
+    int kind;
+    const float* origins;
+    const float* rays;
+    const int32_t* idx;      // packed
+    const float* g_len;
+    const float* g_act;
+    const float* g_dsd;
+    int B, N, H, W, K;
+    float* grad_verts;       // (N,3) accumulated
+    float* grad_sigmas;      // (N,), (N,3) or (N,3,3) accumulated (gradient w.r.t. sigma, i.e. includes the factor 2)
+};
+
+__global__ void __launch_bounds__(256) render_bwd_kernel(const RenderBwdArgs a) {
+    // 8x4 pixel block per warp so that lanes of a warp touch the same Gaussians
+    const int bw = (a.W + 7) / 8, bh = (a.H + 3) / 4;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t per_view = (int64_t)bw * bh;
+    if (wid >= per_view * a.B) return;
+    const int b = (int)(wid / per_view);
+    const int wb = (int)(wid % per_view);
+    const int xi = (wb % bw) * 8 + (lane & 7), yi = (wb / bw) * 4 + (lane >> 3);
+    if (xi >= a.W || yi >= a.H) return;
+    const int64_t r = ((int64_t)b * a.H + yi) * a.W + xi;
+    const float d0 = a.rays[r * 3 + 0], d1 = a.rays[r * 3 + 1], d2 = a.rays[r * 3 + 2];
+    const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
+    for (int k = 0; k < a.K; ++k) {
+        const int gp = a.idx[r * a.K + k];
+        if (gp < 0) break;   // valid entries come first
+        const int g = gp - b * a.N;
+        if (g < 0 || g >= a.N) continue;
+        const float gl = a.g_len[r * a.K + k], ga = a.g_act[r * a.K + k], gd = a.g_dsd[r * a.K + k];
+        float S[9];
+        load_S_dyn(a.kind, a.sigmas, g, S);
+        const float m0 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
+        const float m1 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
+        const float m2 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
+        const Prod9 pd = exact_row_products(d0, d1, d2, S);
+        const Prod9 pm = exact_row_products(m0, m1, m2, S);
+        const float ksk = exact_contract(pd, d0, d1, d2);
+        const float msk = exact_contract(pm, d0, d1, d2);
+        const float g_ksk = (ga * msk - gl) * msk / (ksk * ksk) + gd;   // ray_trace_voge.cu:324-326
+        const float g_msk = (gl - 2.f * ga * msk) / ksk;
+        const float g_msm = ga;
+        const float Sd0 = S[0] * d0 + S[1] * d1 + S[2] * d2, Sd1 = S[3] * d0 + S[4] * d1 + S[5] * d2,
+                    Sd2 = S[6] * d0 + S[7] * d1 + S[8] * d2;
+        const float Sm0 = S[0] * m0 + S[1] * m1 + S[2] * m2, Sm1 = S[3] * m0 + S[4] * m1 + S[5] * m2,
+                    Sm2 = S[6] * m0 + S[7] * m1 + S[8] * m2;
+        const float Stm0 = S[0] * m0 + S[3] * m1 + S[6] * m2, Stm1 = S[1] * m0 + S[4] * m1 + S[7] * m2,
+                    Stm2 = S[2] * m0 + S[5] * m1 + S[8] * m2;
+        float* gv = a.grad_verts + 3 * (int64_t)g;
+        atomicAdd(gv + 0, g_msk * Sd0 + g_msm * (Sm0 + Stm0));
+        atomicAdd(gv + 1, g_msk * Sd1 + g_msm * (Sm1 + Stm1));
+        atomicAdd(gv + 2, g_msk * Sd2 + g_msm * (Sm2 + Stm2));
+        if (a.grad_sigmas != nullptr) {
+            const float dv[3] = {d0, d1, d2}, mv[3] = {m0, m1, m2};
+            if (a.kind == 1) {
+                const float tr = g_ksk * (d0 * d0 + d1 * d1 + d2 * d2) + g_msk * (m0 * d0 + m1 * d1 + m2 * d2) +
+                                 g_msm * (m0 * m0 + m1 * m1 + m2 * m2);
+                atomicAdd(a.grad_sigmas + g, 2.f * tr);
+            } else if (a.kind == 3) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    atomicAdd(a.grad_sigmas + 3 * (int64_t)g + i,
+                              2.f * (g_ksk * dv[i] * dv[i] + g_msk * mv[i] * dv[i] + g_msm * mv[i] * mv[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        atomicAdd(a.grad_sigmas + 9 * (int64_t)g + 3 * i + j,
+                                  2.f * (g_ksk * dv[i] * dv[j] + g_msk * mv[i] * dv[j] + g_msm * mv[i] * mv[j]));
+            }
+        }
+    }
+}
+
+}  // namespace voge
+
+extern "C" int voge_bin_count(const float* verts, const float* sigmas, int sigma_kind, const float* Rm,
+                              const float* Tv, const float* origins, const float* focal, const float* principal,
+                              int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins, int bin_size,
+                              int tile, uint32_t* rects, int32_t* tile_counts, voge_stream_t stream) {
+    using namespace voge;
+    if (B <= 0 || N <= 0) return 0;
+    if (tile <= 0 || tile > 16 || (use_ref_bins && (bin_size <= 0 || bin_size % tile != 0))) return (int)cudaErrorInvalidValue;
+    if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
+    BinArgs a;
+    a.verts = verts; a.sigmas = sigmas; a.kind = sigma_kind; a.Rm = Rm; a.Tv = Tv; a.origins = origins;
+    a.focal = focal; a.principal = principal; a.B = B; a.N = N; a.H = H; a.W = W;
+    a.neg_log_thr = -logf(thr); a.thr_act = thr_act; a.use_ref_bins = use_ref_bins; a.bin_size = bin_size;
+    a.BH = use_ref_bins ? cdiv(H, bin_size) : 1; a.BW = use_ref_bins ? cdiv(W, bin_size) : 1;
+    a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
+    if (a.TX > 65535 || a.TY > 65535) return (int)cudaErrorInvalidValue;
+    a.rects = reinterpret_cast<uint2*>(rects); a.tile_counts = tile_counts;
+    dim3 grid(min(cdiv(N, 256), kNumSMs * 8), B);
+    bin_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int voge_bin_fill(const uint32_t* rects, const int64_t* tile_offsets, int32_t* cursor, int B, int N,
+                             int H, int W, int tile, int32_t* tile_list, voge_stream_t stream) {
+    using namespace voge;
+    if (B <= 0 || N <= 0) return 0;
+    dim3 grid(min(cdiv(N, 256), kNumSMs * 8), B);
+    bin_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(rects), tile_offsets, cursor,
+                                                             B, N, cdiv(W, tile), cdiv(H, tile), tile_list);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
+                                   const float* rays, const int64_t* tile_offsets, const int32_t* tile_list,
+                                   float thr_act, float absorptivity, int B, int N, int H, int W, int K, int tile,
+                                   int32_t* out_idx, float* out_weight, float* out_len, int64_t* out_valid,
+                                   float* out_act, float* out_dsd, uint64_t* stats, voge_stream_t stream) {
+    using namespace voge;
+    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+    RenderArgs a;
+    a.verts = verts; a.sigmas = sigmas; a.origins = origins; a.rays = rays; a.tile_offsets = tile_offsets;
+    a.tile_list = tile_list; a.thr_act = thr_act; a.omega = absorptivity; a.B = B; a.N = N; a.H = H; a.W = W; a.K = K;
+    a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
+    a.out_idx = out_idx; a.out_weight = out_weight; a.out_len = out_len; a.out_valid = out_valid;
+    a.out_act = out_act; a.out_dsd = out_dsd; a.stats = reinterpret_cast<unsigned long long*>(stats);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (sigma_kind == 1) return dispatch_render<1>(a, s);
+    if (sigma_kind == 3) return dispatch_render<3>(a, s);
+    if (sigma_kind == 9) return dispatch_render<9>(a, s);
+    return (int)cudaErrorInvalidValue;
+}
+
+extern "C" int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
+                                    const float* rays, const int32_t* idx, const float* grad_len,
+                                    const float* grad_act, const float* grad_dsd, int B, int N, int H, int W, int K,
+                                    float* grad_verts, float* grad_sigmas, voge_stream_t stream) {
+    using namespace voge;
+    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+    RenderBwdArgs a{verts, sigmas, sigma_kind, origins, rays, idx, grad_len, grad_act, grad_dsd, B, N, H, W, K,
+                    grad_verts, grad_sigmas};
+    const int64_t warps = (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
+    const int64_t grid = (warps * 32 + 255) / 256;
+    render_bwd_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,64 @@
+"""Fused renderer path: one autograd Function for GaussianRenderer.forward's whole chain
+(reference Renderer.py:130-150: camera-centred copies -> ray_tracing -> aggregation).
+
+Forward : per-view tile culling (voge_bin_count / voge_bin_fill) -> voge_render_forward
+Backward: analytic blend backward (voge_aggregation_backward) -> voge_render_backward, which
+          accumulates straight into (N,3) / compact-sigma gradients for all views of the batch
+          (the reference materialises (B*N,3) and (B*N,3,3) gradient tensors).
+"""
+import math
+
+import torch
+
+from . import _C
+
+TILE_MAX = 16
+
+
+def choose_tile(bin_size, K, use_ref_bins):
+    """Largest tile (<= 16 px, dividing bin_size when the reference bins apply) whose per-thread top-K
+    lists fit in shared memory."""
+    cands = [t for t in range(TILE_MAX, 3, -1) if (not use_ref_bins) or bin_size % t == 0]
+    if not cands:
+        cands = [t for t in range(3, 0, -1) if bin_size % t == 0]
+    for t in cands:
+        px = t * t
+        nt = 256 if px > 128 else (128 if px > 64 else 64)
+        if 6144 + K * nt * 12 + nt * 16 <= 200 * 1024:
+            return t
+    raise RuntimeError("voge_b200: max_assign=%d is too large for the fused renderer" % K)
+
+
+class _RenderFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, sigmas, origins, rays, R, T, focal, principal, image_size, thr, absorptivity, K,
+                use_ref_bins, bin_size):
+        thr_act = -math.log(thr + 1e-10)                       # RayTracing.py:85
+        tile = choose_tile(bin_size, K, use_ref_bins)
+        offsets, tile_list = _C.bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act,
+                                          use_ref_bins, bin_size, tile)
+        need_grad = verts.requires_grad or sigmas.requires_grad
+        idx, weight, tlen, valid, act, dsd = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list,
+                                                               thr_act, absorptivity, K, tile, need_act=need_grad)
+        if need_grad:
+            ctx.save_for_backward(verts, sigmas, origins, rays, idx, tlen, act, dsd)
+        ctx.absorptivity = float(absorptivity)
+        ctx.mark_non_differentiable(idx, valid)
+        return weight, idx, valid, tlen
+
+    @staticmethod
+    def backward(ctx, g_weight, _g_idx, _g_valid, g_len_out):
+        verts, sigmas, origins, rays, idx, tlen, act, dsd = ctx.saved_tensors
+        g_act, g_len, g_dsd = _C.aggregation_backward(act, tlen, dsd, g_weight.contiguous(), ctx.absorptivity)
+        if g_len_out is not None:
+            g_len = g_len + g_len_out
+        g_verts, g_sig = _C.render_backward(verts, sigmas, origins, rays, idx, g_len, g_act, g_dsd,
+                                            need_sigma=ctx.needs_input_grad[1])
+        return (g_verts, g_sig) + (None,) * 12
+
+
+def render_fused(verts, sigmas, origins, rays, R, T, focal, principal, image_size, thr, absorptivity, K,
+                 use_ref_bins, bin_size):
+    """-> (vert_weight, vert_index (packed, -1 padded), valid_num i64, vert_hit_length)."""
+    return _RenderFused.apply(verts, sigmas, origins, rays, R, T, focal, principal, tuple(image_size), float(thr),
+                              float(absorptivity), int(K), bool(use_ref_bins), int(bin_size))
