@@ -154,7 +154,8 @@ int voge_scatter_max(const float* weight, const int32_t* idx, int64_t R, int K,
  *   (1e10 padded), out_valid (B,H,W) int64; out_act/out_dsd optional (NULL to skip);
  *   stats optional 2 x uint64 (pairs filtered, pairs refined), must be zeroed by the caller.
  * voge_render_backward: d(len,act,dsd) (B,H,W,K) -> grad_verts (N,3), grad_sigmas (compact, NULL to
- *   skip); both ZEROED by the caller and accumulated into.                                    */
+ *   skip); both ZEROED by the caller and accumulated into.  Only the first valid_num[r] slots of
+ *   idx are read (merge_final rewrites -1 -> 0 in place, Aggregation.py:131).                                  */
 int voge_bin_count(const float* verts, const float* sigmas, int sigma_kind, const float* R,
                    const float* T, const float* origins, const float* focal, const float* principal,
                    int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins,
@@ -170,6 +171,7 @@ int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind,
                         float* out_act, float* out_dsd, uint64_t* stats, voge_stream_t stream);
 int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind,
                          const float* origins, const float* rays, const int32_t* idx,
+                         const int64_t* valid_num,
                          const float* grad_len, const float* grad_act, const float* grad_dsd,
                          int B, int N, int H, int W, int K,
                          float* grad_verts, float* grad_sigmas, voge_stream_t stream);

@@ -17,15 +17,20 @@ class Fragments(object):
     """Per-pixel top-K hit lists: vert_weight (B,H,W,K) f32, vert_index (B,H,W,K) i32 (-1 = empty,
     packed b*N+n for B > 1), valid_num (B,H,W) i64, vert_hit_length (B,H,W,K) f32 (1e10 = empty)."""
 
-    def __init__(self, vert_weight, vert_index, valid_num, vert_hit_length):
+    def __init__(self, vert_weight, vert_index, valid_num, vert_hit_length, points_per_view=None):
         self.vert_weight = vert_weight
         self.vert_index = vert_index
         self.valid_num = valid_num
         self.vert_hit_length = vert_hit_length
+        # extension: number of Gaussians per view, set by GaussianRenderer.  With several views the
+        # indices are packed b*N+n (as in the reference, whose merge_final then asserts out); knowing N
+        # lets interpolate_attr fold them onto an (N, d) attribute table.
+        self.points_per_view = points_per_view
 
     def _map(self, fn):
         return Fragments(vert_weight=fn(self.vert_weight), vert_index=fn(self.vert_index),
-                         valid_num=fn(self.valid_num), vert_hit_length=fn(self.vert_hit_length))
+                         valid_num=fn(self.valid_num), vert_hit_length=fn(self.vert_hit_length),
+                         points_per_view=self.points_per_view)
 
     def __getitem__(self, item):
         assert len(self.valid_num.shape) == 3, 'Index access is only available when batched.'
@@ -115,7 +120,8 @@ class GaussianRenderer(nn.Module):
         w, idx, valid, ln = render_fused(verts[0], sig, origins, rays, R, T, focal, principal, map_size,
                                          st['thr_activation'], st['absorptivity'], st['max_assign'],
                                          use_ref_bins=(M != -1), bin_size=default_bin_size(map_size))
-        return Fragments(vert_weight=w, vert_index=idx, valid_num=valid, vert_hit_length=ln)
+        return Fragments(vert_weight=w, vert_index=idx, valid_num=valid, vert_hit_length=ln,
+                         points_per_view=verts.shape[1])
 
     def _rays(self, image_size):
         """(directions (B,H,W,3), origins (B,3)).  Real pytorch3d cameras go through pytorch3d's own
@@ -160,12 +166,17 @@ class GaussianRenderer(nn.Module):
             sel_idx=sel_idx, sel_act=sel_act, sel_len=sel_len, sel_dsd=sel_dsd,
             occupation_weight=st['absorptivity'])
         return Fragments(vert_weight=vert_weight, vert_index=vert_index, valid_num=valid_num,
-                         vert_hit_length=vert_hit_length)
+                         vert_hit_length=vert_hit_length, points_per_view=verts.shape[1])
+
+
+def _idx_mod(fragments, vert_attr):
+    n = getattr(fragments, 'points_per_view', None)
+    return int(n) if (n is not None and vert_attr.shape[0] == n) else 0
 
 
 def interpolate_attr(fragments: Fragments, vert_attr: torch.Tensor):
     return merge_final(vert_attr=vert_attr, weight=fragments.vert_weight, valid_num=fragments.valid_num,
-                       vert_assign=fragments.vert_index)
+                       vert_assign=fragments.vert_index, idx_mod=_idx_mod(fragments, vert_attr))
 
 
 def get_silhouette(fragments: Fragments):
@@ -183,7 +194,8 @@ def to_colored_background(fragments: Fragments, colors: torch.Tensor,
     if background_color.numel() == 1:
         background_color = background_color.expand(colors.shape[-1])
     return merge_final(vert_attr=colors, weight=fragments.vert_weight, valid_num=fragments.valid_num,
-                       vert_assign=fragments.vert_index, background=background_color.contiguous(), mask_thr=thr)
+                       vert_assign=fragments.vert_index, background=background_color.contiguous(), mask_thr=thr,
+                       idx_mod=_idx_mod(fragments, colors))
 
 
 def to_white_background(fragments: Fragments, colors: torch.Tensor, thr: float = -1):

@@ -293,7 +293,7 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, thr_ac
     return idx, weight, tlen, valid, act, dsd
 
 
-def render_backward(verts, sigmas, origins, rays, idx, g_len, g_act, g_dsd, need_sigma=True):
+def render_backward(verts, sigmas, origins, rays, idx, valid, g_len, g_act, g_dsd, need_sigma=True):
     verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
     idx, g_len, g_act, g_dsd = i32c(idx), f32c(g_len), f32c(g_act), f32c(g_dsd)
     B, H, W, K = (int(s) for s in idx.shape)
@@ -303,6 +303,7 @@ def render_backward(verts, sigmas, origins, rays, idx, g_len, g_act, g_dsd, need
         g_verts = torch.zeros_like(verts)
         g_sig = torch.zeros_like(sigmas) if need_sigma else None
         check(lib().voge_render_backward(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(origins), ptr(rays),
-                                         ptr(idx), ptr(g_len), ptr(g_act), ptr(g_dsd), B, N, H, W, K, ptr(g_verts),
+                                         ptr(idx), ptr(valid), ptr(g_len), ptr(g_act), ptr(g_dsd), B, N, H, W, K,
+                                         ptr(g_verts),
                                          ptr(g_sig), stream_of(verts)), "render_backward")
     return g_verts, g_sig

@@ -180,8 +180,18 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
             ty0 = by0 * tpb; ty1 = min((by1 + 1) * tpb - 1, a.TY - 1);
         }
         // conservative projected-ellipsoid bound (exact tangent lines of {act < thr + margin})
+        // The bound below is the image of the ellipsoid {(x-mu)^T S (x-mu) < thr}: that IS the set
+        // {act < thr} only for a symmetric S (msk = mu^T S d uses the antisymmetric part too), so
+        // it is applied to (numerically) symmetric S only; fp32-level asymmetry (|S_ij - S_ji| <=
+        // 2^-20 (|S_ij|+|S_ji|), e.g. from R D R^T products) is absorbed by doubling the margin.
         float margin;
-        if (!empty && zv > 0.f && gaussian_margin(mu, S, a.thr_act, margin)) {
+        const float as01 = fabsf(S[1] - S[3]), as02 = fabsf(S[2] - S[6]), as12 = fabsf(S[5] - S[7]);
+        const bool sym_exact = (as01 == 0.f) && (as02 == 0.f) && (as12 == 0.f);
+        const bool sym_near = as01 <= 9.5367e-7f * (fabsf(S[1]) + fabsf(S[3])) &&
+                              as02 <= 9.5367e-7f * (fabsf(S[2]) + fabsf(S[6])) &&
+                              as12 <= 9.5367e-7f * (fabsf(S[5]) + fabsf(S[7]));
+        if (!empty && zv > 0.f && sym_near && gaussian_margin(mu, S, a.thr_act, margin)) {
+            if (!sym_exact) margin *= 2.f;
             const float a00 = S[0], a11 = S[4], a22 = S[8];
             const float a01 = 0.5f * (S[1] + S[3]), a02 = 0.5f * (S[2] + S[6]), a12 = 0.5f * (S[5] + S[7]);
             // inverse of the symmetric part (adjugate / det)
@@ -446,6 +456,8 @@ struct RenderBwdArgs {
     const float* origins;
     const float* rays;
     const int32_t* idx;      // packed
+    const int64_t* valid;    // (B,H,W) number of leading valid slots (idx itself may have been rewritten
+                             // -1 -> 0 by merge_final, reference Aggregation.py:131)
     const float* g_len;
     const float* g_act;
     const float* g_dsd;
@@ -468,9 +480,9 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const RenderBwdArgs a) 
     const int64_t r = ((int64_t)b * a.H + yi) * a.W + xi;
     const float d0 = a.rays[r * 3 + 0], d1 = a.rays[r * 3 + 1], d2 = a.rays[r * 3 + 2];
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
-    for (int k = 0; k < a.K; ++k) {
+    const int cnt = (int)min((int64_t)a.K, a.valid[r]);
+    for (int k = 0; k < cnt; ++k) {
         const int gp = a.idx[r * a.K + k];
-        if (gp < 0) break;   // valid entries come first
         const int g = gp - b * a.N;
         if (g < 0 || g >= a.N) continue;
         const float gl = a.g_len[r * a.K + k], ga = a.g_act[r * a.K + k], gd = a.g_dsd[r * a.K + k];
@@ -575,12 +587,13 @@ extern "C" int voge_render_forward(const float* verts, const float* sigmas, int 
 }
 
 extern "C" int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
-                                    const float* rays, const int32_t* idx, const float* grad_len,
-                                    const float* grad_act, const float* grad_dsd, int B, int N, int H, int W, int K,
+                                    const float* rays, const int32_t* idx, const int64_t* valid,
+                                    const float* grad_len, const float* grad_act, const float* grad_dsd, int B,
+                                    int N, int H, int W, int K,
                                     float* grad_verts, float* grad_sigmas, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
-    RenderBwdArgs a{verts, sigmas, sigma_kind, origins, rays, idx, grad_len, grad_act, grad_dsd, B, N, H, W, K,
+    RenderBwdArgs a{verts, sigmas, sigma_kind, origins, rays, idx, valid, grad_len, grad_act, grad_dsd, B, N, H, W, K,
                     grad_verts, grad_sigmas};
     const int64_t warps = (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
     const int64_t grid = (warps * 32 + 255) / 256;

@@ -41,18 +41,23 @@ class _RenderFused(torch.autograd.Function):
         idx, weight, tlen, valid, act, dsd = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list,
                                                                thr_act, absorptivity, K, tile, need_act=need_grad)
         if need_grad:
-            ctx.save_for_backward(verts, sigmas, origins, rays, idx, tlen, act, dsd)
+            ctx.save_for_backward(verts, sigmas, origins, rays, tlen, act, dsd)
+            # idx / valid are handed out as Fragments.vert_index / valid_num and merge_final rewrites
+            # vert_index in place (-1 -> 0, reference Aggregation.py:131; the reference clones the
+            # tensor for that reason, Renderer.py:145).  They are kept outside autograd's version
+            # tracking instead of cloned: the backward only reads the first valid_num slots.
+            ctx.idx, ctx.valid = idx, valid
         ctx.absorptivity = float(absorptivity)
         ctx.mark_non_differentiable(idx, valid)
         return weight, idx, valid, tlen
 
     @staticmethod
     def backward(ctx, g_weight, _g_idx, _g_valid, g_len_out):
-        verts, sigmas, origins, rays, idx, tlen, act, dsd = ctx.saved_tensors
+        verts, sigmas, origins, rays, tlen, act, dsd = ctx.saved_tensors
         g_act, g_len, g_dsd = _C.aggregation_backward(act, tlen, dsd, g_weight.contiguous(), ctx.absorptivity)
         if g_len_out is not None:
             g_len = g_len + g_len_out
-        g_verts, g_sig = _C.render_backward(verts, sigmas, origins, rays, idx, g_len, g_act, g_dsd,
+        g_verts, g_sig = _C.render_backward(verts, sigmas, origins, rays, ctx.idx, ctx.valid, g_len, g_act, g_dsd,
                                             need_sigma=ctx.needs_input_grad[1])
         return (g_verts, g_sig) + (None,) * 12
 
