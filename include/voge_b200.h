@@ -29,6 +29,11 @@ typedef void* voge_stream_t; /* cudaStream_t */
 int voge_version(void);                       /* ABI version, currently 1               */
 const char* voge_error_string(int code);      /* cudaGetErrorString for a returned code */
 int voge_device_sm_count(int* sm_count);      /* SMs of the current device              */
+/* Peak micro-benchmarks for the roofline denominators MEASURED_PEAKS.json does not hold: `blocks`
+ * CTAs of 256 threads, `iters` rounds of 16 independent FFMA (32 flops) resp. 8 MUFU.EX2 per
+ * thread.  The caller times the launch with CUDA events.  `out` = any 4-byte device buffer.  */
+int voge_peak_fp32(int blocks, int iters, float* out, voge_stream_t stream);
+int voge_peak_sfu(int blocks, int iters, float* out, voge_stream_t stream);
 
 /* ---- coarse binning ----------------------------------------------------------------
  * Replaces `rasterize_points_coarse` (ext.cpp:8 -> RasterizeEllipseCoarseCuda,

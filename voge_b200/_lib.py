@@ -20,6 +20,8 @@ SIGNATURES = {
     "voge_version": (_I, []),
     "voge_error_string": (ctypes.c_char_p, [_I]),
     "voge_device_sm_count": (_I, [_P]),
+    "voge_peak_fp32": (_I, [_I, _I, _P, _P]),
+    "voge_peak_sfu": (_I, [_I, _I, _P, _P]),
     "voge_rasterize_coarse_scratch_elems": (_L, [_I, _I, _I, _I, _I]),
     "voge_rasterize_coarse": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "voge_ray_trace_fine": (_I, [_P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
@@ -59,7 +61,17 @@ def lib():
     return _lib
 
 
+# number of kernels launched through the C ABI since import (bench.py reports it as gpu_launches)
+KERNELS_PER_CALL = {"rasterize_coarse": 3}
+launch_count = 0
+# optional hook: bench.py installs a callable(name) -> context manager to time individual ops with
+# CUDA events on the launching stream
+timing_hook = None
+
+
 def check(code, what):
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(what, 1)
     if code != 0:
         msg = lib().voge_error_string(int(code))
         raise RuntimeError("voge_b200.%s failed: CUDA error %d (%s)" % (what, code, msg.decode() if msg else "?"))
