@@ -22,7 +22,7 @@
 namespace voge {
 
 constexpr int kStageFloats = 12;  // floats of filter data per staged candidate (3 x float4)
-constexpr int kQueueCap = 8;      // per-thread survivor queue depth
+constexpr int kQueueCap = 16;     // per-thread survivor queue depth
 
 // Filter data for one candidate, computed by the staging thread.
 //   v0 = (q0, q1, q2, u')   v1 = (S00, S11, S22, S01+S10)   v2 = (S02+S20, S12+S21, idx, 0)

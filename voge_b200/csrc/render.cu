@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
     float* s_len = s_stage + kRChunk * kStageFloats;                            // [K][NT]
     int* s_idx = reinterpret_cast<int*>(s_len + (size_t)a.K * NT);              // [K][NT]  (later: s_k)
     float* s_E = reinterpret_cast<float*>(s_idx + (size_t)a.K * NT);            // [K][NT]
-    unsigned short* s_queue = reinterpret_cast<unsigned short*>(s_E + (size_t)a.K * NT);   // [kQueueCap][NT]
+    unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_E + (size_t)a.K * NT);     // [kQueueCap][NT]
 
     const int tid = threadIdx.x;
     int blk = blockIdx.x;
@@ -367,17 +367,22 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
             }
         }
         __syncthreads();
-        if (live) {
-            const int cn = min(kRChunk, n - base);
-#pragma unroll 4
-            for (int c = 0; c < cn; ++c) {
-                if (filter_pass(s_stage + c * kStageFloats, r)) {
-                    s_queue[qn * NT + tid] = (unsigned short)c;
-                    if (++qn == kQueueCap) drain();
+        // Every lane runs the loop (dead lanes never pass) so that the drain can be WARP-COLLECTIVE:
+        // when any lane's queue is nearly full all lanes refine what they have queued.  Refining
+        // lane-by-lane as queues fill ran the ~100-instruction exact path with 2-3 active lanes
+        // (ncu profiles/r1: 8.2 threads per instruction overall).
+        const int cn = min(kRChunk, n - base);
+        for (int c = 0; c < cn; c += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c + j < cn && live && filter_pass(s_stage + (c + j) * kStageFloats, r)) {
+                    s_queue[qn * NT + tid] = (unsigned char)(c + j);
+                    ++qn;
                 }
             }
-            drain();
+            if (__any_sync(0xffffffffu, qn > kQueueCap - 4)) drain();
         }
+        if (__any_sync(0xffffffffu, qn > 0)) drain();   // queue entries are chunk-local
     }
     if (a.stats != nullptr) {
         // warp-aggregated counters (diagnostics only; NULL in timed runs)
@@ -426,7 +431,7 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
 
 template <int NT, int KIND>
 static int launch_render(const RenderArgs& a, cudaStream_t stream) {
-    const size_t smem = (size_t)kRChunk * kStageFloats * 4 + (size_t)a.K * NT * 12 + (size_t)kQueueCap * NT * 2;
+    const size_t smem = (size_t)kRChunk * kStageFloats * 4 + (size_t)a.K * NT * 12 + (size_t)kQueueCap * NT;
     if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
     VOGE_CUDA_TRY(cudaFuncSetAttribute(render_fwd_kernel<NT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (long long)a.B * a.TX * a.TY;
