@@ -138,6 +138,64 @@ struct TopK {
     }
 };
 
+// Unsorted top-K buffer of packed 64-bit keys (orderable(len) << 32 | idx) in shared memory,
+// [k][thread] layout.  Appending is O(1) and divergence-free while the buffer is not full (the
+// common case: a pixel rarely collects K hits); once full the current maximum is replaced and
+// re-scanned.  One lock-step insertion sort at the end orders the survivors.  Key order ==
+// lexicographic (len, idx) order == the reference's insertion rule (ray_trace_voge.cu:197-213).
+__device__ __forceinline__ unsigned long long pack_key(float len, int g) {
+    const unsigned b = __float_as_uint(len + 0.f);                       // -0 -> +0
+    const unsigned o = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);       // monotone float -> uint
+    return ((unsigned long long)o << 32) | (unsigned)g;
+}
+
+template <int NT>
+struct TopKU {
+    unsigned long long* s_key;  // [K][NT]
+    int K, tid, cnt, maxpos;
+    unsigned long long limit;   // a key is admitted iff key < limit
+
+    __device__ __forceinline__ void init(unsigned long long* keys, int K_, int tid_) {
+        s_key = keys; K = K_; tid = tid_; cnt = 0; maxpos = 0;
+        limit = pack_key(kEmptyLen, 0);   // len < 1e10 strictly (reference :197 with the 1e10 initial slots)
+    }
+    __device__ __forceinline__ void rescan() {
+        unsigned long long m = s_key[tid];
+        int mp = 0;
+        for (int k = 1; k < K; ++k) {
+            const unsigned long long v = s_key[k * NT + tid];
+            if (v > m) { m = v; mp = k; }
+        }
+        limit = m; maxpos = mp;
+    }
+    __device__ __forceinline__ void insert(float len, int g) {
+        if (len != len) return;                          // NaN never compares less (reference :197)
+        const unsigned long long key = pack_key(len, g);
+        if (!(key < limit)) return;
+        if (cnt < K) {
+            s_key[cnt * NT + tid] = key;
+            if (++cnt == K) rescan();
+        } else {
+            s_key[maxpos * NT + tid] = key;
+            rescan();
+        }
+    }
+    // ascending insertion sort of the cnt keys (all lanes of a warp run it together)
+    __device__ __forceinline__ void sort() {
+        for (int i = 1; i < cnt; ++i) {
+            const unsigned long long key = s_key[i * NT + tid];
+            int j = i;
+            while (j > 0) {
+                const unsigned long long p = s_key[(j - 1) * NT + tid];
+                if (p < key) break;
+                s_key[j * NT + tid] = p;
+                --j;
+            }
+            s_key[j * NT + tid] = key;
+        }
+    }
+};
+
 // Per-pixel state of the filter.
 struct RayMono {
     float d0, d1, d2;
@@ -148,6 +206,11 @@ struct RayMono {
         // the filter margin assumes unit rays (the renderer's always are); for anything else the
         // monomials are poisoned with NaN so that the filter never rejects (f = NaN => refine).
         if (!(fabsf(dxx + dyy + dzz - 1.f) <= 1e-3f)) dxx = __int_as_float(0x7fc00000);
+    }
+    // lanes without a pixel: ksk~ = tr(S) > 0, msk~ = 0 => rejected by every filterable candidate
+    __device__ __forceinline__ void set_dead() {
+        d0 = d1 = d2 = 0.f;
+        dxx = dyy = dzz = 1.f; dxy = dxz = dyz = 0.f;
     }
 };
 

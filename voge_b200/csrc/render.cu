@@ -294,10 +294,9 @@ constexpr int kRChunk = 128;
 template <int NT, int KIND>
 __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_stage = reinterpret_cast<float*>(smem_raw);                        // [kRChunk][12]
-    float* s_len = s_stage + kRChunk * kStageFloats;                            // [K][NT]
-    int* s_idx = reinterpret_cast<int*>(s_len + (size_t)a.K * NT);              // [K][NT]  (later: s_k)
-    float* s_E = reinterpret_cast<float*>(s_idx + (size_t)a.K * NT);            // [K][NT]
+    float* s_stage = reinterpret_cast<float*>(smem_raw);                                    // [kRChunk][12]
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_stage + kRChunk * kStageFloats);  // [K][NT]
+    float* s_E = reinterpret_cast<float*>(s_key + (size_t)a.K * NT);                        // [K][NT]
     unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_E + (size_t)a.K * NT);     // [kQueueCap][NT]
 
     const int tid = threadIdx.x;
@@ -325,11 +324,11 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
 
     RayMono r;
-    r.set(0.f, 0.f, 0.f);
+    r.set_dead();
     if (live) r.set(a.rays[ray * 3 + 0], a.rays[ray * 3 + 1], a.rays[ray * 3 + 2]);
 
-    TopK<NT> top;
-    top.init(s_len, s_idx, a.K, tid);
+    TopKU<NT> top;
+    top.init(s_key, a.K, tid);
 
     const int64_t tile_id = ((int64_t)b * a.TY + ty) * a.TX + tx;
     const int64_t beg = a.tile_offsets[tile_id];
@@ -338,11 +337,14 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
 
     int qn = 0;
     unsigned n_ref = 0;
+    // Warp-collective refine: every lane evaluates what it has queued with the bit-faithful
+    // arithmetic.  (Refining lane-by-lane as queues filled ran the ~100-instruction exact path with
+    // 2-3 active lanes: 8.2 threads per instruction in profiles/ncu_r1_render_fwd_v1.)
     auto drain = [&]() {
         for (int j = 0; j < qn; ++j) {
             const int c = s_queue[j * NT + tid];
             const int g = __float_as_int(s_stage[c * kStageFloats + 10]);
-            if (g < 0) continue;
+            if (g < 0 || !live) continue;
             const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r.d0, r.d1, r.d2);
             if (h.act < a.thr_act) top.insert(h.len, g);
         }
@@ -363,19 +365,15 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
                 load_S<KIND>(a.sigmas, g, S);
                 stage_candidate(s_stage + t * kStageFloats, g, mu, S, a.thr_act);
             } else {
-                stage_invalid(s_stage + t * kStageFloats);
+                stage_invalid(s_stage + t * kStageFloats);   // rejected by the filter: no bounds checks below
             }
         }
         __syncthreads();
-        // Every lane runs the loop (dead lanes never pass) so that the drain can be WARP-COLLECTIVE:
-        // when any lane's queue is nearly full all lanes refine what they have queued.  Refining
-        // lane-by-lane as queues fill ran the ~100-instruction exact path with 2-3 active lanes
-        // (ncu profiles/r1: 8.2 threads per instruction overall).
-        const int cn = min(kRChunk, n - base);
+        const int cn = min(kRChunk, (n - base + 3) & ~3);
         for (int c = 0; c < cn; c += 4) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (c + j < cn && live && filter_pass(s_stage + (c + j) * kStageFloats, r)) {
+                if (filter_pass(s_stage + (c + j) * kStageFloats, r)) {
                     s_queue[qn * NT + tid] = (unsigned char)(c + j);
                     ++qn;
                 }
@@ -386,38 +384,46 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
     }
     if (a.stats != nullptr) {
         // warp-aggregated counters (diagnostics only; NULL in timed runs)
-        unsigned long long f = live ? (unsigned long long)n : 0ull, e = n_ref;
+        unsigned long long f = live ? (unsigned long long)n : 0ull, e = live ? n_ref : 0u;
         for (int o = 16; o > 0; o >>= 1) {
             f += __shfl_down_sync(0xffffffffu, f, o);
             e += __shfl_down_sync(0xffffffffu, e, o);
         }
         if ((tid & 31) == 0) { atomicAdd(a.stats, f); atomicAdd(a.stats + 1, (unsigned long long)e); }
     }
-    if (!live) return;
 
-    // ---- epilogue: exact (len, act, dsd) of the survivors, blend weights, fragment write-out ----
+    // ---- epilogue: order the survivors, exact (len, act, dsd), blend weights, fragment write-out ----
+    top.sort();
+    if (!live) return;
     const int cnt = top.cnt;
     int32_t* o_idx = a.out_idx + ray * a.K;
     float* o_len = a.out_len + ray * a.K;
     float* o_w = a.out_weight + ray * a.K;
+    float2* s_ls = reinterpret_cast<float2*>(s_key);   // the key slots are re-used for (len, sqrt(dsd + 1e-10))
+    float s_min = 3.0e38f;
     for (int k = 0; k < cnt; ++k) {
-        const int g = s_idx[k * NT + tid];
+        const int g = (int)(unsigned)(s_key[k * NT + tid] & 0xffffffffull);
         const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r.d0, r.d1, r.d2);
         o_idx[k] = b * a.N + g;
         o_len[k] = h.len;
         if (a.out_act != nullptr) { a.out_act[ray * a.K + k] = h.act; a.out_dsd[ray * a.K + k] = h.dsd; }
-        s_len[k * NT + tid] = h.len;
-        reinterpret_cast<float*>(s_idx)[k * NT + tid] = sqrtf(h.dsd + 1e-10f);   // Aggregation.py:49
+        const float sk = sqrtf(h.dsd + 1e-10f);                                  // Aggregation.py:49
+        s_ls[k * NT + tid] = make_float2(h.len, sk);
         s_E[k * NT + tid] = expf(-h.act);
+        s_min = fminf(s_min, sk);
     }
-    const float* s_s = reinterpret_cast<const float*>(s_idx);
+    // D_m = sum_k E_k Phi((len_m - len_k) s_k).  The list is sorted by len, so beyond the window
+    // |len_m - len_k| * min_k(s_k) >= 4 the erf is saturated: Phi = 1 below the window (those E_k are
+    // summed without evaluating anything), Phi = 0 above it.
     for (int m = 0; m < cnt; ++m) {
-        const float lm = s_len[m * NT + tid];
+        const float lm = s_ls[m * NT + tid].x;
         float D = 0.f;
         for (int k = 0; k < cnt; ++k) {
+            const float2 lk = s_ls[k * NT + tid];
+            const float dl = lm - lk.x;
+            if (dl * s_min <= -kErfSat) break;          // k and everything behind it: Phi = 0
             const float Ek = s_E[k * NT + tid];
-            if (Ek == 0.f) continue;
-            D += Ek * phi((lm - s_len[k * NT + tid]) * s_s[k * NT + tid]);
+            D += Ek * phi(dl * lk.y);
         }
         const float Em = s_E[m * NT + tid];
         o_w[m] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
