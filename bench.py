@@ -394,7 +394,7 @@ def main():
     rays_total = args.views * H * W
 
     timer = OpTimer()
-    for name in ("bin_views", "render_forward", "render_backward", "aggregation_backward", "merge_final_forward",
+    for name in ("bin_views", "render_forward", "render_backward_fused", "merge_final_forward",
                  "merge_final_backward"):
         timer.wrap(_C, name)
 

@@ -181,6 +181,17 @@ int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind
                          int B, int N, int H, int W, int K,
                          float* grad_verts, float* grad_sigmas, voge_stream_t stream);
 
+/* Fused backward of the renderer: d(weight) (B,H,W,K) and optionally d(hit length) -> grad_verts,
+ * grad_sigmas.  Recomputes the hits from idx (first valid_num[r] slots) instead of reading saved
+ * act/dsd, differentiates the blend analytically (Aggregation.py:30-79) and applies the chain rule of
+ * ray_trace_voge.cu:324-330 in ONE kernel.  Outputs ZEROED by the caller, accumulated into.       */
+int voge_render_backward_fused(const float* verts, const float* sigmas, int sigma_kind,
+                               const float* origins, const float* rays, const int32_t* idx,
+                               const int64_t* valid_num, const float* grad_weight,
+                               const float* grad_len_out, float absorptivity,
+                               int B, int N, int H, int W, int K,
+                               float* grad_verts, float* grad_sigmas, voge_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

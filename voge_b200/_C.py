@@ -307,3 +307,21 @@ def render_backward(verts, sigmas, origins, rays, idx, valid, g_len, g_act, g_ds
                                          ptr(g_verts),
                                          ptr(g_sig), stream_of(verts)), "render_backward")
     return g_verts, g_sig
+
+
+def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_len_out, absorptivity,
+                          need_sigma=True):
+    verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
+    idx, g_weight = i32c(idx), f32c(g_weight)
+    g_len_out = f32c(g_len_out) if g_len_out is not None else None
+    B, H, W, K = (int(s) for s in idx.shape)
+    N = int(verts.shape[0])
+    dev = verts.device
+    with torch.cuda.device(dev):
+        g_verts = torch.zeros_like(verts)
+        g_sig = torch.zeros_like(sigmas) if need_sigma else None
+        check(lib().voge_render_backward_fused(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(origins), ptr(rays),
+                                               ptr(idx), ptr(valid), ptr(g_weight), ptr(g_len_out),
+                                               float(absorptivity), B, N, H, W, K, ptr(g_verts), ptr(g_sig),
+                                               stream_of(verts)), "render_backward_fused")
+    return g_verts, g_sig

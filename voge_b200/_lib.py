@@ -38,6 +38,7 @@ SIGNATURES = {
     "voge_bin_fill": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "voge_render_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P,
                                  _P, _P]),
+    "voge_render_backward_fused": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P]),
     "voge_render_backward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
 }
 

@@ -542,7 +542,193 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const RenderBwdArgs a) 
     }
 }
 
+// ---- fused backward: d(weight), d(len) -> d(verts), d(sigmas) in ONE kernel ----------------------------
+// Recompute, don't store: per pixel the K hits are re-evaluated with the bit-faithful arithmetic
+// (so neither act nor dsd is ever written to HBM by the forward), the blend is differentiated
+// analytically inside the depth window where the erf is not saturated, and the chain rule of
+// ray_trace_voge.cu:324-330 is applied straight into the (N,.) parameter gradients.
+struct FusedBwdArgs {
+    const float* verts;
+    const float* sigmas;
+    int kind;
+    const float* origins;
+    const float* rays;
+    const int32_t* idx;
+    const int64_t* valid;
+    const float* g_weight;   // (B,H,W,K)
+    const float* g_len_out;  // optional (B,H,W,K): gradient arriving on Fragments.vert_hit_length
+    float omega;
+    int B, N, H, W, K;
+    float* grad_verts;
+    float* grad_sigmas;      // may be NULL
+};
+
+__device__ __forceinline__ void geom_grad_accumulate(const FusedBwdArgs& a, int g, float m0, float m1, float m2,
+                                                     const float* S, float d0, float d1, float d2, float ksk,
+                                                     float msk, float gl, float ga, float gd) {
+    const float g_ksk = (ga * msk - gl) * msk / (ksk * ksk) + gd;   // ray_trace_voge.cu:324-326
+    const float g_msk = (gl - 2.f * ga * msk) / ksk;
+    const float g_msm = ga;
+    const float Sd0 = S[0] * d0 + S[1] * d1 + S[2] * d2, Sd1 = S[3] * d0 + S[4] * d1 + S[5] * d2,
+                Sd2 = S[6] * d0 + S[7] * d1 + S[8] * d2;
+    const float Sm0 = S[0] * m0 + S[1] * m1 + S[2] * m2, Sm1 = S[3] * m0 + S[4] * m1 + S[5] * m2,
+                Sm2 = S[6] * m0 + S[7] * m1 + S[8] * m2;
+    const float Stm0 = S[0] * m0 + S[3] * m1 + S[6] * m2, Stm1 = S[1] * m0 + S[4] * m1 + S[7] * m2,
+                Stm2 = S[2] * m0 + S[5] * m1 + S[8] * m2;
+    float* gv = a.grad_verts + 3 * (int64_t)g;
+    atomicAdd(gv + 0, g_msk * Sd0 + g_msm * (Sm0 + Stm0));
+    atomicAdd(gv + 1, g_msk * Sd1 + g_msm * (Sm1 + Stm1));
+    atomicAdd(gv + 2, g_msk * Sd2 + g_msm * (Sm2 + Stm2));
+    if (a.grad_sigmas == nullptr) return;
+    const float dv[3] = {d0, d1, d2}, mv[3] = {m0, m1, m2};
+    if (a.kind == 1) {
+        const float tr = g_ksk * (d0 * d0 + d1 * d1 + d2 * d2) + g_msk * (m0 * d0 + m1 * d1 + m2 * d2) +
+                         g_msm * (m0 * m0 + m1 * m1 + m2 * m2);
+        atomicAdd(a.grad_sigmas + g, 2.f * tr);
+    } else if (a.kind == 3) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            atomicAdd(a.grad_sigmas + 3 * (int64_t)g + i,
+                      2.f * (g_ksk * dv[i] * dv[i] + g_msk * mv[i] * dv[i] + g_msm * mv[i] * mv[i]));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                atomicAdd(a.grad_sigmas + 9 * (int64_t)g + 3 * i + j,
+                          2.f * (g_ksk * dv[i] * dv[j] + g_msk * mv[i] * dv[j] + g_msm * mv[i] * mv[j]));
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t A = (size_t)a.K * NT;
+    float2* s_ls = reinterpret_cast<float2*>(smem_raw);   // (len, s = sqrt(dsd + 1e-10))
+    float* s_E = reinterpret_cast<float*>(s_ls + A);
+    float* s_gl = s_E + A;
+    float* s_gd = s_gl + A;
+    float* s_gE = s_gd + A;
+    const int tid = threadIdx.x;
+    // 8x4 pixel block per warp so that lanes of a warp touch the same Gaussians
+    const int bw = (a.W + 7) / 8, bh = (a.H + 3) / 4;
+    const int64_t wid = ((int64_t)blockIdx.x * NT + tid) >> 5;
+    const int lane = tid & 31;
+    const int64_t per_view = (int64_t)bw * bh;
+    if (wid >= per_view * a.B) return;
+    const int b = (int)(wid / per_view);
+    const int wb = (int)(wid % per_view);
+    const int xi = (wb % bw) * 8 + (lane & 7), yi = (wb / bw) * 4 + (lane >> 3);
+    if (xi >= a.W || yi >= a.H) return;
+    const int64_t r = ((int64_t)b * a.H + yi) * a.W + xi;
+    const int cnt = (int)min((int64_t)a.K, a.valid[r]);
+    if (cnt == 0) return;
+    const float d0 = a.rays[r * 3 + 0], d1 = a.rays[r * 3 + 1], d2 = a.rays[r * 3 + 2];
+    const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
+
+    // ---- recompute the hits ----
+    float s_min = 3.0e38f;
+    for (int k = 0; k < cnt; ++k) {
+        const int g = a.idx[r * a.K + k] - b * a.N;
+        Hit h;
+        h.len = kEmptyLen; h.act = kEmptyLen; h.dsd = 0.f;
+        if (g >= 0 && g < a.N) {
+            float S[9];
+            load_S_dyn(a.kind, a.sigmas, g, S);
+            h = exact_pair(__fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0), __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1),
+                           __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2), S, d0, d1, d2);
+        }
+        const float sk = sqrtf(h.dsd + 1e-10f);
+        s_ls[k * NT + tid] = make_float2(h.len, sk);
+        s_E[k * NT + tid] = expf(-h.act);
+        s_gl[k * NT + tid] = 0.f; s_gd[k * NT + tid] = 0.f; s_gE[k * NT + tid] = 0.f;
+        s_min = fminf(s_min, sk);
+    }
+    // ---- blend backward: w_m = e^.5 exp(-omega D_m) E_m, D_m = sum_k E_k Phi((len_m - len_k) s_k) ----
+    for (int m = 0; m < cnt; ++m) {
+        const float Em = s_E[m * NT + tid];
+        if (Em == 0.f) continue;
+        const float lm = s_ls[m * NT + tid].x;
+        float D = 0.f;
+        for (int k = 0; k < cnt; ++k) {
+            const float2 lk = s_ls[k * NT + tid];
+            const float dl = lm - lk.x;
+            if (dl * s_min <= -kErfSat) break;
+            D += s_E[k * NT + tid] * phi(dl * lk.y);
+        }
+        const float w = expf(-(D * a.omega)) * Em * kInvExpMinusHalf;
+        const float gw = a.g_weight[r * a.K + m];
+        const float gD = -a.omega * w * gw;
+        s_gE[m * NT + tid] += w * gw / Em;      // direct path through the trailing exp(-act_m)
+        if (gD == 0.f) continue;
+        float glm = 0.f;
+        for (int k = 0; k < cnt; ++k) {
+            const float2 lk = s_ls[k * NT + tid];
+            const float dl = lm - lk.x;
+            if (dl * s_min <= -kErfSat) break;      // Phi = 0 and Phi' = 0 from here on
+            const float c = dl * lk.y;
+            if (c >= kErfSat) {                      // saturated: Phi = 1, Phi' = 0
+                s_gE[k * NT + tid] += gD;
+                continue;
+            }
+            const float Ek = s_E[k * NT + tid];
+            s_gE[k * NT + tid] += gD * phi(c);
+            const float gc = gD * Ek * expf(-c * c) * kInvSqrtPi;
+            glm += gc * lk.y;
+            s_gl[k * NT + tid] -= gc * lk.y;
+            s_gd[k * NT + tid] += gc * dl / (2.f * lk.y);
+        }
+        s_gl[m * NT + tid] += glm;
+    }
+    // ---- chain rule into the parameters ----
+    for (int k = 0; k < cnt; ++k) {
+        const int g = a.idx[r * a.K + k] - b * a.N;
+        if (g < 0 || g >= a.N) continue;
+        const float ga = -s_E[k * NT + tid] * s_gE[k * NT + tid];
+        float gl = s_gl[k * NT + tid];
+        if (a.g_len_out != nullptr) gl += a.g_len_out[r * a.K + k];
+        const float gd = s_gd[k * NT + tid];
+        if (ga == 0.f && gl == 0.f && gd == 0.f) continue;
+        float S[9];
+        load_S_dyn(a.kind, a.sigmas, g, S);
+        const float m0 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
+        const float m1 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
+        const float m2 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
+        const Prod9 pd = exact_row_products(d0, d1, d2, S);
+        const Prod9 pm = exact_row_products(m0, m1, m2, S);
+        const float ksk = exact_contract(pd, d0, d1, d2);
+        const float msk = exact_contract(pm, d0, d1, d2);
+        geom_grad_accumulate(a, g, m0, m1, m2, S, d0, d1, d2, ksk, msk, gl, ga, gd);
+    }
+}
+
 }  // namespace voge
+
+extern "C" int voge_render_backward_fused(const float* verts, const float* sigmas, int sigma_kind,
+                                          const float* origins, const float* rays, const int32_t* idx,
+                                          const int64_t* valid, const float* grad_weight,
+                                          const float* grad_len_out, float absorptivity, int B, int N, int H,
+                                          int W, int K, float* grad_verts, float* grad_sigmas,
+                                          voge_stream_t stream) {
+    using namespace voge;
+    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+    FusedBwdArgs a{verts, sigmas, sigma_kind, origins, rays, idx, valid, grad_weight, grad_len_out, absorptivity,
+                   B, N, H, W, K, grad_verts, grad_sigmas};
+    const int64_t warps = (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
+    cudaStream_t s = (cudaStream_t)stream;
+    auto launch = [&](auto kernel, int nt) -> int {
+        const size_t smem = (size_t)K * nt * 24;
+        if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+        VOGE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t grid = (warps * 32 + nt - 1) / nt;
+        kernel<<<(unsigned)grid, nt, smem, s>>>(a);
+        VOGE_LAUNCH_CHECK();
+        return 0;
+    };
+    if (K <= 36) return launch(render_bwd_fused_kernel<128>, 128);
+    if (K <= 140) return launch(render_bwd_fused_kernel<64>, 64);
+    return launch(render_bwd_fused_kernel<32>, 32);
+}
 
 extern "C" int voge_bin_count(const float* verts, const float* sigmas, int sigma_kind, const float* Rm,
                               const float* Tv, const float* origins, const float* focal, const float* principal,

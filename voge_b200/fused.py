@@ -2,9 +2,9 @@
 (reference Renderer.py:130-150: camera-centred copies -> ray_tracing -> aggregation).
 
 Forward : per-view tile culling (voge_bin_count / voge_bin_fill) -> voge_render_forward
-Backward: analytic blend backward (voge_aggregation_backward) -> voge_render_backward, which
-          accumulates straight into (N,3) / compact-sigma gradients for all views of the batch
-          (the reference materialises (B*N,3) and (B*N,3,3) gradient tensors).
+Backward: voge_render_backward_fused -- recompute the hits, analytic blend backward, chain rule straight
+          into (N,3) / compact-sigma gradients for all views of the batch (the reference materialises
+          (B*N,3) and (B*N,3,3) gradient tensors and differentiates ~15 PyTorch ops over (R,K,K)).
 """
 import math
 
@@ -37,28 +37,31 @@ class _RenderFused(torch.autograd.Function):
         tile = choose_tile(bin_size, K, use_ref_bins)
         offsets, tile_list = _C.bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act,
                                           use_ref_bins, bin_size, tile)
-        need_grad = verts.requires_grad or sigmas.requires_grad
-        idx, weight, tlen, valid, act, dsd = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list,
-                                                               thr_act, absorptivity, K, tile, need_act=need_grad)
-        if need_grad:
-            ctx.save_for_backward(verts, sigmas, origins, rays, tlen, act, dsd)
+        idx, weight, tlen, valid, _, _ = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list,
+                                                           thr_act, absorptivity, K, tile, need_act=False)
+        if verts.requires_grad or sigmas.requires_grad:
+            # recompute-not-store: only the inputs are kept; the backward re-evaluates the K hits per
+            # pixel from idx (the reference saves mus, isigmas (B*N copies), rays, sel_idx and the
+            # PyTorch aggregation saves ~10 (R,K,K) tensors)
+            ctx.save_for_backward(verts, sigmas, origins, rays)
             # idx / valid are handed out as Fragments.vert_index / valid_num and merge_final rewrites
             # vert_index in place (-1 -> 0, reference Aggregation.py:131; the reference clones the
             # tensor for that reason, Renderer.py:145).  They are kept outside autograd's version
             # tracking instead of cloned: the backward only reads the first valid_num slots.
             ctx.idx, ctx.valid = idx, valid
         ctx.absorptivity = float(absorptivity)
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(idx, valid)
         return weight, idx, valid, tlen
 
     @staticmethod
     def backward(ctx, g_weight, _g_idx, _g_valid, g_len_out):
-        verts, sigmas, origins, rays, tlen, act, dsd = ctx.saved_tensors
-        g_act, g_len, g_dsd = _C.aggregation_backward(act, tlen, dsd, g_weight.contiguous(), ctx.absorptivity)
-        if g_len_out is not None:
-            g_len = g_len + g_len_out
-        g_verts, g_sig = _C.render_backward(verts, sigmas, origins, rays, ctx.idx, ctx.valid, g_len, g_act, g_dsd,
-                                            need_sigma=ctx.needs_input_grad[1])
+        verts, sigmas, origins, rays = ctx.saved_tensors
+        if g_weight is None:
+            g_weight = torch.zeros(ctx.idx.shape, dtype=torch.float32, device=ctx.idx.device)
+        g_verts, g_sig = _C.render_backward_fused(verts, sigmas, origins, rays, ctx.idx, ctx.valid,
+                                                  g_weight.contiguous(), g_len_out, ctx.absorptivity,
+                                                  need_sigma=ctx.needs_input_grad[1])
         return (g_verts, g_sig) + (None,) * 12
 
 
