@@ -412,21 +412,26 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
         s_E[k * NT + tid] = expf(-h.act);
         s_min = fminf(s_min, sk);
     }
-    // D_m = sum_k E_k Phi((len_m - len_k) s_k).  The list is sorted by len, so beyond the window
-    // |len_m - len_k| * min_k(s_k) >= 4 the erf is saturated: Phi = 1 below the window (those E_k are
-    // summed without evaluating anything), Phi = 0 above it.
-    for (int m = 0; m < cnt; ++m) {
-        const float lm = s_ls[m * NT + tid].x;
-        float D = 0.f;
-        for (int k = 0; k < cnt; ++k) {
-            const float2 lk = s_ls[k * NT + tid];
-            const float dl = lm - lk.x;
-            if (dl * s_min <= -kErfSat) break;          // k and everything behind it: Phi = 0
-            const float Ek = s_E[k * NT + tid];
-            D += Ek * phi(dl * lk.y);
+    // D_m = sum_k E_k Phi((len_m - len_k) s_k).  The list is sorted by len, so outside the window
+    // |len_m - len_k| * min_k(s_k) < 4 the erf is saturated: Phi = 1 for k < lo(m) (their E_k are
+    // carried in a running prefix sum -- lo(m) only moves forward), Phi = 0 behind the window.
+    // The summation order is the plain k = 0..cnt-1 order of the stand-alone aggregation kernel.
+    {
+        int lo = 0;
+        float SE = 0.f;
+        for (int m = 0; m < cnt; ++m) {
+            const float lm = s_ls[m * NT + tid].x;
+            while (lo < m && (lm - s_ls[lo * NT + tid].x) * s_min >= kErfSat) { SE += s_E[lo * NT + tid]; ++lo; }
+            float D = SE;
+            for (int k = lo; k < cnt; ++k) {
+                const float2 lk = s_ls[k * NT + tid];
+                const float dl = lm - lk.x;
+                if (dl * s_min <= -kErfSat) break;
+                D += s_E[k * NT + tid] * phi(dl * lk.y);
+            }
+            const float Em = s_E[m * NT + tid];
+            o_w[m] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
         }
-        const float Em = s_E[m * NT + tid];
-        o_w[m] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
     }
     for (int k = cnt; k < a.K; ++k) {
         o_idx[k] = -1; o_len[k] = kEmptyLen; o_w[k] = 0.f;
@@ -609,6 +614,7 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
     float* s_gl = s_E + A;
     float* s_gd = s_gl + A;
     float* s_gE = s_gd + A;
+    float* s_gD = s_gE + A;
     const int tid = threadIdx.x;
     // 8x4 pixel block per warp so that lanes of a warp touch the same Gaussians
     const int bw = (a.W + 7) / 8, bh = (a.H + 3) / 4;
@@ -645,40 +651,68 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
         s_min = fminf(s_min, sk);
     }
     // ---- blend backward: w_m = e^.5 exp(-omega D_m) E_m, D_m = sum_k E_k Phi((len_m - len_k) s_k) ----
-    for (int m = 0; m < cnt; ++m) {
-        const float Em = s_E[m * NT + tid];
-        if (Em == 0.f) continue;
-        const float lm = s_ls[m * NT + tid].x;
-        float D = 0.f;
-        for (int k = 0; k < cnt; ++k) {
-            const float2 lk = s_ls[k * NT + tid];
-            const float dl = lm - lk.x;
-            if (dl * s_min <= -kErfSat) break;
-            D += s_E[k * NT + tid] * phi(dl * lk.y);
-        }
-        const float w = expf(-(D * a.omega)) * Em * kInvExpMinusHalf;
-        const float gw = a.g_weight[r * a.K + m];
-        const float gD = -a.omega * w * gw;
-        s_gE[m * NT + tid] += w * gw / Em;      // direct path through the trailing exp(-act_m)
-        if (gD == 0.f) continue;
-        float glm = 0.f;
-        for (int k = 0; k < cnt; ++k) {
-            const float2 lk = s_ls[k * NT + tid];
-            const float dl = lm - lk.x;
-            if (dl * s_min <= -kErfSat) break;      // Phi = 0 and Phi' = 0 from here on
-            const float c = dl * lk.y;
-            if (c >= kErfSat) {                      // saturated: Phi = 1, Phi' = 0
-                s_gE[k * NT + tid] += gD;
-                continue;
+    // Sorted lens => only the window |len_m - len_k| * s_min < 4 needs erf / exp; k < lo(m) has Phi = 1,
+    // Phi' = 0 (prefix sum of E forward; their d/dE_k = sum of gD_m is applied in one descending sweep).
+    {
+        int lo = 0;
+        float SE = 0.f;
+        for (int m = 0; m < cnt; ++m) {
+            const float Em = s_E[m * NT + tid];
+            const float lm = s_ls[m * NT + tid].x;
+            while (lo < m && (lm - s_ls[lo * NT + tid].x) * s_min >= kErfSat) { SE += s_E[lo * NT + tid]; ++lo; }
+            float gD = 0.f;
+            if (Em != 0.f) {
+                float D = SE;
+                for (int k = lo; k < cnt; ++k) {
+                    const float2 lk = s_ls[k * NT + tid];
+                    const float dl = lm - lk.x;
+                    if (dl * s_min <= -kErfSat) break;
+                    D += s_E[k * NT + tid] * phi(dl * lk.y);
+                }
+                const float w = expf(-(D * a.omega)) * Em * kInvExpMinusHalf;
+                const float gw = a.g_weight[r * a.K + m];
+                gD = -a.omega * w * gw;
+                s_gE[m * NT + tid] += w * gw / Em;      // direct path through the trailing exp(-act_m)
+                if (gD != 0.f) {
+                    float glm = 0.f;
+                    for (int k = lo; k < cnt; ++k) {
+                        const float2 lk = s_ls[k * NT + tid];
+                        const float dl = lm - lk.x;
+                        if (dl * s_min <= -kErfSat) break;      // Phi = 0 and Phi' = 0 from here on
+                        const float c = dl * lk.y;
+                        if (c >= kErfSat) {                      // saturated inside the s_min window
+                            s_gE[k * NT + tid] += gD;
+                            continue;
+                        }
+                        const float Ek = s_E[k * NT + tid];
+                        s_gE[k * NT + tid] += gD * phi(c);
+                        const float gc = gD * Ek * expf(-c * c) * kInvSqrtPi;
+                        glm += gc * lk.y;
+                        s_gl[k * NT + tid] -= gc * lk.y;
+                        s_gd[k * NT + tid] += gc * dl / (2.f * lk.y);
+                    }
+                    s_gl[m * NT + tid] += glm;
+                }
             }
-            const float Ek = s_E[k * NT + tid];
-            s_gE[k * NT + tid] += gD * phi(c);
-            const float gc = gD * Ek * expf(-c * c) * kInvSqrtPi;
-            glm += gc * lk.y;
-            s_gl[k * NT + tid] -= gc * lk.y;
-            s_gd[k * NT + tid] += gc * dl / (2.f * lk.y);
+            s_gD[m * NT + tid] = gD;
         }
-        s_gl[m * NT + tid] += glm;
+        // k < lo(m) received Phi = 1 from m: dD_m/dE_k = 1.  lo(m) is non-decreasing, so walking m
+        // downwards every k gets exactly one add of the running suffix sum of gD.
+        float acc = 0.f;
+        int L = cnt;    // lo(m) for the current m, found with a descending pointer
+        for (int m = cnt - 1; m >= 0; --m) {
+            const float lm = s_ls[m * NT + tid].x;
+            L = min(L, m);
+            while (L > 0 && (lm - s_ls[(L - 1) * NT + tid].x) * s_min < kErfSat) --L;
+            acc += s_gD[m * NT + tid];
+            int Lp = 0;
+            if (m > 0) {
+                const float lp = s_ls[(m - 1) * NT + tid].x;
+                Lp = min(L, m - 1);
+                while (Lp > 0 && (lp - s_ls[(Lp - 1) * NT + tid].x) * s_min < kErfSat) --Lp;
+            }
+            for (int k = Lp; k < L; ++k) s_gE[k * NT + tid] += acc;
+        }
     }
     // ---- chain rule into the parameters ----
     for (int k = 0; k < cnt; ++k) {
@@ -717,7 +751,7 @@ extern "C" int voge_render_backward_fused(const float* verts, const float* sigma
     const int64_t warps = (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
     cudaStream_t s = (cudaStream_t)stream;
     auto launch = [&](auto kernel, int nt) -> int {
-        const size_t smem = (size_t)K * nt * 24;
+        const size_t smem = (size_t)K * nt * 28;
         if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
         VOGE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t grid = (warps * 32 + nt - 1) / nt;
@@ -725,8 +759,8 @@ extern "C" int voge_render_backward_fused(const float* verts, const float* sigma
         VOGE_LAUNCH_CHECK();
         return 0;
     };
-    if (K <= 36) return launch(render_bwd_fused_kernel<128>, 128);
-    if (K <= 140) return launch(render_bwd_fused_kernel<64>, 64);
+    if (K <= 32) return launch(render_bwd_fused_kernel<128>, 128);
+    if (K <= 120) return launch(render_bwd_fused_kernel<64>, 64);
     return launch(render_bwd_fused_kernel<32>, 32);
 }
 
