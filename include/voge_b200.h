@@ -113,12 +113,14 @@ int voge_merge_final(const float* attr, const float* weight, const int32_t* idx,
                      int64_t R, int K, int C, int idx_mod, int n_attr,
                      float* out, voge_stream_t stream);
 
-/* Backward of voge_merge_final: grad_attr (n_attr,C) must be ZEROED by the caller and is
- * accumulated into; grad_weight (R,K) is written in full.  Either may be NULL.            */
+/* Backward of voge_merge_final: grad_attr must be ZEROED by the caller and is accumulated into;
+ * its layout is (n_attr,C), or -- packed4 != 0 and C <= 4 -- (n_attr,4) zero-padded rows so that one
+ * 16-byte vector reduction per hit can be used.  grad_weight (R,K) is written in full.
+ * Either may be NULL.                                                                       */
 int voge_merge_final_backward(const float* attr, const float* weight, const int32_t* idx,
                               const int64_t* valid_num, const float* background,
                               float mask_thr, const float* out, const float* grad_out,
-                              int64_t R, int K, int C, int idx_mod, int n_attr,
+                              int64_t R, int K, int C, int idx_mod, int n_attr, int packed4,
                               float* grad_attr, float* grad_weight, voge_stream_t stream);
 
 /* ---- sampling (inverse rendering) --------------------------------------------------------
@@ -184,13 +186,16 @@ int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind
 /* Fused backward of the renderer: d(weight) (B,H,W,K) and optionally d(hit length) -> grad_verts,
  * grad_sigmas.  Recomputes the hits from idx (first valid_num[r] slots) instead of reading saved
  * act/dsd, differentiates the blend analytically (Aggregation.py:30-79) and applies the chain rule of
- * ray_trace_voge.cu:324-330 in ONE kernel.  Outputs ZEROED by the caller, accumulated into.       */
+ * ray_trace_voge.cu:324-330 in ONE kernel.  grad_packed is ONE buffer of per-Gaussian records
+ * [d verts(3) | d sigma] padded to float4 units so that 16-byte vector reductions can be used:
+ * kind 1: (N,4) = [gx,gy,gz,gsigma]; kind 3: (N,8) = [gx,gy,gz,0,gs0,gs1,gs2,0];
+ * kind 9: (N,12) = [gx,gy,gz,gs00..gs22].  ZEROED by the caller, accumulated into.            */
 int voge_render_backward_fused(const float* verts, const float* sigmas, int sigma_kind,
                                const float* origins, const float* rays, const int32_t* idx,
                                const int64_t* valid_num, const float* grad_weight,
                                const float* grad_len_out, float absorptivity,
                                int B, int N, int H, int W, int K,
-                               float* grad_verts, float* grad_sigmas, voge_stream_t stream);
+                               float* grad_packed, int need_sigma, voge_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -225,13 +225,19 @@ def merge_final_backward(attr, weight, idx, valid_num, grad_out, background=None
     R = idx.numel() // max(K, 1)
     dev = attr.device
     with torch.cuda.device(dev):
-        g_attr = torch.zeros_like(attr) if need_attr else None
+        packed4 = need_attr and C <= 4
+        if packed4:
+            g_attr = torch.zeros((attr.shape[0], 4), dtype=torch.float32, device=dev)
+        else:
+            g_attr = torch.zeros_like(attr) if need_attr else None
         g_w = torch.empty_like(weight) if need_weight else None
         bg = f32c(background) if background is not None else None
         check(lib().voge_merge_final_backward(ptr(attr), ptr(weight), ptr(idx), ptr(valid_num), ptr(bg),
                                               float(mask_thr), None, ptr(grad_out), R, K, C, int(idx_mod),
-                                              int(attr.shape[0]), ptr(g_attr), ptr(g_w), stream_of(attr)),
-              "merge_final_backward")
+                                              int(attr.shape[0]), int(packed4), ptr(g_attr), ptr(g_w),
+                                              stream_of(attr)), "merge_final_backward")
+        if packed4:
+            g_attr = g_attr[:, :C].contiguous()
     return g_attr, g_w
 
 
@@ -316,12 +322,22 @@ def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_
     g_len_out = f32c(g_len_out) if g_len_out is not None else None
     B, H, W, K = (int(s) for s in idx.shape)
     N = int(verts.shape[0])
+    kind = sigma_kind(sigmas)
+    width = {1: 4, 3: 8, 9: 12}[kind]
     dev = verts.device
     with torch.cuda.device(dev):
-        g_verts = torch.zeros_like(verts)
-        g_sig = torch.zeros_like(sigmas) if need_sigma else None
-        check(lib().voge_render_backward_fused(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(origins), ptr(rays),
+        packed = torch.zeros((N, width), dtype=torch.float32, device=dev)
+        check(lib().voge_render_backward_fused(ptr(verts), ptr(sigmas), kind, ptr(origins), ptr(rays),
                                                ptr(idx), ptr(valid), ptr(g_weight), ptr(g_len_out),
-                                               float(absorptivity), B, N, H, W, K, ptr(g_verts), ptr(g_sig),
+                                               float(absorptivity), B, N, H, W, K, ptr(packed), int(bool(need_sigma)),
                                                stream_of(verts)), "render_backward_fused")
+    g_verts = packed[:, :3].contiguous()
+    g_sig = None
+    if need_sigma:
+        if kind == 1:
+            g_sig = packed[:, 3].contiguous()
+        elif kind == 3:
+            g_sig = packed[:, 4:7].contiguous()
+        else:
+            g_sig = packed[:, 3:12].reshape(N, 3, 3)
     return g_verts, g_sig

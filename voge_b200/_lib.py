@@ -30,7 +30,7 @@ SIGNATURES = {
     "voge_aggregation": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _P, _P]),
     "voge_aggregation_backward": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _P, _P, _P]),
     "voge_merge_final": (_I, [_P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _I, _P, _P]),
-    "voge_merge_final_backward": (_I, [_P, _P, _P, _P, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P, _P, _P]),
+    "voge_merge_final_backward": (_I, [_P, _P, _P, _P, _P, _F, _P, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P]),
     "voge_sample": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P]),
     "voge_sample_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P]),
     "voge_scatter_max": (_I, [_P, _P, _L, _I, _I, _P, _P]),
@@ -38,7 +38,7 @@ SIGNATURES = {
     "voge_bin_fill": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "voge_render_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P,
                                  _P, _P]),
-    "voge_render_backward_fused": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "voge_render_backward_fused": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _I, _P]),
     "voge_render_backward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
 }
 

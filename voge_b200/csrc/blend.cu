@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) merge_bwd_kernel(const float* __restrict_
                                                         const int64_t* __restrict__ valid_num,
                                                         const float* __restrict__ background, float mask_thr,
                                                         const float* __restrict__ g_out, int64_t R, int K,
-                                                        int C, int idx_mod, int n_attr, float* __restrict__ g_attr,
+                                                        int C, int idx_mod, int n_attr, int packed4, float* __restrict__ g_attr,
                                                         float* __restrict__ g_weight) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
@@ -205,11 +205,16 @@ __global__ void __launch_bounds__(256) merge_bwd_kernel(const float* __restrict_
             if (g < 0) g = 0;
             if (idx_mod > 0) g %= idx_mod;
             const float w = weight[r * K + k];
+            float v4[4] = {0.f, 0.f, 0.f, 0.f};
             for (int c = 0; c < C && g < n_attr; ++c) {
                 const float go = bg ? gol[c] : g_out[r * C + c];
                 gw = fmaf(go, __ldg(attr + (int64_t)g * C + c), gw);
-                if (g_attr != nullptr && w != 0.f && go != 0.f) atomicAdd(g_attr + (int64_t)g * C + c, w * go);
+                if (packed4) v4[c] = w * go;
+                else if (g_attr != nullptr && w != 0.f && go != 0.f) atomicAdd(g_attr + (int64_t)g * C + c, w * go);
             }
+            // C <= 4 with a (n_attr, 4) padded gradient table: ONE 16-byte vector reduction per hit
+            if (packed4 && g_attr != nullptr && w != 0.f && g < n_attr)
+                atomicAdd(reinterpret_cast<float4*>(g_attr + 4 * (int64_t)g), make_float4(v4[0], v4[1], v4[2], v4[3]));
         }
         if (g_weight != nullptr) g_weight[r * K + k] = gw;
     }
@@ -280,14 +285,15 @@ extern "C" int voge_merge_final(const float* attr, const float* weight, const in
 extern "C" int voge_merge_final_backward(const float* attr, const float* weight, const int32_t* idx,
                                          const int64_t* valid_num, const float* background,
                                          float mask_thr, const float* out, const float* grad_out,
-                                         int64_t R, int K, int C, int idx_mod, int n_attr, float* grad_attr,
-                                         float* grad_weight, voge_stream_t stream) {
+                                         int64_t R, int K, int C, int idx_mod, int n_attr, int packed4,
+                                         float* grad_attr, float* grad_weight, voge_stream_t stream) {
     using namespace voge;
     (void)out;
     if (R <= 0 || C <= 0) return 0;
     if (background != nullptr && C > kMaxBgChannels) return (int)cudaErrorInvalidValue;
     merge_bwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        attr, weight, idx, valid_num, background, mask_thr, grad_out, R, K, C, idx_mod, n_attr, grad_attr, grad_weight);
+        attr, weight, idx, valid_num, background, mask_thr, grad_out, R, K, C, idx_mod, n_attr, packed4 && C <= 4, grad_attr,
+        grad_weight);
     VOGE_LAUNCH_CHECK();
     return 0;
 }
