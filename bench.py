@@ -462,7 +462,7 @@ def main():
     # ---- roofline of the dominant kernel (rank 0; work counted for rank 0's views) ----
     peaks = measure_peaks(dev)
     n_pairs, ref_bin = count_ref_pairs(wl, args, dev)
-    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
     with torch.no_grad():
         st_kw = {}
         orig = _C.render_forward
@@ -491,6 +491,7 @@ def main():
         "reference_bin_size": ref_bin, "avg_launch_ms": fwd["avg_ms"], "launches_timed": fwd["launches"],
         "pairs_filtered_per_launch": int(stats[0].item()) / max(len(wl["renderers"]), 1),
         "pairs_refined_per_launch": int(stats[1].item()) / max(len(wl["renderers"]), 1),
+        "pixels_overflowing_hit_buffer": int(stats[2].item()),
         "hits_per_launch": hits / max(len(wl["renderers"]), 1),
         "fragment_write_GBps": frag_bytes / (fwd["avg_ms"] * 1e-3) / 1e9,
         "hbm_peak_GBps": mp.get("hbm_gbs"),

@@ -154,12 +154,14 @@ int voge_scatter_max(const float* weight, const int32_t* idx, int64_t R, int K,
  * voge_bin_count: per (view, Gaussian) tile rectangle = [reference coarse-bin test of
  *   RayTracing.py:33-57 + rasterize_coarse.cu:20-42,:116-130 at `bin_size` px, if use_ref_bins]
  *   AND [conservative projected-ellipsoid bound]; tiles are `tile` x `tile` px (tile <= 16, divides
- *   bin_size).  rects (B,N,2) uint32 out; tile_counts (B,TY,TX) int32 must be ZEROED by the caller.
+ *   bin_size).  rects (B,N,2) uint32 out = conservative PIXEL rectangle x0|x1<<16, y0|y1<<16 (inclusive,
+ *   empty if x0 > x1); tile_counts (B,TY,TX) int32 must be ZEROED by the caller.
  * voge_bin_fill: scatters Gaussian indices into tile_list using tile_offsets (B*TY*TX+1, int64,
  *   exclusive scan of tile_counts); cursor (B*TY*TX) int32 must be ZEROED by the caller.
  * voge_render_forward: fragments.  out_idx (B,H,W,K) packed b*N+n / -1, out_weight, out_len
  *   (1e10 padded), out_valid (B,H,W) int64; out_act/out_dsd optional (NULL to skip);
- *   stats optional 2 x uint64 (pairs filtered, pairs refined), must be zeroed by the caller.
+ *   rects = the (B,N,2) rectangles of voge_bin_count (pixel units);
+ *   stats optional 4 x uint64 (pairs evaluated, pairs refined, overflowed pixels, -), zeroed by the caller.
  * voge_render_backward: d(len,act,dsd) (B,H,W,K) -> grad_verts (N,3), grad_sigmas (compact, NULL to
  *   skip); both ZEROED by the caller and accumulated into.  Only the first valid_num[r] slots of
  *   idx are read (merge_final rewrites -1 -> 0 in place, Aggregation.py:131).                                  */
@@ -172,7 +174,7 @@ int voge_bin_fill(const uint32_t* rects, const int64_t* tile_offsets, int32_t* c
                   int H, int W, int tile, int32_t* tile_list, voge_stream_t stream);
 int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind,
                         const float* origins, const float* rays, const int64_t* tile_offsets,
-                        const int32_t* tile_list, float thr_act, float absorptivity,
+                        const int32_t* tile_list, const uint32_t* rects, float thr_act, float absorptivity,
                         int B, int N, int H, int W, int K, int tile,
                         int32_t* out_idx, float* out_weight, float* out_len, int64_t* out_valid,
                         float* out_act, float* out_dsd, uint64_t* stats, voge_stream_t stream);

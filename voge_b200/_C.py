@@ -255,7 +255,8 @@ def sigma_kind(sigmas):
 
 def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act, use_ref_bins, bin_size,
               tile):
-    """-> (tile_offsets (B*TY*TX+1,) int64, tile_list (total,) int32).  One host sync (the total)."""
+    """-> (tile_offsets (B*TY*TX+1,) int64, tile_list (total,) int32, rects (B,N,2) int32).
+    One host sync (the total number of list entries)."""
     verts, sigmas = f32c(verts), f32c(sigmas)
     R, T, origins, focal, principal = f32c(R), f32c(T), f32c(origins), f32c(focal), f32c(principal)
     B, N = int(R.shape[0]), int(verts.shape[0])
@@ -276,10 +277,10 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
         cursor = torch.zeros((B * TY * TX,), dtype=torch.int32, device=dev)
         check(lib().voge_bin_fill(ptr(rects), ptr(offsets), ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
                                   stream_of(verts)), "bin_fill")
-    return offsets, tile_list
+    return offsets, tile_list, rects
 
 
-def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, thr_act, absorptivity, K, tile,
+def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects, thr_act, absorptivity, K, tile,
                    need_act=True, stats=None):
     verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
     B, H, W = int(rays.shape[0]), int(rays.shape[1]), int(rays.shape[2])
@@ -293,7 +294,7 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, thr_ac
         act = torch.empty((B, H, W, K), dtype=torch.float32, device=dev) if need_act else None
         dsd = torch.empty((B, H, W, K), dtype=torch.float32, device=dev) if need_act else None
         check(lib().voge_render_forward(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(origins), ptr(rays),
-                                        ptr(tile_offsets), ptr(tile_list), float(thr_act), float(absorptivity),
+                                        ptr(tile_offsets), ptr(tile_list), ptr(rects), float(thr_act), float(absorptivity),
                                         B, N, H, W, K, int(tile), ptr(idx), ptr(weight), ptr(tlen), ptr(valid),
                                         ptr(act), ptr(dsd), ptr(stats), stream_of(verts)), "render_forward")
     return idx, weight, tlen, valid, act, dsd

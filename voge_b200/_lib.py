@@ -36,8 +36,8 @@ SIGNATURES = {
     "voge_scatter_max": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "voge_bin_count": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _P, _P, _P]),
     "voge_bin_fill": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
-    "voge_render_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P,
-                                 _P, _P]),
+    "voge_render_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P,
+                                 _P, _P, _P]),
     "voge_render_backward_fused": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _I, _P]),
     "voge_render_backward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
 }

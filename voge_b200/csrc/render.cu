@@ -88,7 +88,7 @@ struct BinArgs {
     int B, N, H, W;
     float neg_log_thr, thr_act;
     int use_ref_bins, bin_size, BH, BW, tile, TX, TY;
-    uint2* rects;            // (B,N): x = x0 | x1 << 16, y = y0 | y1 << 16 in tile units; empty if x0 > x1
+    uint2* rects;            // (B,N): x = x0 | x1 << 16, y = y0 | y1 << 16 in PIXELS (inclusive); empty if x0 > x1
     int32_t* tile_counts;    // (B, TY*TX)
 };
 
@@ -136,7 +136,6 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
     const float sc = 0.5f * (float)min(a.H, a.W);
     const float half_x = __fdiv_rn(ndc_range(a.W, a.H) / 2.0f, (float)a.W);
     const float half_y = __fdiv_rn(ndc_range(a.H, a.W) / 2.0f, (float)a.H);
-    const int tpb = a.use_ref_bins ? a.bin_size / a.tile : 1;
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < a.N; g += gridDim.x * blockDim.x) {
         float mu[3], S[9];
         mu[0] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
@@ -147,7 +146,8 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
         const float xv = mu[0] * R[0] + mu[1] * R[3] + mu[2] * R[6];
         const float yv = mu[0] * R[1] + mu[1] * R[4] + mu[2] * R[7];
         const float zv = mu[0] * R[2] + mu[1] * R[5] + mu[2] * R[8];
-        int tx0 = 0, tx1 = a.TX - 1, ty0 = 0, ty1 = a.TY - 1;
+        // conservative pixel rectangle in which the Gaussian can be a hit (inclusive bounds)
+        int x0 = 0, x1 = a.W - 1, y0 = 0, y1 = a.H - 1;
         bool empty = false;
         if (a.use_ref_bins) {
             if (zv < 0.f) empty = true;   // rasterize_coarse.cu:35
@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
             ref_bin_range(xn - rx, xn + rx, a.BW, a.bin_size, a.W, a.H, half_x, sc, bx0, bx1);
             ref_bin_range(yn - ry, yn + ry, a.BH, a.bin_size, a.H, a.W, half_y, sc, by0, by1);
             if (bx0 > bx1 || by0 > by1) empty = true;
-            tx0 = bx0 * tpb; tx1 = min((bx1 + 1) * tpb - 1, a.TX - 1);
-            ty0 = by0 * tpb; ty1 = min((by1 + 1) * tpb - 1, a.TY - 1);
+            x0 = bx0 * a.bin_size; x1 = min((bx1 + 1) * a.bin_size - 1, a.W - 1);
+            y0 = by0 * a.bin_size; y1 = min((by1 + 1) * a.bin_size - 1, a.H - 1);
         }
         // conservative projected-ellipsoid bound (exact tangent lines of {act < thr + margin})
         // The bound below is the image of the ellipsoid {(x-mu)^T S (x-mu) < thr}: that IS the set
@@ -231,19 +231,19 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
                     } else {
                         const int pxl = (int)ceilf(fmaxf(xs_lo, 0.f)), pxh = (int)floorf(fminf(xs_hi, fW - 1.f));
                         const int pyl = (int)ceilf(fmaxf(ys_lo, 0.f)), pyh = (int)floorf(fminf(ys_hi, fH - 1.f));
-                        if (pxl > pxh || pyl > pyh) empty = true;
-                        tx0 = max(tx0, pxl / a.tile); tx1 = min(tx1, pxh / a.tile);
-                        ty0 = max(ty0, pyl / a.tile); ty1 = min(ty1, pyh / a.tile);
+                        x0 = max(x0, pxl); x1 = min(x1, pxh);
+                        y0 = max(y0, pyl); y1 = min(y1, pyh);
                     }
                 }
             }
         }
-        if (tx0 > tx1 || ty0 > ty1) empty = true;
+        if (x0 > x1 || y0 > y1) empty = true;
         uint2 rc;
         if (empty) {
             rc = make_uint2(1u, 0u);
         } else {
-            rc = make_uint2((unsigned)tx0 | ((unsigned)tx1 << 16), (unsigned)ty0 | ((unsigned)ty1 << 16));
+            rc = make_uint2((unsigned)x0 | ((unsigned)x1 << 16), (unsigned)y0 | ((unsigned)y1 << 16));
+            const int tx0 = x0 / a.tile, tx1 = x1 / a.tile, ty0 = y0 / a.tile, ty1 = y1 / a.tile;
             int32_t* cnt = a.tile_counts + (int64_t)b * a.TX * a.TY;
             for (int ty = ty0; ty <= ty1; ++ty)
                 for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt + ty * a.TX + tx, 1);
@@ -255,12 +255,12 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
 __global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__ rects,
                                                        const int64_t* __restrict__ tile_offsets,
                                                        int32_t* __restrict__ cursor, int B, int N, int TX, int TY,
-                                                       int32_t* __restrict__ tile_list) {
+                                                       int tile, int32_t* __restrict__ tile_list) {
     const int b = blockIdx.y;
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
         const uint2 rc = rects[(int64_t)b * N + g];
-        const int tx0 = rc.x & 0xffff, tx1 = rc.x >> 16, ty0 = rc.y & 0xffff, ty1 = rc.y >> 16;
-        if (tx0 > tx1) continue;
+        if ((rc.x & 0xffff) > (rc.x >> 16)) continue;
+        const int tx0 = (rc.x & 0xffff) / tile, tx1 = (rc.x >> 16) / tile, ty0 = (rc.y & 0xffff) / tile, ty1 = (rc.y >> 16) / tile;
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) {
                 const int64_t t = ((int64_t)b * TY + ty) * TX + tx;
@@ -278,26 +278,44 @@ struct RenderArgs {
     const float* rays;      // (B,H,W,3)
     const int64_t* tile_offsets;  // (B*TY*TX + 1)
     const int32_t* tile_list;     // local Gaussian indices
+    const uint2* rects;           // (B,N) conservative pixel rectangles from bin_count_kernel
     float thr_act, omega;
-    int B, N, H, W, K, tile, TX, TY;
+    int B, N, H, W, K, tile, TX, TY, cap;
     int32_t* out_idx;       // (B,H,W,K) packed b*N+g, -1 padded
     float* out_weight;      // (B,H,W,K)
     float* out_len;         // (B,H,W,K), 1e10 padded
     int64_t* out_valid;     // (B,H,W)
     float* out_act;         // optional (B,H,W,K)
     float* out_dsd;         // optional (B,H,W,K)
-    unsigned long long* stats;  // optional: [0] pairs filtered, [1] pairs refined
+    unsigned long long* stats;  // optional: [0] pairs evaluated, [1] pairs refined (= [0]), [2] pixels that overflowed
 };
 
-constexpr int kRChunk = 128;
+// Gaussian-major ("splat") forward.  The Gaussians of the C5-like scenes cover a few dozen pixels
+// each while a 16x16 tile sees several hundred candidates, so iterating pixels x candidates evaluates
+// ~10x more pairs than there are near-hits (profiles/ncu_r1_fwd_bwd_v3.md: 460M filtered vs 44M refined
+// pairs per view).  Here every warp takes candidates of the tile list in turn and visits only the
+// pixels of the candidate's conservative pixel rectangle (reference bin rectangle AND tangent bound of
+// {act < thr + margin}, computed by bin_count_kernel) clipped to the tile, evaluates the pair with the
+// bit-faithful arithmetic (exact_pair) and appends hits to the pixel's unsorted key buffer in shared
+// memory (one shared-memory atomic per hit).  Each pixel thread then sorts its buffer, keeps the K
+// smallest (len, idx) keys and runs the blend epilogue.  Results are independent of the order in
+// which warps append (keys are unique and totally ordered) => bit-identical to the pixel-major path.
+constexpr int kSplatChunk = 128;   // candidates between two per-pixel compactions
+
+template <int NT>
+__device__ __forceinline__ int pix_to_col(int lx, int ly, int tile) {
+    if (NT == 256 && tile == 16) return (((ly >> 2) * 2 + (lx >> 3)) << 5) + ((ly & 3) << 3) + (lx & 7);
+    return ly * tile + lx;
+}
 
 template <int NT, int KIND>
-__global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
+__global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 4)) render_fwd_kernel(const RenderArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_stage = reinterpret_cast<float*>(smem_raw);                                    // [kRChunk][12]
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_stage + kRChunk * kStageFloats);  // [K][NT]
-    float* s_E = reinterpret_cast<float*>(s_key + (size_t)a.K * NT);                        // [K][NT]
-    unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_E + (size_t)a.K * NT);     // [kQueueCap][NT]
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);           // [cap][NT]
+    float* s_ray = reinterpret_cast<float*>(s_key + (size_t)a.cap * NT);                   // [3][NT]
+    int* s_cnt = reinterpret_cast<int*>(s_ray + 3 * NT);                                   // [NT]
+    unsigned long long* s_lim = reinterpret_cast<unsigned long long*>(s_cnt + NT);         // [NT] admission limit per pixel
+    float* s_E = reinterpret_cast<float*>(s_key + (size_t)a.K * NT);                       // epilogue alias, [K][NT]
 
     const int tid = threadIdx.x;
     int blk = blockIdx.x;
@@ -305,8 +323,7 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
     const int ty = blk % a.TY;
     const int b = blk / a.TY;
 
-    // pixel of this thread: 16x16 tiles give every warp an 8x4 block (locality for culling and
-    // atomics); other tile sizes use the linear order
+    // pixel owned by this thread (inverse of pix_to_col)
     int lx, ly;
     bool in_tile;
     if (a.tile == 16 && NT == 256) {
@@ -322,80 +339,163 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
     const bool live = in_tile && xi < a.W && yi < a.H;
     const int64_t ray = ((int64_t)b * a.H + yi) * a.W + xi;
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
-
-    RayMono r;
-    r.set_dead();
-    if (live) r.set(a.rays[ray * 3 + 0], a.rays[ray * 3 + 1], a.rays[ray * 3 + 2]);
-
-    TopKU<NT> top;
-    top.init(s_key, a.K, tid);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    if (live) { r0 = a.rays[ray * 3 + 0]; r1 = a.rays[ray * 3 + 1]; r2 = a.rays[ray * 3 + 2]; }
+    s_ray[tid] = r0; s_ray[NT + tid] = r1; s_ray[2 * NT + tid] = r2;
+    s_cnt[tid] = 0;
+    s_lim[tid] = pack_key(kEmptyLen, 0);
 
     const int64_t tile_id = ((int64_t)b * a.TY + ty) * a.TX + tx;
     const int64_t beg = a.tile_offsets[tile_id];
     const int n = (int)(a.tile_offsets[tile_id + 1] - beg);
     const int32_t* list = a.tile_list + beg;
+    __syncthreads();
 
-    int qn = 0;
-    unsigned n_ref = 0;
-    // Warp-collective refine: every lane evaluates what it has queued with the bit-faithful
-    // arithmetic.  (Refining lane-by-lane as queues filled ran the ~100-instruction exact path with
-    // 2-3 active lanes: 8.2 threads per instruction in profiles/ncu_r1_render_fwd_v1.)
-    auto drain = [&]() {
-        for (int j = 0; j < qn; ++j) {
-            const int c = s_queue[j * NT + tid];
-            const int g = __float_as_int(s_stage[c * kStageFloats + 10]);
-            if (g < 0 || !live) continue;
-            const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r.d0, r.d1, r.d2);
-            if (h.act < a.thr_act) top.insert(h.len, g);
-        }
-        n_ref += qn;
-        qn = 0;
-    };
-
-    for (int base = 0; base < n; base += kRChunk) {
-        __syncthreads();
-        for (int t = tid; t < kRChunk; t += NT) {
-            const int m = base + t;
-            if (m < n) {
-                const int g = list[m];
-                float mu[3], S[9];
-                mu[0] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
-                mu[1] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
-                mu[2] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
-                load_S<KIND>(a.sigmas, g, S);
-                stage_candidate(s_stage + t * kStageFloats, g, mu, S, a.thr_act);
-            } else {
-                stage_invalid(s_stage + t * kStageFloats);   // rejected by the filter: no bounds checks below
-            }
-        }
-        __syncthreads();
-        const int cn = min(kRChunk, (n - base + 3) & ~3);
-        for (int c = 0; c < cn; c += 4) {
+    // ---- phase A: Gaussian-major exact evaluation over each candidate's pixel rectangle, in chunks of
+    // kSplatChunk candidates; after every chunk each pixel thread compacts its buffer to the K smallest
+    // keys and publishes its K-th key as the admission limit for the following chunks ----
+    const int warp = tid >> 5, lane = tid & 31;
+    const int px0 = tx * a.tile, py0 = ty * a.tile;
+    const int pxe = min(px0 + a.tile, a.W) - 1, pye = min(py0 + a.tile, a.H) - 1;
+    unsigned n_eval = 0;
+    bool overflow = false;
+    // Software pipeline over this warp's candidates (i = warp, warp + NT/32, ...): the index is fetched two
+    // items ahead and the Gaussian's record (rectangle, mean, S) one item ahead, so the two dependent L2
+    // round trips overlap with the evaluation of the current candidate.
+    constexpr int kStep = NT / 32;
+    int g_nn = (warp + kStep < n) ? __ldg(list + warp + kStep) : -1;
+    int g_n = (warp < n) ? __ldg(list + warp) : -1;
+    uint2 rc_n = make_uint2(1u, 0u);
+    float v_n[3] = {0.f, 0.f, 0.f};
+    float S_n[9];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (filter_pass(s_stage + (c + j) * kStageFloats, r)) {
-                    s_queue[qn * NT + tid] = (unsigned char)(c + j);
-                    ++qn;
+    for (int q = 0; q < 9; ++q) S_n[q] = 0.f;
+    if (g_n >= 0) {
+        rc_n = a.rects[(int64_t)b * a.N + g_n];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) v_n[q] = __ldg(a.verts + 3 * (int64_t)g_n + q);
+        load_S<KIND>(a.sigmas, g_n, S_n);
+    }
+    for (int base = 0; base < n; base += kSplatChunk) {
+        const int end = min(n, base + kSplatChunk);
+        for (int i = base + warp; i < end; i += kStep) {
+            const int g = g_n;
+            const uint2 rc = rc_n;
+            const float m0 = __fsub_rn(v_n[0], c0), m1 = __fsub_rn(v_n[1], c1), m2 = __fsub_rn(v_n[2], c2);
+            float S[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) S[q] = S_n[q];
+            // prefetch the next record / the index after it
+            g_n = g_nn;
+            g_nn = (i + 2 * kStep < n) ? __ldg(list + i + 2 * kStep) : -1;
+            if (g_n >= 0) {
+                rc_n = a.rects[(int64_t)b * a.N + g_n];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) v_n[q] = __ldg(a.verts + 3 * (int64_t)g_n + q);
+                load_S<KIND>(a.sigmas, g_n, S_n);
+            }
+            const int xl = max((int)(rc.x & 0xffffu), px0), xh = min((int)(rc.x >> 16), pxe);
+            const int yl = max((int)(rc.y & 0xffffu), py0), yh = min((int)(rc.y >> 16), pye);
+            const int w = xh - xl + 1, h = yh - yl + 1;
+            if (w <= 0 || h <= 0) continue;
+            // ray-independent part of exact_pair: t_ij = rn(mu_i S_ij) and msm (shared by msk / msm in the reference)
+            Prod9 pm;
+            float msm;
+            if (KIND == 9) {
+                pm = exact_row_products(m0, m1, m2, S);
+                msm = exact_contract(pm, m0, m1, m2);
+            } else {
+                pm.t[0] = __fmul_rn(m0, S[0]); pm.t[4] = __fmul_rn(m1, S[4]); pm.t[8] = __fmul_rn(m2, S[8]);
+                msm = __fmaf_rn(pm.t[8], m2, __fmaf_rn(pm.t[4], m1, __fmul_rn(pm.t[0], m0)));
+            }
+            const int area = w * h;
+            const unsigned inv_w = (65536u + (unsigned)w - 1u) / (unsigned)w;   // exact floor(p / w) for p < 256, w <= 16
+            for (int p = lane; p < area; p += 32) {
+                const int yy = (int)(((unsigned)p * inv_w) >> 16);
+                const int xx = p - yy * w;
+                const int col = pix_to_col<NT>(xl + xx - px0, yl + yy - py0, a.tile);
+                const float d0 = s_ray[col], d1 = s_ray[NT + col], d2 = s_ray[2 * NT + col];
+                float ksk, msk;
+                if (KIND == 9) {
+                    const Prod9 pd = exact_row_products(d0, d1, d2, S);
+                    ksk = exact_contract(pd, d0, d1, d2);
+                    msk = exact_contract(pm, d0, d1, d2);
+                } else {
+                    const float t0 = __fmul_rn(d0, S[0]), t1 = __fmul_rn(d1, S[4]), t2 = __fmul_rn(d2, S[8]);
+                    ksk = __fmaf_rn(t2, d2, __fmaf_rn(t1, d1, __fmul_rn(t0, d0)));
+                    msk = __fmaf_rn(pm.t[8], d2, __fmaf_rn(pm.t[4], d1, __fmul_rn(pm.t[0], d0)));
+                }
+                const float len = __fdiv_rn(msk, ksk);
+                const float act = __fsub_rn(msm, __fdiv_rn(__fmul_rn(msk, msk), ksk));
+                ++n_eval;
+                if (act < a.thr_act && len == len) {
+                    const unsigned long long key = pack_key(len, g);
+                    if (key < s_lim[col]) {     // initially len < 1e10 (reference :197), later the pixel's K-th key
+                        const int slot = atomicAdd(&s_cnt[col], 1);
+                        if (slot < a.cap) s_key[slot * NT + col] = key;
+                    }
                 }
             }
-            if (__any_sync(0xffffffffu, qn > kQueueCap - 4)) drain();
         }
-        if (__any_sync(0xffffffffu, qn > 0)) drain();   // queue entries are chunk-local
+        __syncthreads();
+        // compaction: keep the K smallest keys of this pixel, publish the K-th as the new limit
+        int c = s_cnt[tid];
+        if (c > a.cap) { overflow = true; c = a.cap; }
+        if (c > a.K) {
+            while (c > a.K) {           // drop the current maximum
+                unsigned long long mx = s_key[tid];
+                int mp = 0;
+                for (int k = 1; k < c; ++k) {
+                    const unsigned long long v = s_key[k * NT + tid];
+                    if (v > mx) { mx = v; mp = k; }
+                }
+                --c;
+                s_key[mp * NT + tid] = s_key[c * NT + tid];
+            }
+            unsigned long long mx = s_key[tid];
+            for (int k = 1; k < c; ++k) {
+                const unsigned long long v = s_key[k * NT + tid];
+                if (v > mx) mx = v;
+            }
+            s_lim[tid] = mx;
+            s_cnt[tid] = c;
+        }
+        __syncthreads();
     }
     if (a.stats != nullptr) {
-        // warp-aggregated counters (diagnostics only; NULL in timed runs)
-        unsigned long long f = live ? (unsigned long long)n : 0ull, e = live ? n_ref : 0u;
-        for (int o = 16; o > 0; o >>= 1) {
-            f += __shfl_down_sync(0xffffffffu, f, o);
-            e += __shfl_down_sync(0xffffffffu, e, o);
+        unsigned long long e = n_eval, o = (live && overflow) ? 1ull : 0ull;
+        for (int s = 16; s > 0; s >>= 1) {
+            e += __shfl_down_sync(0xffffffffu, e, s);
+            o += __shfl_down_sync(0xffffffffu, o, s);
         }
-        if ((tid & 31) == 0) { atomicAdd(a.stats, f); atomicAdd(a.stats + 1, (unsigned long long)e); }
+        if (lane == 0) { atomicAdd(a.stats, e); atomicAdd(a.stats + 1, e); atomicAdd(a.stats + 2, o); }
     }
 
-    // ---- epilogue: order the survivors, exact (len, act, dsd), blend weights, fragment write-out ----
-    top.sort();
-    if (!live) return;
+    // ---- phase B: per pixel, order the (at most K) survivors ----
+    TopKU<NT> top;
+    top.init(s_key, a.K, tid);
+    if (!live) {
+        top.cnt = 0;
+    } else if (overflow) {
+        // a single chunk delivered more hits than the buffer holds (rare): stream all candidates of the
+        // tile through the replace-the-maximum top-K buffer for this pixel alone
+        for (int i = 0; i < n; ++i) {
+            const int g = __ldg(list + i);
+            const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r0, r1, r2);
+            if (h.act < a.thr_act) top.insert(h.len, g);
+        }
+        top.sort();
+    } else {
+        top.cnt = min(s_cnt[tid], a.K);
+        top.sort();
+    }
     const int cnt = top.cnt;
+    // the epilogue's E array aliases key rows K..1.5K of ALL columns: every thread must be done with
+    // its unsorted entries before anyone writes there
+    __syncthreads();
+    if (!live) return;
+
+    // ---- epilogue: exact (len, act, dsd) of the survivors, blend weights, fragment write-out ----
     int32_t* o_idx = a.out_idx + ray * a.K;
     float* o_len = a.out_len + ray * a.K;
     float* o_w = a.out_weight + ray * a.K;
@@ -403,7 +503,7 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
     float s_min = 3.0e38f;
     for (int k = 0; k < cnt; ++k) {
         const int g = (int)(unsigned)(s_key[k * NT + tid] & 0xffffffffull);
-        const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r.d0, r.d1, r.d2);
+        const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r0, r1, r2);
         o_idx[k] = b * a.N + g;
         o_len[k] = h.len;
         if (a.out_act != nullptr) { a.out_act[ray * a.K + k] = h.act; a.out_dsd[ray * a.K + k] = h.dsd; }
@@ -440,9 +540,20 @@ __global__ void __launch_bounds__(NT) render_fwd_kernel(const RenderArgs a) {
     a.out_valid[ray] = cnt;
 }
 
+// per-pixel hit buffer capacity: 2K when it fits comfortably, never below 1.5K (the epilogue aliases
+// its E array onto slots K..1.5K)
+static int hit_capacity(int K, int nt) {
+    int cap = 2 * K;
+    // prefer three resident CTAs per SM (<= ~72 KB each) when the minimum depth allows it
+    while (cap > (3 * K + 1) / 2 && (size_t)cap * nt * 8 + (size_t)nt * 24 > 73 * 1024) --cap;
+    return cap;
+}
+
 template <int NT, int KIND>
-static int launch_render(const RenderArgs& a, cudaStream_t stream) {
-    const size_t smem = (size_t)kRChunk * kStageFloats * 4 + (size_t)a.K * NT * 12 + (size_t)kQueueCap * NT;
+static int launch_render(const RenderArgs& a0, cudaStream_t stream) {
+    RenderArgs a = a0;
+    a.cap = hit_capacity(a.K, NT);
+    const size_t smem = (size_t)a.cap * NT * 8 + (size_t)NT * 24;
     if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
     VOGE_CUDA_TRY(cudaFuncSetAttribute(render_fwd_kernel<NT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (long long)a.B * a.TX * a.TY;
@@ -456,10 +567,7 @@ template <int KIND>
 static int dispatch_render(const RenderArgs& a, cudaStream_t s) {
     const int px = a.tile * a.tile;
     if (px > 256) return (int)cudaErrorInvalidValue;
-    if (px > 128) {
-        if ((size_t)a.K * 256 * 12 > 200 * 1024) return (int)cudaErrorInvalidValue;
-        return launch_render<256, KIND>(a, s);
-    }
+    if (px > 128) return launch_render<256, KIND>(a, s);
     if (px > 64) return launch_render<128, KIND>(a, s);
     return launch_render<64, KIND>(a, s);
 }
@@ -804,21 +912,22 @@ extern "C" int voge_bin_fill(const uint32_t* rects, const int64_t* tile_offsets,
     if (B <= 0 || N <= 0) return 0;
     dim3 grid(min(cdiv(N, 256), kNumSMs * 8), B);
     bin_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(rects), tile_offsets, cursor,
-                                                             B, N, cdiv(W, tile), cdiv(H, tile), tile_list);
+                                                             B, N, cdiv(W, tile), cdiv(H, tile), tile, tile_list);
     VOGE_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
                                    const float* rays, const int64_t* tile_offsets, const int32_t* tile_list,
-                                   float thr_act, float absorptivity, int B, int N, int H, int W, int K, int tile,
+                                   const uint32_t* rects, float thr_act, float absorptivity, int B, int N, int H,
+                                   int W, int K, int tile,
                                    int32_t* out_idx, float* out_weight, float* out_len, int64_t* out_valid,
                                    float* out_act, float* out_dsd, uint64_t* stats, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
     RenderArgs a;
     a.verts = verts; a.sigmas = sigmas; a.origins = origins; a.rays = rays; a.tile_offsets = tile_offsets;
-    a.tile_list = tile_list; a.thr_act = thr_act; a.omega = absorptivity; a.B = B; a.N = N; a.H = H; a.W = W; a.K = K;
+    a.tile_list = tile_list; a.rects = reinterpret_cast<const uint2*>(rects); a.cap = 0; a.thr_act = thr_act; a.omega = absorptivity; a.B = B; a.N = N; a.H = H; a.W = W; a.K = K;
     a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
     a.out_idx = out_idx; a.out_weight = out_weight; a.out_len = out_len; a.out_valid = out_valid;
     a.out_act = out_act; a.out_dsd = out_dsd; a.stats = reinterpret_cast<unsigned long long*>(stats);

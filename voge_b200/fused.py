@@ -18,13 +18,16 @@ TILE_MAX = 16
 def choose_tile(bin_size, K, use_ref_bins):
     """Largest tile (<= 16 px, dividing bin_size when the reference bins apply) whose per-thread top-K
     lists fit in shared memory."""
-    cands = [t for t in range(TILE_MAX, 3, -1) if (not use_ref_bins) or bin_size % t == 0]
+    import os
+    tmax = int(os.environ.get("VOGE_TILE_MAX", TILE_MAX))
+    cands = [t for t in range(tmax, 3, -1) if (not use_ref_bins) or bin_size % t == 0]
     if not cands:
         cands = [t for t in range(3, 0, -1) if bin_size % t == 0]
     for t in cands:
         px = t * t
         nt = 256 if px > 128 else (128 if px > 64 else 64)
-        if 6144 + K * nt * 12 + nt * 16 <= 200 * 1024:
+        cap = (3 * K + 1) // 2                       # minimum per-pixel hit-buffer depth (csrc/render.cu)
+        if cap * nt * 8 + nt * 24 <= 200 * 1024:
             return t
     raise RuntimeError("voge_b200: max_assign=%d is too large for the fused renderer" % K)
 
@@ -35,9 +38,9 @@ class _RenderFused(torch.autograd.Function):
                 use_ref_bins, bin_size):
         thr_act = -math.log(thr + 1e-10)                       # RayTracing.py:85
         tile = choose_tile(bin_size, K, use_ref_bins)
-        offsets, tile_list = _C.bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act,
+        offsets, tile_list, rects = _C.bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act,
                                           use_ref_bins, bin_size, tile)
-        idx, weight, tlen, valid, _, _ = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list,
+        idx, weight, tlen, valid, _, _ = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list, rects,
                                                            thr_act, absorptivity, K, tile, need_act=False)
         if verts.requires_grad or sigmas.requires_grad:
             # recompute-not-store: only the inputs are kept; the backward re-evaluates the K hits per
