@@ -220,6 +220,74 @@ __global__ void __launch_bounds__(256) merge_bwd_kernel(const float* __restrict_
     }
 }
 
+// Specialisation for C <= 4 channels (colours) with the padded (n_attr,4) gradient table: per-channel
+// state lives in registers, the attribute row of a hit is gathered once per pass, and each hit issues
+// exactly one 16-byte vector reduction.
+template <int C>
+__global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __restrict__ attr,
+                                                              const float* __restrict__ weight,
+                                                              const int32_t* __restrict__ idx,
+                                                              const int64_t* __restrict__ valid_num,
+                                                              const float* __restrict__ background, float mask_thr,
+                                                              const float* __restrict__ g_out, int64_t R, int K,
+                                                              int idx_mod, int n_attr, float* __restrict__ g_attr4,
+                                                              float* __restrict__ g_weight) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int nv = valid_num != nullptr ? (int)min((int64_t)K, valid_num[r]) : K;
+    const float* wrow = weight + r * K;
+    const int32_t* irow = idx + r * K;
+    float go[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) go[c] = g_out[r * C + c];
+    float g_sumw = 0.f;
+    if (background != nullptr) {
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.f;
+        float wsum = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float w = wrow[k];
+            wsum += w;
+            if (k < nv) {
+                int g = max(irow[k], 0);
+                if (idx_mod > 0) g %= idx_mod;
+                if (g < n_attr) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[c] = fmaf(w, __ldg(attr + (int64_t)g * C + c), acc[c]);
+                }
+            }
+        }
+        const float sil = fminf(wsum, 1.f);
+        const float mask = mask_thr > 0.f ? (sil > mask_thr ? 1.f : 0.f) : sil;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            go[c] *= min1_grad(acc[c] + (1.f - mask) * background[c]);
+            if (!(mask_thr > 0.f)) g_sumw -= go[c] * background[c];
+        }
+        g_sumw *= min1_grad(wsum);
+    }
+    for (int k = 0; k < K; ++k) {
+        float gw = g_sumw;
+        if (k < nv) {
+            int g = max(irow[k], 0);
+            if (idx_mod > 0) g %= idx_mod;
+            if (g < n_attr) {
+                const float w = wrow[k];
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    gw = fmaf(go[c], __ldg(attr + (int64_t)g * C + c), gw);
+                    v[c] = w * go[c];
+                }
+                if (g_attr4 != nullptr && w != 0.f)
+                    atomicAdd(reinterpret_cast<float4*>(g_attr4 + 4 * (int64_t)g), make_float4(v[0], v[1], v[2], v[3]));
+            }
+        }
+        if (g_weight != nullptr) g_weight[r * K + k] = gw;
+    }
+}
+
 template <int NT>
 static int launch_agg_fwd(const int32_t* idx, const float* act, const float* len, const float* dsd,
                           float omega, int64_t R, int K, float* weight, int64_t* valid_num,
@@ -291,6 +359,16 @@ extern "C" int voge_merge_final_backward(const float* attr, const float* weight,
     (void)out;
     if (R <= 0 || C <= 0) return 0;
     if (background != nullptr && C > kMaxBgChannels) return (int)cudaErrorInvalidValue;
+    if (C <= 4 && (packed4 || grad_attr == nullptr)) {
+        const unsigned grid = (unsigned)((R + 255) / 256);
+        cudaStream_t s = (cudaStream_t)stream;
+#define VOGE_MB(CC) merge_bwd_small_kernel<CC><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, mask_thr, \
+                                                                    grad_out, R, K, idx_mod, n_attr, grad_attr, grad_weight)
+        if (C == 1) VOGE_MB(1); else if (C == 2) VOGE_MB(2); else if (C == 3) VOGE_MB(3); else VOGE_MB(4);
+#undef VOGE_MB
+        VOGE_LAUNCH_CHECK();
+        return 0;
+    }
     merge_bwd_kernel<<<(unsigned)((R + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         attr, weight, idx, valid_num, background, mask_thr, grad_out, R, K, C, idx_mod, n_attr, packed4 && C <= 4, grad_attr,
         grad_weight);

@@ -729,11 +729,8 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const size_t A = (size_t)a.K * NT;
     float2* s_ls = reinterpret_cast<float2*>(smem_raw);   // (len, s = sqrt(dsd + 1e-10))
-    float* s_E = reinterpret_cast<float*>(s_ls + A);
-    float* s_gl = s_E + A;
-    float* s_gd = s_gl + A;
-    float* s_gE = s_gd + A;
-    float* s_gD = s_gE + A;
+    float* s_E = reinterpret_cast<float*>(s_ls + A);      // exp(-act)
+    float* s_wg = s_E + A;                                // w_m * dL/dw_m
     const int tid = threadIdx.x;
     // 8x4 pixel block per warp so that lanes of a warp touch the same Gaussians
     const int bw = (a.W + 7) / 8, bh = (a.H + 3) / 4;
@@ -750,8 +747,9 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
     if (cnt == 0) return;
     const float d0 = a.rays[r * 3 + 0], d1 = a.rays[r * 3 + 1], d2 = a.rays[r * 3 + 2];
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
+    const float omega = a.omega;
 
-    // ---- recompute the hits ----
+    // ---- pass 0: recompute the hits (bit-faithful) ----
     float s_min = 3.0e38f;
     for (int k = 0; k < cnt; ++k) {
         const int g = a.idx[r * a.K + k] - b * a.N;
@@ -766,12 +764,11 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
         const float sk = sqrtf(h.dsd + 1e-10f);
         s_ls[k * NT + tid] = make_float2(h.len, sk);
         s_E[k * NT + tid] = expf(-h.act);
-        s_gl[k * NT + tid] = 0.f; s_gd[k * NT + tid] = 0.f; s_gE[k * NT + tid] = 0.f;
         s_min = fminf(s_min, sk);
     }
-    // ---- blend backward: w_m = e^.5 exp(-omega D_m) E_m, D_m = sum_k E_k Phi((len_m - len_k) s_k) ----
-    // Sorted lens => only the window |len_m - len_k| * s_min < 4 needs erf / exp; k < lo(m) has Phi = 1,
-    // Phi' = 0 (prefix sum of E forward; their d/dE_k = sum of gD_m is applied in one descending sweep).
+    // ---- pass 1: weights.  w_m = e^.5 exp(-omega D_m) E_m, D_m = sum_k E_k Phi((len_m - len_k) s_k);
+    // sorted lens => Phi = 1 below the window |len_m - len_k| s_min < 4 (running prefix of E), 0 above ----
+    float total_gD = 0.f;
     {
         int lo = 0;
         float SE = 0.f;
@@ -779,7 +776,7 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
             const float Em = s_E[m * NT + tid];
             const float lm = s_ls[m * NT + tid].x;
             while (lo < m && (lm - s_ls[lo * NT + tid].x) * s_min >= kErfSat) { SE += s_E[lo * NT + tid]; ++lo; }
-            float gD = 0.f;
+            float wg = 0.f;
             if (Em != 0.f) {
                 float D = SE;
                 for (int k = lo; k < cnt; ++k) {
@@ -788,70 +785,66 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
                     if (dl * s_min <= -kErfSat) break;
                     D += s_E[k * NT + tid] * phi(dl * lk.y);
                 }
-                const float w = expf(-(D * a.omega)) * Em * kInvExpMinusHalf;
-                const float gw = a.g_weight[r * a.K + m];
-                gD = -a.omega * w * gw;
-                s_gE[m * NT + tid] += w * gw / Em;      // direct path through the trailing exp(-act_m)
-                if (gD != 0.f) {
-                    float glm = 0.f;
-                    for (int k = lo; k < cnt; ++k) {
-                        const float2 lk = s_ls[k * NT + tid];
-                        const float dl = lm - lk.x;
-                        if (dl * s_min <= -kErfSat) break;      // Phi = 0 and Phi' = 0 from here on
-                        const float c = dl * lk.y;
-                        if (c >= kErfSat) {                      // saturated inside the s_min window
-                            s_gE[k * NT + tid] += gD;
-                            continue;
-                        }
-                        const float Ek = s_E[k * NT + tid];
-                        s_gE[k * NT + tid] += gD * phi(c);
-                        const float gc = gD * Ek * expf(-c * c) * kInvSqrtPi;
-                        glm += gc * lk.y;
-                        s_gl[k * NT + tid] -= gc * lk.y;
-                        s_gd[k * NT + tid] += gc * dl / (2.f * lk.y);
-                    }
-                    s_gl[m * NT + tid] += glm;
-                }
+                wg = expf(-(D * omega)) * Em * kInvExpMinusHalf * a.g_weight[r * a.K + m];
             }
-            s_gD[m * NT + tid] = gD;
-        }
-        // k < lo(m) received Phi = 1 from m: dD_m/dE_k = 1.  lo(m) is non-decreasing, so walking m
-        // downwards every k gets exactly one add of the running suffix sum of gD.
-        float acc = 0.f;
-        int L = cnt;    // lo(m) for the current m, found with a descending pointer
-        for (int m = cnt - 1; m >= 0; --m) {
-            const float lm = s_ls[m * NT + tid].x;
-            L = min(L, m);
-            while (L > 0 && (lm - s_ls[(L - 1) * NT + tid].x) * s_min < kErfSat) --L;
-            acc += s_gD[m * NT + tid];
-            int Lp = 0;
-            if (m > 0) {
-                const float lp = s_ls[(m - 1) * NT + tid].x;
-                Lp = min(L, m - 1);
-                while (Lp > 0 && (lp - s_ls[(Lp - 1) * NT + tid].x) * s_min < kErfSat) --Lp;
-            }
-            for (int k = Lp; k < L; ++k) s_gE[k * NT + tid] += acc;
+            s_wg[m * NT + tid] = wg;
+            total_gD -= omega * wg;       // gD_m = dL/dD_m = -omega w_m dL/dw_m
         }
     }
-    // ---- chain rule into the parameters ----
-    for (int k = 0; k < cnt; ++k) {
-        const int g = a.idx[r * a.K + k] - b * a.N;
-        if (g < 0 || g >= a.N) continue;
-        const float ga = -s_E[k * NT + tid] * s_gE[k * NT + tid];
-        float gl = s_gl[k * NT + tid];
-        if (a.g_len_out != nullptr) gl += a.g_len_out[r * a.K + k];
-        const float gd = s_gd[k * NT + tid];
-        if (ga == 0.f && gl == 0.f && gd == 0.f) continue;
-        float S[9];
-        load_S_dyn(a.kind, a.sigmas, g, S);
-        const float m0 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
-        const float m1 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
-        const float m2 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
-        const Prod9 pd = exact_row_products(d0, d1, d2, S);
-        const Prod9 pm = exact_row_products(m0, m1, m2, S);
-        const float ksk = exact_contract(pd, d0, d1, d2);
-        const float msk = exact_contract(pm, d0, d1, d2);
-        geom_grad_accumulate(a, g, m0, m1, m2, S, d0, d1, d2, ksk, msk, gl, ga, gd);
+    // ---- pass 2: per slot j gather every contribution inside its (symmetric) window [lo_j, hi_j] in
+    // registers and apply the chain rule of ray_trace_voge.cu:324-330 at once ----
+    {
+        int lo_j = 0, hi_j = -1;
+        float pref = 0.f;                 // sum of gD_m over m <= hi_j
+        for (int j = 0; j < cnt; ++j) {
+            const float2 lsj = s_ls[j * NT + tid];
+            const float lj = lsj.x, sj = lsj.y;
+            while (lo_j < j && (lj - s_ls[lo_j * NT + tid].x) * s_min >= kErfSat) ++lo_j;
+            while (hi_j + 1 < cnt && (s_ls[(hi_j + 1) * NT + tid].x - lj) * s_min < kErfSat) {
+                ++hi_j;
+                pref -= omega * s_wg[hi_j * NT + tid];
+            }
+            const float Ej = s_E[j * NT + tid];
+            if (Ej == 0.f) continue;
+            const float wgj = s_wg[j * NT + tid];
+            const float gDj = -omega * wgj;
+            // direct path through the trailing exp(-act_j)  +  rows m behind the window see Phi = 1
+            float gE = wgj / Ej + (total_gD - pref);
+            float gl = 0.f, gd = 0.f;
+            for (int i = lo_j; i <= hi_j; ++i) {
+                const float2 lsi = s_ls[i * NT + tid];
+                const float dl = lsi.x - lj;
+                const float gDi = -omega * s_wg[i * NT + tid];
+                // row i, column j:  c = (len_i - len_j) s_j
+                const float c = dl * sj;
+                if (c >= kErfSat) {
+                    gE += gDi;
+                } else if (c > -kErfSat) {
+                    gE += gDi * phi(c);
+                    const float gc = gDi * Ej * expf(-c * c) * kInvSqrtPi;
+                    gl -= gc * sj;
+                    gd += gc * dl / (2.f * sj);
+                }
+                // row j, column i:  c' = (len_j - len_i) s_i  ->  d/d len_j
+                const float c2_ = -dl * lsi.y;
+                if (fabsf(c2_) < kErfSat) gl += gDj * s_E[i * NT + tid] * expf(-c2_ * c2_) * kInvSqrtPi * lsi.y;
+            }
+            const float ga = -Ej * gE;
+            if (a.g_len_out != nullptr) gl += a.g_len_out[r * a.K + j];
+            if (ga == 0.f && gl == 0.f && gd == 0.f) continue;
+            const int g = a.idx[r * a.K + j] - b * a.N;
+            if (g < 0 || g >= a.N) continue;
+            float S[9];
+            load_S_dyn(a.kind, a.sigmas, g, S);
+            const float m0 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
+            const float m1 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
+            const float m2 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
+            const Prod9 pd = exact_row_products(d0, d1, d2, S);
+            const Prod9 pm = exact_row_products(m0, m1, m2, S);
+            const float ksk = exact_contract(pd, d0, d1, d2);
+            const float msk = exact_contract(pm, d0, d1, d2);
+            geom_grad_accumulate(a, g, m0, m1, m2, S, d0, d1, d2, ksk, msk, gl, ga, gd);
+        }
     }
 }
 
@@ -871,7 +864,7 @@ extern "C" int voge_render_backward_fused(const float* verts, const float* sigma
     const int64_t warps = (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
     cudaStream_t s = (cudaStream_t)stream;
     auto launch = [&](auto kernel, int nt) -> int {
-        const size_t smem = (size_t)K * nt * 28;
+        const size_t smem = (size_t)K * nt * 16;
         if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
         VOGE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t grid = (warps * 32 + nt - 1) / nt;
@@ -879,8 +872,8 @@ extern "C" int voge_render_backward_fused(const float* verts, const float* sigma
         VOGE_LAUNCH_CHECK();
         return 0;
     };
-    if (K <= 32) return launch(render_bwd_fused_kernel<128>, 128);
-    if (K <= 120) return launch(render_bwd_fused_kernel<64>, 64);
+    if (K <= 56) return launch(render_bwd_fused_kernel<128>, 128);
+    if (K <= 200) return launch(render_bwd_fused_kernel<64>, 64);
     return launch(render_bwd_fused_kernel<32>, 32);
 }
 
