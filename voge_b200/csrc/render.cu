@@ -302,6 +302,10 @@ struct RenderArgs {
 // which warps append (keys are unique and totally ordered) => bit-identical to the pixel-major path.
 constexpr int kSplatChunk = 128;   // candidates between two per-pixel compactions
 
+// floor(p / w) = (p * kInvW[w]) >> 16 exactly for p < 256, 1 <= w <= 16
+__constant__ unsigned kInvW[17] = {0u, 65536u, 32768u, 21846u, 16384u, 13108u, 10923u, 9363u, 8192u,
+                                   7282u, 6554u, 5958u, 5462u, 5042u, 4682u, 4370u, 4096u};
+
 template <int NT>
 __device__ __forceinline__ int pix_to_col(int lx, int ly, int tile) {
     if (NT == 256 && tile == 16) return (((ly >> 2) * 2 + (lx >> 3)) << 5) + ((ly & 3) << 3) + (lx & 7);
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 4)) render_fwd_kernel(con
                 msm = __fmaf_rn(pm.t[8], m2, __fmaf_rn(pm.t[4], m1, __fmul_rn(pm.t[0], m0)));
             }
             const int area = w * h;
-            const unsigned inv_w = (65536u + (unsigned)w - 1u) / (unsigned)w;   // exact floor(p / w) for p < 256, w <= 16
+            const unsigned inv_w = kInvW[w];
             for (int p = lane; p < area; p += 32) {
                 const int yy = (int)(((unsigned)p * inv_w) >> 16);
                 const int xx = p - yy * w;
