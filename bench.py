@@ -484,7 +484,11 @@ def main():
     roofline = {
         "kernel": "render_fwd_kernel (fused filter/refine/top-K/blend)",
         "bound": "fp32", "achieved": achieved, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["fp32_tflops"], "traffic": None,
+        "frac": achieved / peaks["fp32_tflops"],
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/ncu_r1_final.md:
+        # 301.4 + 505.1 MB for a 2-view launch), scaled to the views of one launch here
+        "traffic": 806.46e6 / 2 * min(args.chunk, count) if (args.n == 1_000_000 and args.hw == 1024) else None,
+        "traffic_source": "profiles/ncu_r1_final.md",
         "peak_source": "in-run FFMA micro-benchmark (MEASURED_PEAKS.json holds HBM and bf16-GEMM only)",
         "sfu_peak_tops": peaks["sfu_tops"],
         "algorithmic_pairs_per_launch": pairs_per_launch, "flop_per_pair": FLOP_PER_PAIR,
