@@ -143,6 +143,21 @@ int voge_sample_backward(const float* image, const float* weight, const int32_t*
 int voge_scatter_max(const float* weight, const int32_t* idx, int64_t R, int K,
                      int num_vert, float* wmax, voge_stream_t stream);
 
+/* ---- dense-ray API (next tier) --------------------------------------------------
+ * Replace `ray_trace_voge_ray` (ext.cpp:11 -> RayTraceVogeRay, voge_ray_tracing_ray.cu:242-283),
+ * `ray_trace_voge_ray_backward` (ext.cpp:12, :287-325) and `find_nearest_k` (ext.cpp:13, :328-375).
+ * mus (M,3), isigmas (M,3,3), rays (N,3); outputs (N,M) resp. (N,K).  grad_mus / grad_isg ZEROED by
+ * the caller; grad_rays written in full.  find_nearest_k pads with idx -1, len 1e10, act 0, dsd 0.   */
+int voge_ray_trace_ray(const float* mus, const float* isigmas, const float* rays, int M, int N,
+                       float* out_len, float* out_act, float* out_dsd, voge_stream_t stream);
+int voge_ray_trace_ray_backward(const float* mus, const float* isigmas, const float* rays,
+                                const float* grad_len, const float* grad_act, const float* grad_dsd,
+                                int M, int N, float* grad_rays, float* grad_mus, float* grad_isg,
+                                voge_stream_t stream);
+int voge_find_nearest_k(const float* len_in, const float* act_in, const float* dsd_in, float thr_act,
+                        int M, int K, int N, int32_t* out_idx, float* out_len, float* out_act,
+                        float* out_dsd, voge_stream_t stream);
+
 /* ---- fused renderer path (GaussianRenderer.forward, reference VoGE/Renderer.py:102-150) ------
  * Same results as rasterize_coarse -> ray_trace_voge_fine -> aggregation on the renderer's own
  * call pattern, without the per-view (B,N,.) copies, the (B,BH,BW,M) bin table or the (R,K,K)

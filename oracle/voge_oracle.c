@@ -294,3 +294,42 @@ VO_EXPORT int vo_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Dense-ray API: RayTraceVogeRayKernel voge_ray_tracing_ray.cu:114-143 (same Innerdot3d, hence
+ * the same contracted rounding sequence) and FindNearestKKernel :191-239 (same insert-then-bubble
+ * top-K; padding idx -1, len 1e10, act 0, dsd 0 from the host wrapper :344-347). */
+VO_EXPORT void vo_ray_trace_ray(const float* mus, const float* isigmas, const float* rays, int M, int N,
+                                float* out_len, float* out_act, float* out_dsd) {
+    for (int r = 0; r < N; ++r)
+        for (int p = 0; p < M; ++p)
+            vo_pair(mus + (int64_t)p * 3, isigmas + (int64_t)p * 9, rays + (int64_t)r * 3,
+                    out_len + (int64_t)r * M + p, out_act + (int64_t)r * M + p, out_dsd + (int64_t)r * M + p);
+}
+
+VO_EXPORT void vo_find_nearest_k(const float* len_in, const float* act_in, const float* dsd_in, float thr_act,
+                                 int M, int K, int N, int32_t* out_idx, float* out_len, float* out_act,
+                                 float* out_dsd) {
+    for (int r = 0; r < N; ++r) {
+        int32_t* pidx = out_idx + (int64_t)r * K;
+        float* plen = out_len + (int64_t)r * K;
+        float* pact = out_act + (int64_t)r * K;
+        float* pdsd = out_dsd + (int64_t)r * K;
+        for (int k = 0; k < K; ++k) { pidx[k] = -1; plen[k] = 1e10f; pact[k] = 0.f; pdsd[k] = 0.f; }
+        int cur = 0;
+        for (int m = 0; m < M; ++m) {
+            const float len = len_in[(int64_t)r * M + m], act = act_in[(int64_t)r * M + m];
+            if (act < thr_act && len < plen[cur]) {
+                plen[cur] = len; pact[cur] = act; pdsd[cur] = dsd_in[(int64_t)r * M + m]; pidx[cur] = m;
+                for (int t = cur; t > 0 && plen[t] < plen[t - 1]; --t) {
+                    float f; int32_t i;
+                    f = plen[t]; plen[t] = plen[t - 1]; plen[t - 1] = f;
+                    f = pact[t]; pact[t] = pact[t - 1]; pact[t - 1] = f;
+                    f = pdsd[t]; pdsd[t] = pdsd[t - 1]; pdsd[t - 1] = f;
+                    i = pidx[t]; pidx[t] = pidx[t - 1]; pidx[t - 1] = i;
+                }
+                if (cur < K - 1) cur++;
+            }
+        }
+    }
+}

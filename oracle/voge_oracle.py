@@ -155,6 +155,38 @@ def scatter_max(weight, idx, num_vert):
     return out
 
 
+def ray_trace_ray(mus, isigmas, rays):
+    """-> (len, act, dsd) each (N,M); voge_ray_tracing_ray.cu:114-143."""
+    mus, isg, rays = _f(_np(mus)).reshape(-1, 3), _f(_np(isigmas)).reshape(-1, 9), _f(_np(rays)).reshape(-1, 3)
+    M, N = mus.shape[0], rays.shape[0]
+    out = [np.empty((N, M), np.float32) for _ in range(3)]
+    lib().vo_ray_trace_ray(_p(mus), _p(isg), _p(rays), M, N, _p(out[0]), _p(out[1]), _p(out[2]))
+    return tuple(out)
+
+
+def ray_trace_ray_backward(mus, isigmas, rays, g_len, g_act, g_dsd):
+    """Dense backward (voge_ray_tracing_ray.cu:147-188) through the fine-backward restatement: the (N,M) table
+    is a (1,N,1,M) hit list whose slot m holds Gaussian m."""
+    mus, rays = _f(_np(mus)).reshape(-1, 3), _f(_np(rays)).reshape(-1, 3)
+    M, N = mus.shape[0], rays.shape[0]
+    idx = np.broadcast_to(np.arange(M, dtype=np.int32), (1, N, 1, M)).copy()
+    shp = (1, N, 1, M)
+    gr, gm, gs = ray_trace_fine_backward(mus, isigmas, rays.reshape(1, N, 1, 3), idx, _f(_np(g_len)).reshape(shp),
+                                         _f(_np(g_act)).reshape(shp), _f(_np(g_dsd)).reshape(shp))
+    return gr.reshape(N, 3), gm, gs
+
+
+def find_nearest_k(len_in, act_in, dsd_in, thr_act, K):
+    """-> (idx i32, len, act, dsd) each (N,K); voge_ray_tracing_ray.cu:191-239."""
+    ln, ac, ds = _f(_np(len_in)), _f(_np(act_in)), _f(_np(dsd_in))
+    N, M = ln.shape
+    idx = np.empty((N, K), np.int32)
+    out = [np.empty((N, K), np.float32) for _ in range(3)]
+    lib().vo_find_nearest_k(_p(ln), _p(ac), _p(ds), ctypes.c_float(thr_act), M, int(K), N, _p(idx), _p(out[0]), _p(out[1]),
+                            _p(out[2]))
+    return idx, out[0], out[1], out[2]
+
+
 def num_threads():
     return int(lib().vo_num_threads())
 

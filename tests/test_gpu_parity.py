@@ -193,3 +193,50 @@ def test_against_reference_gpu_golden(C, golden_dir):
         gi, gw = C.sample_voge_backward(t("img"), t("w"), t("idx"), t("gf"), t("gs"))
         assert torch.allclose(gi, t("g_image"), rtol=1e-5, atol=1e-6) and torch.allclose(gw, t("g_weight"), rtol=1e-5, atol=1e-6)
         assert torch.equal(C.scatter_max(t("w"), t("idx"), B * n), t("wmax"))
+
+
+def test_dense_ray_api(oracle, C):
+    """Next-tier rows: ray_trace_voge_ray / backward / find_nearest_k vs the oracle and, when the
+    prebuilt reference extension is present, vs the UNMODIFIED reference kernels on this GPU."""
+    import math
+    g = torch.Generator().manual_seed(31)
+    M, N, K = 57, 203, 9
+    mus = torch.randn(M, 3, generator=g) * 0.5 + torch.tensor([0.0, 0.0, 4.0])
+    A = torch.randn(M, 3, 3, generator=g) * 0.2 + torch.eye(3)
+    sig = (A @ A.transpose(1, 2)) * 30.0
+    rays = torch.nn.functional.normalize(torch.randn(N, 3, generator=g) * 0.15 + torch.tensor([0.0, 0.0, 1.0]), dim=1)
+    ln, ac, ds = C.ray_trace_voge_ray(mus.to(DEV), sig.to(DEV), rays.to(DEV))
+    ln_o, ac_o, ds_o = oracle.ray_trace_ray(mus, sig, rays)
+    assert np.array_equal(ln.cpu().numpy(), ln_o) and np.array_equal(ac.cpu().numpy(), ac_o) and np.array_equal(ds.cpu().numpy(), ds_o)
+    thr_act = -math.log(0.01 + 1e-10)
+    got = C.find_nearest_k(ln, ac, ds, thr_act, K)
+    want = oracle.find_nearest_k(ln_o, ac_o, ds_o, thr_act, K)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.cpu().numpy(), b)
+    assert (want[0] >= 0).sum() > 50 and (want[0] < 0).sum() > 50
+    gl, ga, gd = (torch.randn(N, M, generator=g) for _ in range(3))
+    gr, gm, gs = C.ray_trace_voge_ray_backward(mus.to(DEV), sig.to(DEV), rays.to(DEV), gl.to(DEV), ga.to(DEV), gd.to(DEV))
+    gr_o, gm_o, gs_o = oracle.ray_trace_ray_backward(mus, sig, rays, gl, ga, gd)
+    for a, b in ((gr, gr_o), (gm, gm_o), (gs, gs_o)):
+        assert np.abs(a.cpu().numpy() - b).max() <= 2e-5 * np.abs(b).max()
+    # python-level autograd wrappers (incl. the corrected find_nearest_k backward)
+    from voge_b200.RayTracing import find_farest_k, find_nearest_k, ray_trace_voge_ray
+    mu_p, sg_p = mus.to(DEV).requires_grad_(True), sig.to(DEV).requires_grad_(True)
+    l2, a2, d2 = ray_trace_voge_ray(mu_p, sg_p, rays.to(DEV))
+    i3, l3, a3, d3 = find_nearest_k(l2, a2, d2, K, 0.01)
+    (l3.clamp(max=100).sum() + 2 * a3.sum() + 3 * d3.sum()).backward()
+    assert torch.isfinite(mu_p.grad).all() and mu_p.grad.abs().sum() > 0
+    i4, l4, _, _ = find_farest_k(l2.detach(), a2.detach(), d2.detach(), K, 0.01)
+    assert (l4[:, 0] >= l3[:, 0].detach())[(i3[:, 0] >= 0)].all()
+    try:
+        import build_ref
+        ref = build_ref.load_ref()
+    except Exception:
+        return
+    r = ref.ray_trace_voge_ray(mus.to(DEV), sig.to(DEV), rays.to(DEV))
+    assert all(torch.equal(x, y) for x, y in zip(r, (ln, ac, ds)))
+    rk = ref.find_nearest_k(ln, ac, ds, thr_act, K)
+    assert all(torch.equal(x, y) for x, y in zip(rk, got))
+    rb = ref.ray_trace_voge_ray_backward(mus.to(DEV), sig.to(DEV), rays.to(DEV), gl.to(DEV), ga.to(DEV), gd.to(DEV))
+    for x, y in zip(rb, (gr, gm, gs)):
+        assert (x - y).abs().max() <= 2e-5 * x.abs().max()

@@ -31,14 +31,16 @@ def test_python_surface_matches_reference_names():
         "Renderer": ["GaussianRenderer", "GaussianRenderSettings", "Fragments", "interpolate_attr", "get_silhouette",
                      "to_colored_background", "to_white_background"],
         "RayTracing": ["ray_tracing", "rasterize_coarse", "ray_tracing_fine", "convert_to_box", "_RayTraceVoGE",
-                       "_RasterizeCoarse"],
+                       "_RasterizeCoarse", "ray_trace_voge_ray", "find_nearest_k", "find_farest_k", "_RayTraceVoGERay",
+                       "_FindNearestK"],
         "Aggregation": ["aggregation", "merge_final", "expend_sigma", "get_cross_activation", "assign2weight",
                         "inverse_cumsum", "get_ray_camera_space"],
         "Sampler": ["sample_features", "scatter_max_weight", "_SampleVoGE", "_ScatterMax"],
         "Meshes": ["GaussianMeshes", "GaussianMeshesNaive", "DeformedGaussianMeshes"],
         "Utils": ["ind_sel", "ind_fill", "rotation_theta", "eye_like"],
         "_C": ["rasterize_points_coarse", "ray_trace_voge_fine", "ray_trace_voge_fine_backward", "sample_voge",
-               "sample_voge_backward", "scatter_max"],
+               "sample_voge_backward", "scatter_max", "ray_trace_voge_ray", "ray_trace_voge_ray_backward",
+               "find_nearest_k"],
     }.items():
         for n in names:
             assert hasattr(getattr(V, mod), n), "%s.%s missing" % (mod, n)

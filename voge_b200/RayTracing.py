@@ -103,6 +103,76 @@ def ray_tracing_fine(mus, isigmas, rays, bin_points, thr, bin_size, n_assign, in
                                points_per_view)
 
 
+def ray_trace_voge_ray(mus, sigmas, rays):
+    """Dense (rays x Gaussians) hit quantities without culling or top-K (reference :97-108):
+    mus (M,3), sigmas float | (M,) | (M,3,3), rays (N,3) -> (hit_len, hit_act, hit_dsd), each (N,M)."""
+    if isinstance(sigmas, (float, int)):
+        sigmas = torch.eye(3, device=mus.device)[None].expand(mus.shape[0], -1, -1) * sigmas
+    if sigmas.dim() == 1:
+        sigmas = sigmas.view(-1, 1, 1) * torch.eye(3, device=sigmas.device)[None]
+    assert mus.is_cuda and sigmas.is_cuda and rays.is_cuda
+    assert mus.dim() == 2 and mus.shape[1] == 3
+    assert rays.dim() == 2 and rays.shape[1] == 3
+    assert sigmas.dim() == 3 and sigmas.shape[1] == 3 and sigmas.shape[2] == 3
+    return _RayTraceVoGERay.apply(mus, sigmas, rays)
+
+
+def find_nearest_k(hit_len_in, hit_act_in, hit_dsd_in, K, thr):
+    """K nearest hits (ascending length) with activation below the threshold (reference :111-115)."""
+    assert hit_len_in.is_cuda and hit_act_in.is_cuda and hit_dsd_in.is_cuda
+    thr_act = -math.log(thr + 1 / inf)
+    return _FindNearestK.apply(hit_len_in, hit_act_in, hit_dsd_in, thr_act, K)
+
+
+def find_farest_k(hit_len_in, hit_act_in, hit_dsd_in, K, thr):
+    """K farthest hits: nearest-K on negated lengths (reference :118-123)."""
+    assert hit_len_in.is_cuda and hit_act_in.is_cuda and hit_dsd_in.is_cuda
+    thr_act = -math.log(thr + 1 / inf)
+    point_idx, hit_len, hit_act, hit_dsd = _FindNearestK.apply(-hit_len_in, hit_act_in, hit_dsd_in, thr_act, K)
+    return point_idx, -hit_len, hit_act, hit_dsd
+
+
+class _RayTraceVoGERay(torch.autograd.Function):
+    """reference :209-220"""
+
+    @staticmethod
+    def forward(ctx, mus, sigmas, rays):
+        hit_len, hit_act, hit_dsd = _C.ray_trace_voge_ray(mus, sigmas, rays)
+        ctx.save_for_backward(mus, sigmas, rays)
+        return hit_len, hit_act, hit_dsd
+
+    @staticmethod
+    def backward(ctx, grad_hit_len, grad_hit_act, grad_hit_dsd):
+        mus, sigmas, rays = ctx.saved_tensors
+        grad_ray, grad_mus, grad_sig = _C.ray_trace_voge_ray_backward(
+            mus, sigmas, rays, grad_hit_len.contiguous(), grad_hit_act.contiguous(), grad_hit_dsd.contiguous())
+        return grad_mus, grad_sig, grad_ray
+
+
+class _FindNearestK(torch.autograd.Function):
+    """reference :223-241.  The reference's backward scatters the act / dsd gradients onto the tensor that
+    already holds the len gradient (:238-240, a defect); here each gradient goes to its own input."""
+
+    @staticmethod
+    def forward(ctx, hit_len_in, hit_act_in, hit_dsd_in, thr, K):
+        point_idx, hit_len, hit_act, hit_dsd = _C.find_nearest_k(hit_len_in, hit_act_in, hit_dsd_in, thr, K)
+        ctx.save_for_backward(point_idx)
+        ctx.in_shape = hit_len_in.shape
+        ctx.mark_non_differentiable(point_idx)
+        return point_idx, hit_len, hit_act, hit_dsd
+
+    @staticmethod
+    def backward(ctx, grad_point_idx, grad_hit_len, grad_hit_act, grad_hit_dsd):
+        (point_idx,) = ctx.saved_tensors
+        valid = point_idx >= 0
+        index = point_idx.clamp(min=0).long()
+        outs = []
+        for g in (grad_hit_len, grad_hit_act, grad_hit_dsd):
+            z = torch.zeros(ctx.in_shape, dtype=g.dtype, device=g.device)
+            outs.append(z.scatter_add(1, index, g * valid))
+        return outs[0], outs[1], outs[2], None, None
+
+
 class _RasterizeCoarse(torch.autograd.Function):
     """Non-differentiable binning (reference :126-151)."""
 

@@ -172,6 +172,51 @@ def scatter_max(vert_weight, vert_index, num_vert):
     return wmax
 
 
+def ray_trace_voge_ray(mus, isigmas, rays):
+    """Reference: RayTraceVogeRay, voge_ray_tracing_ray.cu:242-283. -> (len, act, dsd), each (N, M)."""
+    require_cuda(mus, isigmas, rays)
+    mus, isigmas, rays = f32c(mus), f32c(isigmas), f32c(rays)
+    M, N = int(isigmas.shape[0]), int(rays.shape[0])
+    dev = mus.device
+    with torch.cuda.device(dev):
+        out = [torch.empty((N, M), dtype=torch.float32, device=dev) for _ in range(3)]
+        check(lib().voge_ray_trace_ray(ptr(mus), ptr(isigmas), ptr(rays), M, N, ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                                       stream_of(mus)), "ray_trace_ray")
+    return tuple(out)
+
+
+def ray_trace_voge_ray_backward(mus, isigmas, rays, grad_len, grad_act, grad_dsd):
+    """Reference: RayTraceVogeRayBackward, :287-325. -> (grad_ray (N,3), grad_mus (M,3), grad_sig (M,3,3))."""
+    require_cuda(mus, isigmas, rays, grad_len, grad_act, grad_dsd)
+    mus, isigmas, rays = f32c(mus), f32c(isigmas), f32c(rays)
+    grad_len, grad_act, grad_dsd = f32c(grad_len), f32c(grad_act), f32c(grad_dsd)
+    M, N = int(isigmas.shape[0]), int(rays.shape[0])
+    dev = mus.device
+    with torch.cuda.device(dev):
+        g_ray = torch.zeros((N, 3), dtype=torch.float32, device=dev)
+        g_mus = torch.zeros((M, 3), dtype=torch.float32, device=dev)
+        g_sig = torch.zeros((M, 3, 3), dtype=torch.float32, device=dev)
+        check(lib().voge_ray_trace_ray_backward(ptr(mus), ptr(isigmas), ptr(rays), ptr(grad_len), ptr(grad_act),
+                                                ptr(grad_dsd), M, N, ptr(g_ray), ptr(g_mus), ptr(g_sig),
+                                                stream_of(mus)), "ray_trace_ray_backward")
+    return g_ray, g_mus, g_sig
+
+
+def find_nearest_k(hit_len_in, hit_act_in, hit_dsd_in, thr_act, K):
+    """Reference: FindNearestK, :328-375. -> (point_idx i32, len, act, dsd), each (N, K)."""
+    require_cuda(hit_len_in, hit_act_in, hit_dsd_in)
+    hit_len_in, hit_act_in, hit_dsd_in = f32c(hit_len_in), f32c(hit_act_in), f32c(hit_dsd_in)
+    N, M, K = int(hit_len_in.shape[0]), int(hit_len_in.shape[1]), int(K)
+    dev = hit_len_in.device
+    with torch.cuda.device(dev):
+        idx = torch.empty((N, K), dtype=torch.int32, device=dev)
+        out = [torch.empty((N, K), dtype=torch.float32, device=dev) for _ in range(3)]
+        check(lib().voge_find_nearest_k(ptr(hit_len_in), ptr(hit_act_in), ptr(hit_dsd_in), float(thr_act), M, K, N,
+                                        ptr(idx), ptr(out[0]), ptr(out[1]), ptr(out[2]), stream_of(hit_len_in)),
+              "find_nearest_k")
+    return idx, out[0], out[1], out[2]
+
+
 # ---- fused blend ops (PyTorch-only in the reference, Aggregation.py) ---------------------------
 def aggregation_forward(sel_idx, sel_act, sel_len, sel_dsd, absorptivity):
     require_cuda(sel_idx, sel_act, sel_len, sel_dsd)

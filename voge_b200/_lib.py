@@ -34,6 +34,9 @@ SIGNATURES = {
     "voge_sample": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P]),
     "voge_sample_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P]),
     "voge_scatter_max": (_I, [_P, _P, _L, _I, _I, _P, _P]),
+    "voge_ray_trace_ray": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "voge_ray_trace_ray_backward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "voge_find_nearest_k": (_I, [_P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P]),
     "voge_bin_count": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _P, _P, _P]),
     "voge_bin_fill": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "voge_render_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P,
