@@ -138,3 +138,79 @@ def test_fused_culling_is_conservative_on_hard_cases():
     renderer, gm = _setup(sc, "full", M=-1, K=12)
     a, b = _both(renderer, gm)
     assert torch.equal(a.vert_index, b.vert_index) and torch.equal(a.vert_hit_length, b.vert_hit_length)
+
+
+def test_fused_edge_cases(oracle):
+    from voge_b200.cameras import PerspectiveCameras
+    from voge_b200.Meshes import GaussianMeshesNaive
+    from voge_b200.Renderer import GaussianRenderer, GaussianRenderSettings, interpolate_attr, to_white_background
+    # (a) a single Gaussian, K = 1, image smaller than a tile, per-view intrinsics
+    R, T = oracle.look_at_view(torch.tensor([3.0, 2.5]), torch.tensor([0.0, 30.0]), torch.tensor([0.0, 45.0]))
+    cams = PerspectiveCameras(focal_length=torch.tensor([[20.0, 20.0], [30.0, 25.0]]),
+                              principal_point=torch.tensor([[6.0, 4.5], [5.0, 5.0]]), R=R, T=T, in_ndc=False,
+                              image_size=((9, 12),), device=DEV)
+    st = GaussianRenderSettings(image_size=(9, 12), max_assign=1, max_point_per_bin=1)
+    r = GaussianRenderer(cams, st).to(DEV)
+    gm = GaussianMeshesNaive(torch.zeros(1, 3, device=DEV), torch.tensor([3.0], device=DEV))
+    a, b = _both(r, gm)
+    assert torch.equal(a.vert_index, b.vert_index) and torch.equal(a.vert_hit_length, b.vert_hit_length)
+    assert a.vert_index.shape == (2, 9, 12, 1) and (a.vert_index[1] >= 1).any() and (a.valid_num.sum() > 10)
+    img = to_white_background(a, torch.tensor([[0.2, 0.4, 0.6]], device=DEV))
+    assert img.shape == (2, 9, 12, 3) and torch.isfinite(img).all() and img.min() < 0.99
+    # (b) nothing visible: everything behind the camera -> all-empty fragments
+    gm2 = GaussianMeshesNaive(torch.tensor([[0.0, 0.0, 50.0]], device=DEV), torch.tensor([3.0], device=DEV))
+    R1, T1 = oracle.look_at_view(3.0, 0.0, 0.0)
+    cams1 = PerspectiveCameras(focal_length=20.0, principal_point=((6.0, 4.5),), R=R1, T=T1, in_ndc=False,
+                               image_size=((9, 12),), device=DEV)
+    r1 = GaussianRenderer(cams1, GaussianRenderSettings(image_size=(9, 12), max_assign=4)).to(DEV)
+    f = r1(gm2)
+    assert (f.vert_index == -1).all() and (f.vert_weight == 0).all() and (f.vert_hit_length == 1e10).all() and (f.valid_num == 0).all()
+    assert torch.equal(to_white_background(f, torch.rand(1, 3, device=DEV)), torch.ones(1, 9, 12, 3, device=DEV))
+    # (c) inverse_sigma=True (covariances given) goes through the fused path with autograd through torch.inverse
+    sc = small_scene(seed=13, aniso=True, n=120)
+    cov = torch.inverse(0.5 * (sc["sigmas"] + sc["sigmas"].transpose(1, 2)))
+    cams3 = PerspectiveCameras(focal_length=sc["focal"], principal_point=(sc["principal"],), R=sc["R"], T=sc["T"],
+                               in_ndc=False, image_size=(sc["image_size"],), device=DEV)
+    st3 = GaussianRenderSettings(image_size=sc["image_size"], max_assign=6, inverse_sigma=True, max_point_per_bin=120)
+    r3 = GaussianRenderer(cams3, st3).to(DEV)
+    covp = cov.to(DEV).requires_grad_(True)
+    gm3 = GaussianMeshesNaive(sc["verts"].to(DEV), covp)
+    a3, b3 = _both(r3, gm3)
+    assert torch.equal(a3.vert_index, b3.vert_index) and (a3.vert_index >= 0).sum() > 200
+    interpolate_attr(a3, sc["colors"].to(DEV)).sum().backward()
+    assert torch.isfinite(covp.grad).all() and covp.grad.abs().sum() > 0
+
+
+def test_camera_gradients_use_op_by_op_path():
+    """rays / origins that require grad (pose optimisation) fall back to the op-by-op chain, whose
+    _RayTraceVoGE backward returns grad_rays (reference RayTracing.py:179-206)."""
+    from voge_b200.cameras import PerspectiveCameras
+    from voge_b200.Meshes import GaussianMeshesNaive
+    from voge_b200.Renderer import GaussianRenderer, GaussianRenderSettings, get_silhouette
+    sc = small_scene(seed=17, aniso=False, n=150)
+    Rp = sc["R"].to(DEV).requires_grad_(True)
+    Tp = sc["T"].to(DEV).requires_grad_(True)
+    cams = PerspectiveCameras(focal_length=sc["focal"], principal_point=(sc["principal"],), R=Rp, T=Tp, in_ndc=False,
+                              image_size=(sc["image_size"],), device=DEV)
+    r = GaussianRenderer(cams, GaussianRenderSettings(image_size=sc["image_size"], max_assign=6, max_point_per_bin=150)).to(DEV)
+    f = r(GaussianMeshesNaive(sc["verts"].to(DEV), sc["sigmas"][:, 0, 0].contiguous().to(DEV)))
+    get_silhouette(f).sum().backward()
+    assert Rp.grad is not None and torch.isfinite(Rp.grad).all() and Rp.grad.abs().sum() > 0
+    assert Tp.grad is not None and torch.isfinite(Tp.grad).all() and Tp.grad.abs().sum() > 0
+
+
+def test_sampler_api_roundtrip(oracle):
+    """sample_features / scatter_max_weight on fragments from the renderer (Sampler.py:5-42), fwd + bwd."""
+    from voge_b200.Sampler import sample_features, scatter_max_weight
+    sc = small_scene(seed=19, aniso=True, n=200)
+    renderer, gm = _setup(sc, "full", M=200)
+    frag = renderer(gm)
+    H, W = sc["image_size"]
+    img = torch.rand(1, H, W, 3, generator=torch.Generator().manual_seed(5)).to(DEV).requires_grad_(True)
+    feat, wsum = sample_features(frag, img, n_vert=200)
+    f_o, s_o = oracle.sample(img.detach().cpu(), frag.vert_weight.detach().cpu(), frag.vert_index.cpu(), 200)
+    assert np.allclose(feat.detach().cpu().numpy(), f_o, rtol=1e-4, atol=1e-5) and np.allclose(wsum.detach().cpu().numpy(), s_o, rtol=1e-4, atol=1e-5)
+    (feat.sum() + wsum.sum()).backward()
+    assert torch.isfinite(img.grad).all() and gm.verts.grad is not None and torch.isfinite(gm.verts.grad).all()
+    wmax = scatter_max_weight(frag, n_vert=200)
+    assert np.array_equal(wmax.cpu().numpy(), oracle.scatter_max(frag.vert_weight.detach().cpu(), frag.vert_index.cpu(), 200))
