@@ -434,14 +434,39 @@ def main():
         h2d = sum(t.numel() * 4 for t in [h_verts, h_sig, h_col] + h_targets)
         loss_host = torch.zeros(1).pin_memory()
 
+        copy_stream = torch.cuda.Stream(device=dev)
+
         def e2e_step():
-            with torch.no_grad():
+            # H2D on a copy stream, overlapped with compute: parameters first, then one event per chunk of
+            # target images; the compute stream waits only for what it is about to consume.
+            main = torch.cuda.current_stream(dev)
+            copy_stream.wait_stream(main)        # previous step must be done with the buffers we overwrite
+            with torch.cuda.stream(copy_stream), torch.no_grad():
                 wl["gm"].verts.copy_(h_verts, non_blocking=True)
                 wl["gm"].sigmas.copy_(h_sig, non_blocking=True)
                 wl["colors"].copy_(h_col, non_blocking=True)
-            tdev = [t.to(dev, non_blocking=True) for t in h_targets]
-            ls = fit_step(wl, tdev, args.views)
-            loss_host.copy_(ls.reshape(1), non_blocking=True)
+                ev_params = torch.cuda.Event(); ev_params.record(copy_stream)
+                tdev, evs = [], []
+                for t in h_targets:
+                    d = t.to(dev, non_blocking=True)
+                    d.record_stream(main)
+                    e = torch.cuda.Event(); e.record(copy_stream)
+                    tdev.append(d); evs.append(e)
+            main.wait_event(ev_params)
+            from voge_b200.distributed import allreduce_gradients
+            from voge_b200.Renderer import to_white_background
+            gm, col = wl["gm"], wl["colors"]
+            gm.verts.grad = None; gm.sigmas.grad = None; col.grad = None
+            total = None
+            for renderer, tgt, e in zip(wl["renderers"], tdev, evs):
+                main.wait_event(e)
+                frag = renderer(gm)
+                img = to_white_background(frag, col)
+                loss_c = ((img - tgt) ** 2).sum() / (args.views * H * W * 3)
+                loss_c.backward()
+                total = loss_c.detach() if total is None else total + loss_c.detach()
+            allreduce_gradients([gm.verts, gm.sigmas, col])
+            loss_host.copy_(total.reshape(1), non_blocking=True)
             torch.cuda.synchronize()
             return float(loss_host[0])
         for _ in range(2):
@@ -458,6 +483,10 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4}
 
     if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel (rank 0; work counted for rank 0's views) ----
     peaks = measure_peaks(dev)
@@ -482,7 +511,7 @@ def main():
         pass
     frag_bytes = (12 * args.k + 8) * (count * H * W) / max(len(wl["renderers"]), 1)
     roofline = {
-        "kernel": "render_fwd_kernel (fused filter/refine/top-K/blend)",
+        "kernel": "render_fwd_kernel (fused Gaussian-major ray trace + top-K + blend weights)",
         "bound": "fp32", "achieved": achieved, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["fp32_tflops"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/ncu_r1_final.md:
@@ -520,6 +549,10 @@ def main():
     if not args.no_ref_gpu:
         line["ref_gpu"] = ref_gpu_sample(wl, args, dev)
     print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
