@@ -144,7 +144,7 @@ def build_workload(args, dev, first, count):
         tg = [torch.rand(H, W, 3, generator=torch.Generator().manual_seed(1000 + first + c0 + i)) for i in range(cc)]
         targets.append(torch.stack(tg))
     gm = GaussianMeshes(verts, sig).to(dev)
-    col = torch.nn.Parameter(colors.to(dev))
+    col = torch.nn.Parameter(colors.to(dev), requires_grad=os.environ.get("VOGE_NO_COLOR_GRAD") != "1")
     return dict(gm=gm, colors=col, renderers=renderers, targets_host=targets, H=H, W=W, verts_host=verts,
                 sig_host=sig, colors_host=colors)
 

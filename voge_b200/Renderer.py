@@ -133,7 +133,19 @@ class GaussianRenderer(nn.Module):
                                                unit_directions=True, n_pts_per_ray=1, min_depth=0, max_depth=10)
             bundle = sampler(cams)
             return bundle.directions, bundle.origins[:, 0, 0, :]
-        return generate_rays(cams, image_size)
+        # The rays depend only on the camera tensors: regenerate them (a dozen elementwise passes over
+        # (B,H,W,3)) only when one of those tensors was replaced or written to, or when gradients must
+        # flow to the camera.  The reference rebuilds them on every forward.
+        tensors = [t for t in (cams.R, cams.T, cams.focal_length, cams.principal_point) if torch.is_tensor(t)]
+        if any(t.requires_grad for t in tensors):
+            return generate_rays(cams, image_size)
+        key = (tuple(image_size),) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+        cache = getattr(self, '_ray_cache', None)
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                cache = (key,) + tuple(generate_rays(cams, image_size))
+            self._ray_cache = cache
+        return cache[1], cache[2]
 
     def forward(self, gmeshes, **kwargs):
         assert not self.cameras.in_ndc(), 'Got NDC camera. Cameras.in_ndc must be set to false.'

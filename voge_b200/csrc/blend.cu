@@ -220,10 +220,72 @@ __global__ void __launch_bounds__(256) merge_bwd_kernel(const float* __restrict_
     }
 }
 
-// Specialisation for C <= 4 channels (colours) with the padded (n_attr,4) gradient table: per-channel
-// state lives in registers, the attribute row of a hit is gathered once per pass, and each hit issues
-// exactly one 16-byte vector reduction.
-template <int C>
+// Per-thread rows of the (R,K) tensors are read / written as 16-byte vectors when K % 4 == 0: a scalar
+// access at a 4K-byte lane stride costs one L1 sector operation per lane and slot, which -- not DRAM --
+// bounded the first version of these kernels (~1 TB/s, profiles/ncu_r1_final.md).
+struct Row4 {
+    float w[4];
+    int g[4];
+};
+template <bool VEC>
+__device__ __forceinline__ Row4 load_row4(const float* __restrict__ wrow, const int32_t* __restrict__ irow, int k, int K) {
+    Row4 o;
+    if (VEC) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
+        const int4 i4 = *reinterpret_cast<const int4*>(irow + k);
+        o.w[0] = w4.x; o.w[1] = w4.y; o.w[2] = w4.z; o.w[3] = w4.w;
+        o.g[0] = i4.x; o.g[1] = i4.y; o.g[2] = i4.z; o.g[3] = i4.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o.w[j] = (k + j < K) ? wrow[k + j] : 0.f;
+            o.g[j] = (k + j < K) ? irow[k + j] : -1;
+        }
+    }
+    return o;
+}
+
+template <int C, bool VEC>
+__global__ void __launch_bounds__(256) merge_fwd_small_kernel(const float* __restrict__ attr,
+                                                              const float* __restrict__ weight,
+                                                              const int32_t* __restrict__ idx,
+                                                              const int64_t* __restrict__ valid_num,
+                                                              const float* __restrict__ background, float mask_thr,
+                                                              int64_t R, int K, int idx_mod, int n_attr,
+                                                              float* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int nv = valid_num != nullptr ? (int)min((int64_t)K, valid_num[r]) : K;
+    const float* wrow = weight + r * K;
+    const int32_t* irow = idx + r * K;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    float wsum = 0.f;
+    for (int k = 0; k < K; k += 4) {
+        const Row4 row = load_row4<VEC>(wrow, irow, k, K);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            wsum += row.w[j];
+            int g = max(row.g[j], 0);            // Aggregation.py:131  vert_assign += (vert_assign < 0)
+            if (idx_mod > 0) g %= idx_mod;
+            if (k + j < nv && g < n_attr) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = fmaf(row.w[j], __ldg(attr + (int64_t)g * C + c), acc[c]);
+            }
+        }
+    }
+    if (background != nullptr) {
+        const float sil = fminf(wsum, 1.f);                                      // Renderer.py:157-159
+        const float mask = mask_thr > 0.f ? (sil > mask_thr ? 1.f : 0.f) : sil;  // :167-168
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fminf(acc[c] + (1.f - mask) * background[c], 1.f);   // :171
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[r * C + c] = acc[c];
+}
+
+template <int C, bool VEC>
 __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __restrict__ attr,
                                                               const float* __restrict__ weight,
                                                               const int32_t* __restrict__ idx,
@@ -246,15 +308,16 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[c] = 0.f;
         float wsum = 0.f;
-        for (int k = 0; k < K; ++k) {
-            const float w = wrow[k];
-            wsum += w;
-            if (k < nv) {
-                int g = max(irow[k], 0);
-                if (idx_mod > 0) g %= idx_mod;
-                if (g < n_attr) {
+        for (int k = 0; k < K; k += 4) {
+            const Row4 row = load_row4<VEC>(wrow, irow, k, K);
 #pragma unroll
-                    for (int c = 0; c < C; ++c) acc[c] = fmaf(w, __ldg(attr + (int64_t)g * C + c), acc[c]);
+            for (int j = 0; j < 4; ++j) {
+                wsum += row.w[j];
+                int g = max(row.g[j], 0);
+                if (idx_mod > 0) g %= idx_mod;
+                if (k + j < nv && g < n_attr) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[c] = fmaf(row.w[j], __ldg(attr + (int64_t)g * C + c), acc[c]);
                 }
             }
         }
@@ -267,24 +330,35 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
         }
         g_sumw *= min1_grad(wsum);
     }
-    for (int k = 0; k < K; ++k) {
-        float gw = g_sumw;
-        if (k < nv) {
-            int g = max(irow[k], 0);
+    for (int k = 0; k < K; k += 4) {
+        const Row4 row = load_row4<VEC>(wrow, irow, k, K);
+        float gw4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float gw = g_sumw;
+            int g = max(row.g[j], 0);
             if (idx_mod > 0) g %= idx_mod;
-            if (g < n_attr) {
-                const float w = wrow[k];
+            if (k + j < nv && g < n_attr) {
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     gw = fmaf(go[c], __ldg(attr + (int64_t)g * C + c), gw);
-                    v[c] = w * go[c];
+                    v[c] = row.w[j] * go[c];
                 }
-                if (g_attr4 != nullptr && w != 0.f)
+                if (g_attr4 != nullptr && row.w[j] != 0.f)
                     atomicAdd(reinterpret_cast<float4*>(g_attr4 + 4 * (int64_t)g), make_float4(v[0], v[1], v[2], v[3]));
             }
+            gw4[j] = gw;
         }
-        if (g_weight != nullptr) g_weight[r * K + k] = gw;
+        if (g_weight != nullptr) {
+            if (VEC) {
+                *reinterpret_cast<float4*>(g_weight + r * K + k) = make_float4(gw4[0], gw4[1], gw4[2], gw4[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (k + j < K) g_weight[r * K + k + j] = gw4[j];
+            }
+        }
     }
 }
 
@@ -343,6 +417,23 @@ extern "C" int voge_merge_final(const float* attr, const float* weight, const in
                                 voge_stream_t stream) {
     using namespace voge;
     if (R <= 0 || C <= 0) return 0;
+    if (C <= 4) {
+        const unsigned grid = (unsigned)((R + 255) / 256);
+        cudaStream_t s = (cudaStream_t)stream;
+#define VOGE_MF(CC)                                                                                                 \
+    do {                                                                                                            \
+        if (K % 4 == 0)                                                                                             \
+            merge_fwd_small_kernel<CC, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,        \
+                                                                  mask_thr, R, K, idx_mod, n_attr, out);            \
+        else                                                                                                        \
+            merge_fwd_small_kernel<CC, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,       \
+                                                                   mask_thr, R, K, idx_mod, n_attr, out);           \
+    } while (0)
+        if (C == 1) VOGE_MF(1); else if (C == 2) VOGE_MF(2); else if (C == 3) VOGE_MF(3); else VOGE_MF(4);
+#undef VOGE_MF
+        VOGE_LAUNCH_CHECK();
+        return 0;
+    }
     const int64_t total = R * C;
     merge_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         attr, weight, idx, valid_num, background, mask_thr, R, K, C, idx_mod, n_attr, out);
@@ -362,8 +453,17 @@ extern "C" int voge_merge_final_backward(const float* attr, const float* weight,
     if (C <= 4 && (packed4 || grad_attr == nullptr)) {
         const unsigned grid = (unsigned)((R + 255) / 256);
         cudaStream_t s = (cudaStream_t)stream;
-#define VOGE_MB(CC) merge_bwd_small_kernel<CC><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, mask_thr, \
-                                                                    grad_out, R, K, idx_mod, n_attr, grad_attr, grad_weight)
+#define VOGE_MB(CC)                                                                                                 \
+    do {                                                                                                            \
+        if (K % 4 == 0)                                                                                             \
+            merge_bwd_small_kernel<CC, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,        \
+                                                                  mask_thr, grad_out, R, K, idx_mod, n_attr,       \
+                                                                  grad_attr, grad_weight);                          \
+        else                                                                                                        \
+            merge_bwd_small_kernel<CC, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,       \
+                                                                   mask_thr, grad_out, R, K, idx_mod, n_attr,      \
+                                                                   grad_attr, grad_weight);                         \
+    } while (0)
         if (C == 1) VOGE_MB(1); else if (C == 2) VOGE_MB(2); else if (C == 3) VOGE_MB(3); else VOGE_MB(4);
 #undef VOGE_MB
         VOGE_LAUNCH_CHECK();
