@@ -500,21 +500,47 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 4)) render_fwd_kernel(con
     if (!live) return;
 
     // ---- epilogue: exact (len, act, dsd) of the survivors, blend weights, fragment write-out ----
+    // Each thread owns a (K,) row of every fragment tensor; rows are written four slots at a time as
+    // 16-byte vectors when K % 4 == 0 (a scalar store at a 4K-byte lane stride costs one L1/L2 sector
+    // operation per lane and slot).
     int32_t* o_idx = a.out_idx + ray * a.K;
     float* o_len = a.out_len + ray * a.K;
     float* o_w = a.out_weight + ray * a.K;
+    const bool vec = (a.K & 3) == 0;
     float2* s_ls = reinterpret_cast<float2*>(s_key);   // the key slots are re-used for (len, sqrt(dsd + 1e-10))
     float s_min = 3.0e38f;
-    for (int k = 0; k < cnt; ++k) {
-        const int g = (int)(unsigned)(s_key[k * NT + tid] & 0xffffffffull);
-        const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r0, r1, r2);
-        o_idx[k] = b * a.N + g;
-        o_len[k] = h.len;
-        if (a.out_act != nullptr) { a.out_act[ray * a.K + k] = h.act; a.out_dsd[ray * a.K + k] = h.dsd; }
-        const float sk = sqrtf(h.dsd + 1e-10f);                                  // Aggregation.py:49
-        s_ls[k * NT + tid] = make_float2(h.len, sk);
-        s_E[k * NT + tid] = expf(-h.act);
-        s_min = fminf(s_min, sk);
+    for (int k0 = 0; k0 < a.K; k0 += 4) {
+        int iv[4];
+        float lv[4], av[4], dv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            iv[j] = -1; lv[j] = kEmptyLen; av[j] = kEmptyLen; dv[j] = 0.f;
+            if (k < cnt) {
+                const int g = (int)(unsigned)(s_key[k * NT + tid] & 0xffffffffull);
+                const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r0, r1, r2);
+                iv[j] = b * a.N + g; lv[j] = h.len; av[j] = h.act; dv[j] = h.dsd;
+                const float sk = sqrtf(h.dsd + 1e-10f);                              // Aggregation.py:49
+                s_ls[k * NT + tid] = make_float2(h.len, sk);
+                s_E[k * NT + tid] = expf(-h.act);
+                s_min = fminf(s_min, sk);
+            }
+        }
+        if (vec) {
+            *reinterpret_cast<int4*>(o_idx + k0) = make_int4(iv[0], iv[1], iv[2], iv[3]);
+            *reinterpret_cast<float4*>(o_len + k0) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+            if (a.out_act != nullptr) {
+                *reinterpret_cast<float4*>(a.out_act + ray * a.K + k0) = make_float4(av[0], av[1], av[2], av[3]);
+                *reinterpret_cast<float4*>(a.out_dsd + ray * a.K + k0) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (k0 + j >= a.K) break;
+                o_idx[k0 + j] = iv[j]; o_len[k0 + j] = lv[j];
+                if (a.out_act != nullptr) { a.out_act[ray * a.K + k0 + j] = av[j]; a.out_dsd[ray * a.K + k0 + j] = dv[j]; }
+            }
+        }
     }
     // D_m = sum_k E_k Phi((len_m - len_k) s_k).  The list is sorted by len, so outside the window
     // |len_m - len_k| * min_k(s_k) < 4 the erf is saturated: Phi = 1 for k < lo(m) (their E_k are
@@ -523,23 +549,34 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 4)) render_fwd_kernel(con
     {
         int lo = 0;
         float SE = 0.f;
-        for (int m = 0; m < cnt; ++m) {
-            const float lm = s_ls[m * NT + tid].x;
-            while (lo < m && (lm - s_ls[lo * NT + tid].x) * s_min >= kErfSat) { SE += s_E[lo * NT + tid]; ++lo; }
-            float D = SE;
-            for (int k = lo; k < cnt; ++k) {
-                const float2 lk = s_ls[k * NT + tid];
-                const float dl = lm - lk.x;
-                if (dl * s_min <= -kErfSat) break;
-                D += s_E[k * NT + tid] * phi(dl * lk.y);
+        for (int m0 = 0; m0 < a.K; m0 += 4) {
+            float wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = m0 + j;
+                wv[j] = 0.f;
+                if (m < cnt) {
+                    const float lm = s_ls[m * NT + tid].x;
+                    while (lo < m && (lm - s_ls[lo * NT + tid].x) * s_min >= kErfSat) { SE += s_E[lo * NT + tid]; ++lo; }
+                    float D = SE;
+                    for (int k = lo; k < cnt; ++k) {
+                        const float2 lk = s_ls[k * NT + tid];
+                        const float dl = lm - lk.x;
+                        if (dl * s_min <= -kErfSat) break;
+                        D += s_E[k * NT + tid] * phi(dl * lk.y);
+                    }
+                    const float Em = s_E[m * NT + tid];
+                    wv[j] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
+                }
             }
-            const float Em = s_E[m * NT + tid];
-            o_w[m] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
+            if (vec) {
+                *reinterpret_cast<float4*>(o_w + m0) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (m0 + j < a.K) o_w[m0 + j] = wv[j];
+            }
         }
-    }
-    for (int k = cnt; k < a.K; ++k) {
-        o_idx[k] = -1; o_len[k] = kEmptyLen; o_w[k] = 0.f;
-        if (a.out_act != nullptr) { a.out_act[ray * a.K + k] = kEmptyLen; a.out_dsd[ray * a.K + k] = 0.f; }
     }
     a.out_valid[ray] = cnt;
 }
