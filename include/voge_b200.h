@@ -170,7 +170,8 @@ int voge_find_nearest_k(const float* len_in, const float* act_in, const float* d
  *   RayTracing.py:33-57 + rasterize_coarse.cu:20-42,:116-130 at `bin_size` px, if use_ref_bins]
  *   AND [conservative projected-ellipsoid bound]; tiles are `tile` x `tile` px (tile <= 16, divides
  *   bin_size).  rects (B,N,2) uint32 out = conservative PIXEL rectangle x0|x1<<16, y0|y1<<16 (inclusive,
- *   empty if x0 > x1); tile_counts (B,TY,TX) int32 must be ZEROED by the caller.
+ *   empty if x0 > x1); tile_counts (B,TY,TX) int32 must be ZEROED by the caller; tile_items (optional, same
+ *   shape, ZEROED) accumulates the rectangle area inside each tile (the tile's number of ITEMS, trace.cu).
  * voge_bin_fill: scatters Gaussian indices into tile_list using tile_offsets (B*TY*TX+1, int64,
  *   exclusive scan of tile_counts); cursor (B*TY*TX) int32 must be ZEROED by the caller.
  * voge_render_forward: fragments.  out_idx (B,H,W,K) packed b*N+n / -1, out_weight, out_len
@@ -183,7 +184,7 @@ int voge_find_nearest_k(const float* len_in, const float* act_in, const float* d
 int voge_bin_count(const float* verts, const float* sigmas, int sigma_kind, const float* R,
                    const float* T, const float* origins, const float* focal, const float* principal,
                    int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins,
-                   int bin_size, int tile, uint32_t* rects, int32_t* tile_counts,
+                   int bin_size, int tile, uint32_t* rects, int32_t* tile_counts, int32_t* tile_items,
                    voge_stream_t stream);
 int voge_bin_fill(const uint32_t* rects, const int64_t* tile_offsets, int32_t* cursor, int B, int N,
                   int H, int W, int tile, int32_t* tile_list, voge_stream_t stream);
@@ -193,6 +194,34 @@ int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind,
                         int B, int N, int H, int W, int K, int tile,
                         int32_t* out_idx, float* out_weight, float* out_len, int64_t* out_valid,
                         float* out_act, float* out_dsd, uint64_t* stats, voge_stream_t stream);
+/* ---- forward pipeline of the fused renderer (csrc/trace.cu, csrc/select.cu) ----------------------------
+ * Same fragments as voge_render_forward, in three launches and without any per-pixel capacity limit:
+ *   voge_trace_hits: every item (tile-list entry x pixel of its rectangle inside the tile) is evaluated with
+ *       the reference's arithmetic (ray_trace_voge.cu:188-193); hits (act < thr_act, len < 1e10, :197) are
+ *       appended as (orderable len bits, local Gaussian index) to the pixel's segment.  The segments of a
+ *       tile start at tile_item_offsets[tile] (B*TY*TX+1, int64 = exclusive scan of voge_bin_count's
+ *       tile_items) and hold one slot per rectangle covering the pixel; hits is
+ *       (tile_item_offsets[last], 2) uint32 = (orderable len bits, index) pairs.  Out: counts / seg_base (B*TY*TX, NT) per pixel column
+ *       (col = ly*tile + lx, NT = voge_trace_threads(tile)).
+ *   voge_select_topk: per pixel the K smallest (len, idx), ascending (== the reference's insertion rule,
+ *       ray_trace_voge.cu:197-213) -> out_idx (B,H,W,K) packed b*N+n / -1, out_valid (B,H,W) int64.
+ *   voge_blend_weights: exact re-evaluation of the first valid[r] slots of idx, blend weights
+ *       (Aggregation.py:30-107) -> out_weight, out_len (1e10 padded), optional out_act / out_dsd.
+ *   stats optional 4 x uint64 ([0] items evaluated, [2] pixels selected with the exact 64-bit keys), zeroed
+ *   by the caller.                                                                                         */
+int voge_trace_threads(int tile);
+int voge_trace_hits(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
+                    const float* rays, const int64_t* tile_offsets, const int32_t* tile_list,
+                    const uint32_t* rects, const int64_t* tile_item_offsets, float thr_act, int B, int N,
+                    int H, int W, int tile, int32_t* counts, int64_t* seg_base, uint32_t* hits,
+                    uint64_t* stats, voge_stream_t stream);
+int voge_select_topk(const int32_t* counts, const int64_t* seg_base, const uint32_t* hits,
+                     int B, int N, int H, int W, int K, int tile,
+                     int32_t* out_idx, int64_t* out_valid, uint64_t* stats, voge_stream_t stream);
+int voge_blend_weights(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
+                       const float* rays, const int32_t* idx, const int64_t* valid, float absorptivity,
+                       int B, int N, int H, int W, int K, float* out_weight, float* out_len,
+                       float* out_act, float* out_dsd, voge_stream_t stream);
 int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind,
                          const float* origins, const float* rays, const int32_t* idx,
                          const int64_t* valid_num,

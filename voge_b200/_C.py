@@ -300,8 +300,8 @@ def sigma_kind(sigmas):
 
 def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act, use_ref_bins, bin_size,
               tile):
-    """-> (tile_offsets (B*TY*TX+1,) int64, tile_list (total,) int32, rects (B,N,2) int32).
-    One host sync (the total number of list entries)."""
+    """-> (tile_offsets (B*TY*TX+1,) int64, tile_list (total,) int32, rects (B,N,2) int32,
+    tile_item_offsets (B*TY*TX+1,) int64 with .total_items).  One host sync (the two totals)."""
     verts, sigmas = f32c(verts), f32c(sigmas)
     R, T, origins, focal, principal = f32c(R), f32c(T), f32c(origins), f32c(focal), f32c(principal)
     B, N = int(R.shape[0]), int(verts.shape[0])
@@ -310,23 +310,30 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
     dev = verts.device
     with torch.cuda.device(dev):
         rects = torch.empty((B, N, 2), dtype=torch.int32, device=dev)
-        counts = torch.zeros((B * TY * TX + 1,), dtype=torch.int32, device=dev)
+        # row 0: list entries per tile, row 1: items (rectangle pixels) per tile; one leading zero column so
+        # that the inclusive scan is the exclusive offset table
+        counts = torch.zeros((2, B * TY * TX + 1), dtype=torch.int32, device=dev)
         check(lib().voge_bin_count(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(R), ptr(T), ptr(origins),
                                    ptr(focal), ptr(principal), B, N, H, W, float(thr), float(thr_act),
-                                   int(bool(use_ref_bins)), int(bin_size), int(tile), ptr(rects), ptr(counts),
-                                   stream_of(verts)), "bin_count")
-        offsets = torch.cumsum(counts, 0, dtype=torch.int64)
-        total = int(offsets[-1].item())
-        offsets = torch.cat([offsets.new_zeros(1), offsets[:-1]])   # exclusive scan, B*TY*TX+1 entries
+                                   int(bool(use_ref_bins)), int(bin_size), int(tile), ptr(rects), ptr(counts[0, 1:]),
+                                   ptr(counts[1, 1:]), stream_of(verts)), "bin_count")
+        offsets = torch.cumsum(counts, 1, dtype=torch.int64)
+        totals = offsets[:, -1].tolist()
+        total, total_items = int(totals[0]), int(totals[1])
         tile_list = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
         cursor = torch.zeros((B * TY * TX,), dtype=torch.int32, device=dev)
-        check(lib().voge_bin_fill(ptr(rects), ptr(offsets), ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
+        check(lib().voge_bin_fill(ptr(rects), ptr(offsets[0]), ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
                                   stream_of(verts)), "bin_fill")
-    return offsets, tile_list, rects
+    item_offsets = offsets[1]
+    item_offsets.total_items = total_items
+    return offsets[0], tile_list, rects, item_offsets
 
 
 def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects, thr_act, absorptivity, K, tile,
-                   need_act=True, stats=None):
+                   need_act=True, stats=None, item_offsets=None):
+    """Fragments of the fused renderer.  With item_offsets (bin_views' fourth result): trace_hits ->
+    select_topk -> blend_weights, no per-pixel capacity limit.  Without: the one-launch shared-memory top-K
+    kernel (voge_render_forward) -- same results, kept for cross-checks and very large item counts."""
     verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
     B, H, W = int(rays.shape[0]), int(rays.shape[1]), int(rays.shape[2])
     N, K = int(verts.shape[0]), int(K)
@@ -338,10 +345,29 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
         valid = torch.empty((B, H, W), dtype=torch.int64, device=dev)
         act = torch.empty((B, H, W, K), dtype=torch.float32, device=dev) if need_act else None
         dsd = torch.empty((B, H, W, K), dtype=torch.float32, device=dev) if need_act else None
-        check(lib().voge_render_forward(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(origins), ptr(rays),
-                                        ptr(tile_offsets), ptr(tile_list), ptr(rects), float(thr_act), float(absorptivity),
-                                        B, N, H, W, K, int(tile), ptr(idx), ptr(weight), ptr(tlen), ptr(valid),
-                                        ptr(act), ptr(dsd), ptr(stats), stream_of(verts)), "render_forward")
+        skind, st = sigma_kind(sigmas), stream_of(verts)
+        if item_offsets is None:
+            check(lib().voge_render_forward(ptr(verts), ptr(sigmas), skind, ptr(origins), ptr(rays),
+                                            ptr(tile_offsets), ptr(tile_list), ptr(rects), float(thr_act),
+                                            float(absorptivity), B, N, H, W, K, int(tile), ptr(idx), ptr(weight),
+                                            ptr(tlen), ptr(valid), ptr(act), ptr(dsd), ptr(stats), st),
+                  "render_forward")
+            return idx, weight, tlen, valid, act, dsd
+        nt = int(lib().voge_trace_threads(int(tile)))
+        n_tiles = int(tile_offsets.numel()) - 1
+        total_items = int(item_offsets.total_items)
+        counts = torch.empty((n_tiles * nt,), dtype=torch.int32, device=dev)
+        seg_base = torch.empty((n_tiles * nt,), dtype=torch.int64, device=dev)
+        hits = torch.empty((max(total_items, 1), 2), dtype=torch.int32, device=dev)
+        check(lib().voge_trace_hits(ptr(verts), ptr(sigmas), skind, ptr(origins), ptr(rays), ptr(tile_offsets),
+                                    ptr(tile_list), ptr(rects), ptr(item_offsets), float(thr_act), B, N, H, W,
+                                    int(tile), ptr(counts), ptr(seg_base), ptr(hits), ptr(stats), st),
+              "trace_hits")
+        check(lib().voge_select_topk(ptr(counts), ptr(seg_base), ptr(hits), B, N, H, W, K, int(tile),
+                                     ptr(idx), ptr(valid), ptr(stats), st), "select_topk")
+        check(lib().voge_blend_weights(ptr(verts), ptr(sigmas), skind, ptr(origins), ptr(rays), ptr(idx), ptr(valid),
+                                       float(absorptivity), B, N, H, W, K, ptr(weight), ptr(tlen), ptr(act), ptr(dsd),
+                                       st), "blend_weights")
     return idx, weight, tlen, valid, act, dsd
 
 

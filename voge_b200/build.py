@@ -12,8 +12,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvoge_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["api.cu", "coarse.cu", "fine_fwd.cu", "fine_bwd.cu", "blend.cu", "sample.cu", "render.cu", "dense.cu"]
-HEADERS = ["common.cuh", "fine_core.cuh", os.path.join("..", "..", "include", "voge_b200.h")]
+SOURCES = ["api.cu", "coarse.cu", "fine_fwd.cu", "fine_bwd.cu", "blend.cu", "sample.cu", "render.cu", "trace.cu", "select.cu", "dense.cu"]
+HEADERS = ["common.cuh", "fine_core.cuh", "render_core.cuh", "blend_core.cuh", os.path.join("..", "..", "include", "voge_b200.h")]
 
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -37,25 +37,33 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if not force and not _stale():
         return LIB
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    t_hdr = max(os.path.getmtime(h) for h in hdrs if os.path.exists(h))
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for s in srcs:
         o = os.path.join(HERE, "build", os.path.basename(s) + ".o")
         objs.append(o)
+        # per-object staleness: recompile only what changed (the sorting networks of select.cu take minutes)
+        if not force and os.path.exists(o) and os.path.getmtime(o) > max(os.path.getmtime(s), t_hdr):
+            continue
         cmd = [NVCC, *FLAGS, "-c", s, "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    log = []
     for s, p in procs:
         out, _ = p.communicate()
-        log.append(out)
+        with open(os.path.join(HERE, "build", os.path.basename(s) + ".ptxas.log"), "w") as f:
+            f.write(out)
+        if verbose:
+            print(out)
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("nvcc failed on " + s)
     with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
-        f.write("\n".join(log))
-    if verbose:
-        print("\n".join(log))
+        for s in srcs:
+            lp = os.path.join(HERE, "build", os.path.basename(s) + ".ptxas.log")
+            if os.path.exists(lp):
+                f.write(open(lp).read() + "\n")
     cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
     return LIB

@@ -14,66 +14,10 @@
 #include "../../include/voge_b200.h"
 #include "blend_core.cuh"
 #include "fine_core.cuh"
+#include "render_core.cuh"
+#include <type_traits>
 
 namespace voge {
-
-// ---- parameter access ----------------------------------------------------------------------------
-// sigma kinds: 1 = (N,) isotropic, 3 = (N,3) diagonal, 9 = (N,3,3) full.  S = 2 * sigma (Renderer.py:137)
-template <int KIND>
-__device__ __forceinline__ void load_S(const float* __restrict__ sig, int g, float* S) {
-    if (KIND == 1) {
-        const float s = 2.f * __ldg(sig + g);
-        S[0] = s; S[1] = 0.f; S[2] = 0.f; S[3] = 0.f; S[4] = s; S[5] = 0.f; S[6] = 0.f; S[7] = 0.f; S[8] = s;
-    } else if (KIND == 3) {
-        S[0] = 2.f * __ldg(sig + 3 * (int64_t)g); S[4] = 2.f * __ldg(sig + 3 * (int64_t)g + 1);
-        S[8] = 2.f * __ldg(sig + 3 * (int64_t)g + 2);
-        S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) S[i] = 2.f * __ldg(sig + 9 * (int64_t)g + i);
-    }
-}
-
-__device__ __forceinline__ void load_S_dyn(int kind, const float* __restrict__ sig, int g, float* S) {
-    if (kind == 1) load_S<1>(sig, g, S);
-    else if (kind == 3) load_S<3>(sig, g, S);
-    else load_S<9>(sig, g, S);
-}
-
-// exact_pair specialised for a diagonal S: identical bits to exact_pair with explicit zeros
-// (fma(0, c, acc) == acc), at a third of the work.
-__device__ __forceinline__ Hit exact_pair_diag(float m0, float m1, float m2, float s0, float s1, float s2,
-                                               float d0, float d1, float d2) {
-    const float t0 = __fmul_rn(d0, s0), t1 = __fmul_rn(d1, s1), t2 = __fmul_rn(d2, s2);
-    const float u0 = __fmul_rn(m0, s0), u1 = __fmul_rn(m1, s1), u2 = __fmul_rn(m2, s2);
-    const float ksk = __fmaf_rn(t2, d2, __fmaf_rn(t1, d1, __fmul_rn(t0, d0)));
-    const float msk = __fmaf_rn(u2, d2, __fmaf_rn(u1, d1, __fmul_rn(u0, d0)));
-    const float msm = __fmaf_rn(u2, m2, __fmaf_rn(u1, m1, __fmul_rn(u0, m0)));
-    Hit h;
-    h.len = __fdiv_rn(msk, ksk);
-    h.act = __fsub_rn(msm, __fdiv_rn(__fmul_rn(msk, msk), ksk));
-    h.dsd = ksk;
-    return h;
-}
-
-template <int KIND>
-__device__ __forceinline__ Hit exact_hit(const float* __restrict__ verts, const float* __restrict__ sig, int g,
-                                         float c0, float c1, float c2, float d0, float d1, float d2) {
-    const float m0 = __fsub_rn(__ldg(verts + 3 * (int64_t)g), c0);       // verts - ray_origin, Renderer.py:130
-    const float m1 = __fsub_rn(__ldg(verts + 3 * (int64_t)g + 1), c1);
-    const float m2 = __fsub_rn(__ldg(verts + 3 * (int64_t)g + 2), c2);
-    if (KIND == 1) {
-        const float s = 2.f * __ldg(sig + g);
-        return exact_pair_diag(m0, m1, m2, s, s, s, d0, d1, d2);
-    } else if (KIND == 3) {
-        return exact_pair_diag(m0, m1, m2, 2.f * __ldg(sig + 3 * (int64_t)g), 2.f * __ldg(sig + 3 * (int64_t)g + 1),
-                               2.f * __ldg(sig + 3 * (int64_t)g + 2), d0, d1, d2);
-    } else {
-        float S[9];
-        load_S<9>(sig, g, S);
-        return exact_pair(m0, m1, m2, S, d0, d1, d2);
-    }
-}
 
 // ---- binning ---------------------------------------------------------------------------------------
 struct BinArgs {
@@ -90,6 +34,7 @@ struct BinArgs {
     int use_ref_bins, bin_size, BH, BW, tile, TX, TY;
     uint2* rects;            // (B,N): x = x0 | x1 << 16, y = y0 | y1 << 16 in PIXELS (inclusive); empty if x0 > x1
     int32_t* tile_counts;    // (B, TY*TX)
+    int32_t* tile_items;     // optional (B, TY*TX): sum over the tile's entries of the rectangle area inside the tile
 };
 
 __device__ __forceinline__ float edge_min(int i, int bin, int S1, int S2, float half) {
@@ -245,8 +190,12 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
             rc = make_uint2((unsigned)x0 | ((unsigned)x1 << 16), (unsigned)y0 | ((unsigned)y1 << 16));
             const int tx0 = x0 / a.tile, tx1 = x1 / a.tile, ty0 = y0 / a.tile, ty1 = y1 / a.tile;
             int32_t* cnt = a.tile_counts + (int64_t)b * a.TX * a.TY;
+            int32_t* itm = a.tile_items != nullptr ? a.tile_items + (int64_t)b * a.TX * a.TY : nullptr;
             for (int ty = ty0; ty <= ty1; ++ty)
-                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt + ty * a.TX + tx, 1);
+                for (int tx = tx0; tx <= tx1; ++tx) {
+                    atomicAdd(cnt + ty * a.TX + tx, 1);
+                    if (itm != nullptr) atomicAdd(itm + ty * a.TX + tx, rect_area_in_tile(rc, tx, ty, a.tile));
+                }
         }
         a.rects[(int64_t)b * a.N + g] = rc;
     }
@@ -301,16 +250,6 @@ struct RenderArgs {
 // smallest (len, idx) keys and runs the blend epilogue.  Results are independent of the order in
 // which warps append (keys are unique and totally ordered) => bit-identical to the pixel-major path.
 constexpr int kSplatChunk = 128;   // candidates between two per-pixel compactions
-
-// floor(p / w) = (p * kInvW[w]) >> 16 exactly for p < 256, 1 <= w <= 16
-__constant__ unsigned kInvW[17] = {0u, 65536u, 32768u, 21846u, 16384u, 13108u, 10923u, 9363u, 8192u,
-                                   7282u, 6554u, 5958u, 5462u, 5042u, 4682u, 4370u, 4096u};
-
-template <int NT>
-__device__ __forceinline__ int pix_to_col(int lx, int ly, int tile) {
-    if (NT == 256 && tile == 16) return (((ly >> 2) * 2 + (lx >> 3)) << 5) + ((ly & 3) << 3) + (lx & 7);
-    return ly * tile + lx;
-}
 
 template <int NT, int KIND>
 __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 4)) render_fwd_kernel(const RenderArgs a) {
@@ -765,7 +704,7 @@ __device__ __forceinline__ void geom_grad_accumulate(const FusedBwdArgs& a, int 
     }
 }
 
-template <int NT>
+template <int NT, int KIND>
 __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const size_t A = (size_t)a.K * NT;
@@ -789,23 +728,38 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
     const float d0 = a.rays[r * 3 + 0], d1 = a.rays[r * 3 + 1], d2 = a.rays[r * 3 + 2];
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
     const float omega = a.omega;
+    const int32_t* i_idx = a.idx + r * a.K;
+    const float* i_gw = a.g_weight + r * a.K;
+    const int pack_off = b * a.N;
+    const bool vec = (a.K & 3) == 0;
 
-    // ---- pass 0: recompute the hits (bit-faithful) ----
+    // ---- pass 0: recompute the hits (bit-faithful), four slots at a time so that the dependent gathers
+    // (index -> mean, S) of several slots are in flight together ----
     float s_min = 3.0e38f;
-    for (int k = 0; k < cnt; ++k) {
-        const int g = a.idx[r * a.K + k] - b * a.N;
-        Hit h;
-        h.len = kEmptyLen; h.act = kEmptyLen; h.dsd = 0.f;
-        if (g >= 0 && g < a.N) {
-            float S[9];
-            load_S_dyn(a.kind, a.sigmas, g, S);
-            h = exact_pair(__fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0), __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1),
-                           __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2), S, d0, d1, d2);
+    for (int k0 = 0; k0 < cnt; k0 += 4) {
+        int gv[4] = {-1, -1, -1, -1};
+        if (vec) {
+            const int4 q = *reinterpret_cast<const int4*>(i_idx + k0);
+            gv[0] = q.x; gv[1] = q.y; gv[2] = q.z; gv[3] = q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k0 + j < cnt) gv[j] = i_idx[k0 + j];
         }
-        const float sk = sqrtf(h.dsd + 1e-10f);
-        s_ls[k * NT + tid] = make_float2(h.len, sk);
-        s_E[k * NT + tid] = expf(-h.act);
-        s_min = fminf(s_min, sk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            if (k < cnt) {
+                const int g = gv[j] - pack_off;
+                Hit h;
+                h.len = kEmptyLen; h.act = kEmptyLen; h.dsd = 0.f;
+                if (g >= 0 && g < a.N) h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, d0, d1, d2);
+                const float sk = sqrtf(h.dsd + 1e-10f);
+                s_ls[k * NT + tid] = make_float2(h.len, sk);
+                s_E[k * NT + tid] = expf(-h.act);
+                s_min = fminf(s_min, sk);
+            }
+        }
     }
     // ---- pass 1: weights.  w_m = e^.5 exp(-omega D_m) E_m, D_m = sum_k E_k Phi((len_m - len_k) s_k);
     // sorted lens => Phi = 1 below the window |len_m - len_k| s_min < 4 (running prefix of E), 0 above ----
@@ -826,7 +780,7 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
                     if (dl * s_min <= -kErfSat) break;
                     D += s_E[k * NT + tid] * phi(dl * lk.y);
                 }
-                wg = expf(-(D * omega)) * Em * kInvExpMinusHalf * a.g_weight[r * a.K + m];
+                wg = expf(-(D * omega)) * Em * kInvExpMinusHalf * i_gw[m];
             }
             s_wg[m * NT + tid] = wg;
             total_gD -= omega * wg;       // gD_m = dL/dD_m = -omega w_m dL/dw_m
@@ -838,6 +792,18 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
         int lo_j = 0, hi_j = -1;
         float pref = 0.f;                 // sum of gD_m over m <= hi_j
         for (int j = 0; j < cnt; ++j) {
+            // the Gaussian's record is fetched first: the gathers overlap with the window loop below
+            const int g = i_idx[j] - pack_off;
+            const bool g_ok = g >= 0 && g < a.N;
+            float S[9], m0 = 0.f, m1 = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) S[q] = 0.f;
+            if (g_ok) {
+                load_S<KIND>(a.sigmas, g, S);
+                m0 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
+                m1 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
+                m2 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
+            }
             const float2 lsj = s_ls[j * NT + tid];
             const float lj = lsj.x, sj = lsj.y;
             while (lo_j < j && (lj - s_ls[lo_j * NT + tid].x) * s_min >= kErfSat) ++lo_j;
@@ -873,13 +839,7 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
             const float ga = -Ej * gE;
             if (a.g_len_out != nullptr) gl += a.g_len_out[r * a.K + j];
             if (ga == 0.f && gl == 0.f && gd == 0.f) continue;
-            const int g = a.idx[r * a.K + j] - b * a.N;
-            if (g < 0 || g >= a.N) continue;
-            float S[9];
-            load_S_dyn(a.kind, a.sigmas, g, S);
-            const float m0 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
-            const float m1 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
-            const float m2 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
+            if (!g_ok) continue;
             const Prod9 pd = exact_row_products(d0, d1, d2, S);
             const Prod9 pm = exact_row_products(m0, m1, m2, S);
             const float ksk = exact_contract(pd, d0, d1, d2);
@@ -913,15 +873,21 @@ extern "C" int voge_render_backward_fused(const float* verts, const float* sigma
         VOGE_LAUNCH_CHECK();
         return 0;
     };
-    if (K <= 56) return launch(render_bwd_fused_kernel<128>, 128);
-    if (K <= 200) return launch(render_bwd_fused_kernel<64>, 64);
-    return launch(render_bwd_fused_kernel<32>, 32);
+    auto by_threads = [&](auto kind_tag) -> int {
+        constexpr int KIND = decltype(kind_tag)::value;
+        if (K <= 56) return launch(render_bwd_fused_kernel<128, KIND>, 128);
+        if (K <= 200) return launch(render_bwd_fused_kernel<64, KIND>, 64);
+        return launch(render_bwd_fused_kernel<32, KIND>, 32);
+    };
+    if (sigma_kind == 1) return by_threads(std::integral_constant<int, 1>{});
+    if (sigma_kind == 3) return by_threads(std::integral_constant<int, 3>{});
+    return by_threads(std::integral_constant<int, 9>{});
 }
 
 extern "C" int voge_bin_count(const float* verts, const float* sigmas, int sigma_kind, const float* Rm,
                               const float* Tv, const float* origins, const float* focal, const float* principal,
                               int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins, int bin_size,
-                              int tile, uint32_t* rects, int32_t* tile_counts, voge_stream_t stream) {
+                              int tile, uint32_t* rects, int32_t* tile_counts, int32_t* tile_items, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || N <= 0) return 0;
     if (tile <= 0 || tile > 16 || (use_ref_bins && (bin_size <= 0 || bin_size % tile != 0))) return (int)cudaErrorInvalidValue;
@@ -933,7 +899,7 @@ extern "C" int voge_bin_count(const float* verts, const float* sigmas, int sigma
     a.BH = use_ref_bins ? cdiv(H, bin_size) : 1; a.BW = use_ref_bins ? cdiv(W, bin_size) : 1;
     a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
     if (a.TX > 65535 || a.TY > 65535) return (int)cudaErrorInvalidValue;
-    a.rects = reinterpret_cast<uint2*>(rects); a.tile_counts = tile_counts;
+    a.rects = reinterpret_cast<uint2*>(rects); a.tile_counts = tile_counts; a.tile_items = tile_items;
     dim3 grid(min(cdiv(N, 256), kNumSMs * 8), B);
     bin_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     VOGE_LAUNCH_CHECK();

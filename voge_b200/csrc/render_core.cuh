@@ -1,0 +1,111 @@
+// render_core.cuh -- helpers shared by the fused renderer kernels (render.cu: binning, backward;
+// trace.cu: forward pipeline): compact-sigma access, exact_pair specialisations, tile pixel layout.
+#pragma once
+#include "common.cuh"
+
+namespace voge {
+
+// ---- parameter access ----------------------------------------------------------------------------
+// sigma kinds: 1 = (N,) isotropic, 3 = (N,3) diagonal, 9 = (N,3,3) full.  S = 2 * sigma (Renderer.py:137)
+template <int KIND>
+__device__ __forceinline__ void load_S(const float* __restrict__ sig, int g, float* S) {
+    if (KIND == 1) {
+        const float s = 2.f * __ldg(sig + g);
+        S[0] = s; S[1] = 0.f; S[2] = 0.f; S[3] = 0.f; S[4] = s; S[5] = 0.f; S[6] = 0.f; S[7] = 0.f; S[8] = s;
+    } else if (KIND == 3) {
+        S[0] = 2.f * __ldg(sig + 3 * (int64_t)g); S[4] = 2.f * __ldg(sig + 3 * (int64_t)g + 1);
+        S[8] = 2.f * __ldg(sig + 3 * (int64_t)g + 2);
+        S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) S[i] = 2.f * __ldg(sig + 9 * (int64_t)g + i);
+    }
+}
+
+__device__ __forceinline__ void load_S_dyn(int kind, const float* __restrict__ sig, int g, float* S) {
+    if (kind == 1) load_S<1>(sig, g, S);
+    else if (kind == 3) load_S<3>(sig, g, S);
+    else load_S<9>(sig, g, S);
+}
+
+// exact_pair specialised for a diagonal S: identical bits to exact_pair with explicit zeros
+// (fma(0, c, acc) == acc), at a third of the work.
+__device__ __forceinline__ Hit exact_pair_diag(float m0, float m1, float m2, float s0, float s1, float s2,
+                                               float d0, float d1, float d2) {
+    const float t0 = __fmul_rn(d0, s0), t1 = __fmul_rn(d1, s1), t2 = __fmul_rn(d2, s2);
+    const float u0 = __fmul_rn(m0, s0), u1 = __fmul_rn(m1, s1), u2 = __fmul_rn(m2, s2);
+    const float ksk = __fmaf_rn(t2, d2, __fmaf_rn(t1, d1, __fmul_rn(t0, d0)));
+    const float msk = __fmaf_rn(u2, d2, __fmaf_rn(u1, d1, __fmul_rn(u0, d0)));
+    const float msm = __fmaf_rn(u2, m2, __fmaf_rn(u1, m1, __fmul_rn(u0, m0)));
+    Hit h;
+    h.len = __fdiv_rn(msk, ksk);
+    h.act = __fsub_rn(msm, __fdiv_rn(__fmul_rn(msk, msk), ksk));
+    h.dsd = ksk;
+    return h;
+}
+
+template <int KIND>
+__device__ __forceinline__ Hit exact_hit(const float* __restrict__ verts, const float* __restrict__ sig, int g,
+                                         float c0, float c1, float c2, float d0, float d1, float d2) {
+    const float m0 = __fsub_rn(__ldg(verts + 3 * (int64_t)g), c0);       // verts - ray_origin, Renderer.py:130
+    const float m1 = __fsub_rn(__ldg(verts + 3 * (int64_t)g + 1), c1);
+    const float m2 = __fsub_rn(__ldg(verts + 3 * (int64_t)g + 2), c2);
+    if (KIND == 1) {
+        const float s = 2.f * __ldg(sig + g);
+        return exact_pair_diag(m0, m1, m2, s, s, s, d0, d1, d2);
+    } else if (KIND == 3) {
+        return exact_pair_diag(m0, m1, m2, 2.f * __ldg(sig + 3 * (int64_t)g), 2.f * __ldg(sig + 3 * (int64_t)g + 1),
+                               2.f * __ldg(sig + 3 * (int64_t)g + 2), d0, d1, d2);
+    } else {
+        float S[9];
+        load_S<9>(sig, g, S);
+        return exact_pair(m0, m1, m2, S, d0, d1, d2);
+    }
+}
+
+// floor(p / w) = (p * kInvW[w]) >> 16 exactly for p < 256, 1 <= w <= 16
+static __constant__ unsigned kInvW[17] = {0u, 65536u, 32768u, 21846u, 16384u, 13108u, 10923u, 9363u, 8192u,
+                                   7282u, 6554u, 5958u, 5462u, 5042u, 4682u, 4370u, 4096u};
+
+template <int NT>
+__device__ __forceinline__ int pix_to_col(int lx, int ly, int tile) {
+    if (NT == 256 && tile == 16) return (((ly >> 2) * 2 + (lx >> 3)) << 5) + ((ly & 3) << 3) + (lx & 7);
+    return ly * tile + lx;
+}
+
+
+// inverse of pix_to_col: pixel (lx, ly) of column `col`
+template <int NT>
+__device__ __forceinline__ void col_to_pix(int col, int tile, int& lx, int& ly, bool& in_tile) {
+    if (NT == 256 && tile == 16) {
+        const int w = col >> 5, l = col & 31;
+        lx = (w & 1) * 8 + (l & 7);
+        ly = (w >> 1) * 4 + (l >> 3);
+        in_tile = true;
+    } else {
+        lx = col % tile; ly = col / tile;
+        in_tile = col < tile * tile;
+    }
+}
+
+// Pixels of the rectangle rc (x0|x1<<16, y0|y1<<16, inclusive, inside the image) that lie in tile (tx,ty):
+// the number of ITEMS the entry contributes to the tile (trace.cu).  0 if the intersection is empty.
+__host__ __device__ __forceinline__ int rect_area_in_tile(uint2 rc, int tx, int ty, int tile) {
+    const int xl = max((int)(rc.x & 0xffffu), tx * tile), xh = min((int)(rc.x >> 16), tx * tile + tile - 1);
+    const int yl = max((int)(rc.y & 0xffffu), ty * tile), yh = min((int)(rc.y >> 16), ty * tile + tile - 1);
+    return max(xh - xl + 1, 0) * max(yh - yl + 1, 0);
+}
+
+// threads per tile CTA (= pixel columns per tile in the per-tile hit tables)
+static inline int tile_threads(int tile) {
+    const int px = tile * tile;
+    return px > 128 ? 256 : (px > 64 ? 128 : 64);
+}
+
+// monotone float -> uint (the high word of pack_key)
+__device__ __forceinline__ unsigned orderable(float len) {
+    const unsigned b = __float_as_uint(len + 0.f);                       // -0 -> +0
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+}  // namespace voge

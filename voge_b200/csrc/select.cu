@@ -1,0 +1,387 @@
+// select.cu -- second and third stage of the forward pipeline of the fused renderer (see trace.cu):
+//   select_topk_kernel   : per pixel, the K smallest (len, idx) hits of its segment in ascending order
+//                          (== the reference's insertion rule, ray_trace_voge.cu:197-213) -> vert_index,
+//                          valid_num; register sorting networks on 32-bit composites, exact 64-bit
+//                          selection where a composite ties or the segment exceeds the largest network;
+//   blend_weights_kernel : per pixel, exact re-evaluation of the survivors (bit-faithful exact_pair),
+//                          windowed erf blend (reference VoGE/Aggregation.py:30-107) -> vert_weight,
+//                          vert_hit_length (+ optional act / dsd).
+#include "../../include/voge_b200.h"
+#include "blend_core.cuh"
+#include "fine_core.cuh"
+#include "render_core.cuh"
+#include <utility>
+
+namespace voge {
+
+struct SelectArgs {
+    const int32_t* counts;        // (B*TY*TX, TNT) hits per pixel column (col = ly*tile + lx)
+    const int64_t* seg_base;      // (B*TY*TX, TNT)
+    const uint2* hits;            // (orderable len bits, local Gaussian index)
+    int B, N, H, W, K, tile, TX, TY;
+    int32_t* out_idx;             // (B,H,W,K) packed b*N+g, -1 padded
+    int64_t* out_valid;           // (B,H,W)
+    unsigned long long* stats;    // optional: [2] pixels selected with the exact 64-bit keys
+};
+
+// Batcher's odd-even merge sort on N registers (N a power of two): 63 / 191 / 543 compare-exchanges for
+// N = 16 / 32 / 64, each a VIMNMX pair on 32-bit keys.  The comparator list is built at compile time and
+// applied through a fold expression, so every register index is a literal (no local-memory array).
+template <int N>
+struct OddEvenNet {
+    static constexpr int kMax = (N <= 16) ? 63 : (N <= 32 ? 191 : 543);
+    short lo[kMax], hi[kMax];
+    int n;
+    constexpr OddEvenNet() : lo{}, hi{}, n(0) {
+        for (int p = 1; p < N; p <<= 1)
+            for (int k = p; k >= 1; k >>= 1)
+                for (int j = k % p; j + k < N; j += 2 * k)
+                    for (int i = 0; i < k; ++i)
+                        if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                            lo[n] = (short)(i + j); hi[n] = (short)(i + j + k); ++n;
+                        }
+    }
+};
+
+template <int N, size_t... I>
+__device__ __forceinline__ void sort_network_impl(unsigned (&r)[N], std::index_sequence<I...>) {
+    constexpr OddEvenNet<N> net{};
+    static_assert(net.n == OddEvenNet<N>::kMax, "comparator count");
+    ((void)([&] {
+         const unsigned x = r[net.lo[I]], y = r[net.hi[I]];
+         r[net.lo[I]] = min(x, y);
+         r[net.hi[I]] = max(x, y);
+     }()),
+     ...);
+}
+
+template <int N>
+__device__ __forceinline__ void sort_network(unsigned (&r)[N]) {
+    sort_network_impl<N>(r, std::make_index_sequence<OddEvenNet<N>::kMax>{});
+}
+
+// K smallest keys of a segment of c <= N hits, ascending, through 32-bit composites
+// ((len bits - smallest len bits of the segment) << 6 | slot): exact as long as the segment's lens span less
+// than 2^26 float steps (8 binades) and no two hits share their len; returns false otherwise (the caller
+// then selects with the full (len, idx) keys).  Writes the (K,) index row, -1 padded.
+template <int N>
+__device__ __forceinline__ bool select_network(const uint2* __restrict__ hs, int c, int K, int pack_off,
+                                               int32_t* __restrict__ o_idx) {
+    unsigned r[N];
+    unsigned omin = 0xffffffffu, omax = 0u;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        r[j] = 0xffffffffu;
+        if (j < c) {
+            r[j] = __ldg(&hs[j].x);
+            omin = min(omin, r[j]);
+            omax = max(omax, r[j]);
+        }
+    }
+    if (c > 0 && omax - omin >= 0x3ffffffu) return false;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+        if (j < c) r[j] = ((r[j] - omin) << 6) | (unsigned)j;
+    sort_network<N>(r);
+    bool tie = false;
+#pragma unroll
+    for (int i = 1; i < N; ++i) tie = tie || ((i < c) && ((r[i] ^ r[i - 1]) < 64u));
+    if (tie) return false;
+    const int m = min(c, K);
+    const bool vec = (K & 3) == 0;
+#pragma unroll
+    for (int i0 = 0; i0 < N; i0 += 4) {
+        if (i0 < K) {
+            int v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (i0 + j < m) ? pack_off + (int)__ldg(&hs[r[i0 + j] & 63u].y) : -1;
+            if (vec) {
+                *reinterpret_cast<int4*>(o_idx + i0) = make_int4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (i0 + j < K) o_idx[i0 + j] = v[j];
+            }
+        }
+    }
+    for (int k = N; k < K; ++k) o_idx[k] = -1;
+    return true;
+}
+
+// exact selection with the full (len, idx) keys: K passes, each extracting the smallest key above the
+// previous one (keys are unique: a Gaussian hits a pixel at most once).  O(K c) loads, any c.
+__device__ __noinline__ void select_exact(const uint2* __restrict__ hs, int c, int K, int pack_off,
+                                          int32_t* __restrict__ o_idx) {
+    unsigned long long prev = 0ull;
+    const int m = min(c, K);
+    for (int k = 0; k < m; ++k) {
+        unsigned long long best = 0xffffffffffffffffull;
+        for (int j = 0; j < c; ++j) {
+            const uint2 h = hs[j];
+            const unsigned long long key = ((unsigned long long)h.x << 32) | h.y;
+            if ((k == 0 || key > prev) && key < best) best = key;
+        }
+        o_idx[k] = pack_off + (int)(unsigned)(best & 0xffffffffull);
+        prev = best;
+    }
+    for (int k = m; k < K; ++k) o_idx[k] = -1;
+}
+
+// thread -> pixel of a tile: 8x4 pixel blocks per warp on 16x16 tiles (neighbouring pixels see the same
+// Gaussians), row-major otherwise
+template <int TNT>
+__device__ __forceinline__ void thread_to_pix(int t, int tile, int& lx, int& ly, bool& in_tile) {
+    if (TNT == 256 && tile == 16) {
+        const int w = t >> 5, l = t & 31;
+        lx = (w & 1) * 8 + (l & 7);
+        ly = (w >> 1) * 4 + (l >> 3);
+        in_tile = true;
+    } else {
+        lx = t % tile; ly = t / tile;
+        in_tile = t < tile * tile;
+    }
+}
+
+template <int NT, int TNT>
+__global__ void __launch_bounds__(NT, 512 / NT) select_topk_kernel(const SelectArgs a) {
+    const int tid = threadIdx.x;
+    constexpr int PARTS = TNT / NT;
+    const int64_t tile_id = blockIdx.x / PARTS;
+    const int t = (int)(tile_id % ((int64_t)a.TX * a.TY));
+    const int b = (int)(tile_id / ((int64_t)a.TX * a.TY));
+    const int tx = t % a.TX, ty = t / a.TX;
+    int lx, ly;
+    bool in_tile;
+    thread_to_pix<TNT>((blockIdx.x % PARTS) * NT + tid, a.tile, lx, ly, in_tile);
+    const int col = ly * a.tile + lx;
+    const int xi = tx * a.tile + lx, yi = ty * a.tile + ly;
+    const bool live = in_tile && xi < a.W && yi < a.H;
+    const int c = live ? a.counts[tile_id * TNT + col] : 0;
+    const int wmax = __reduce_max_sync(0xffffffffu, c);
+    if (!live) return;
+    const int64_t ray = ((int64_t)b * a.H + yi) * a.W + xi;
+    int32_t* o_idx = a.out_idx + ray * a.K;
+    a.out_valid[ray] = min(c, a.K);
+    const int64_t base = a.seg_base[tile_id * TNT + col];
+    const uint2* hs = a.hits + base;
+    const int pack_off = b * a.N;
+    bool done;
+    if (wmax <= 16) done = select_network<16>(hs, c, a.K, pack_off, o_idx);
+    else if (wmax <= 32) done = select_network<32>(hs, c, a.K, pack_off, o_idx);
+    else if (c <= 64) done = select_network<64>(hs, c, a.K, pack_off, o_idx);
+    else done = false;
+    if (!done) {
+        select_exact(hs, c, a.K, pack_off, o_idx);
+        if (a.stats != nullptr) atomicAdd(a.stats + 2, 1ull);
+    }
+}
+
+template <int NT, int TNT>
+static int launch_select(const SelectArgs& a, cudaStream_t stream) {
+    const long long grid = (long long)a.B * a.TX * a.TY * (TNT / NT);
+    if (grid <= 0 || grid > 2147483647LL) return (int)cudaErrorInvalidValue;
+    select_topk_kernel<NT, TNT><<<(unsigned)grid, NT, 0, stream>>>(a);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- blend -------------------------------------------------------------------------------------------------
+struct BlendArgs {
+    const float* verts;
+    const float* sigmas;
+    const float* origins;
+    const float* rays;
+    const int32_t* idx;           // (B,H,W,K) packed, first valid[r] slots
+    const int64_t* valid;         // (B,H,W)
+    float omega;
+    int B, N, H, W, K;
+    float* out_weight;            // (B,H,W,K)
+    float* out_len;               // (B,H,W,K), 1e10 padded
+    float* out_act;               // optional (B,H,W,K)
+    float* out_dsd;               // optional (B,H,W,K)
+};
+
+template <int NT, int KIND>
+__global__ void __launch_bounds__(NT) blend_weights_kernel(const BlendArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_ls = reinterpret_cast<float2*>(smem_raw);                 // [K][NT] (len, sqrt(dsd + 1e-10))
+    float* s_E = reinterpret_cast<float*>(s_ls + (size_t)a.K * NT);     // [K][NT] exp(-act)
+    const int tid = threadIdx.x;
+    // 8x4 pixel block per warp so that lanes of a warp touch the same Gaussians
+    const int bw = (a.W + 7) / 8, bh = (a.H + 3) / 4;
+    const int64_t wid = ((int64_t)blockIdx.x * NT + tid) >> 5;
+    const int lane = tid & 31;
+    const int64_t per_view = (int64_t)bw * bh;
+    if (wid >= per_view * a.B) return;
+    const int b = (int)(wid / per_view);
+    const int wb = (int)(wid % per_view);
+    const int xi = (wb % bw) * 8 + (lane & 7), yi = (wb / bw) * 4 + (lane >> 3);
+    if (xi >= a.W || yi >= a.H) return;
+    const int64_t ray = ((int64_t)b * a.H + yi) * a.W + xi;
+    const int cnt = (int)min((int64_t)a.K, a.valid[ray]);
+
+    // ---- exact (len, act, dsd) of the survivors, blend weights, fragment write-out ----
+    // Each thread owns a (K,) row of every fragment tensor; rows are written four slots at a time as
+    // 16-byte vectors when K % 4 == 0 (a scalar store at a 4K-byte lane stride costs one L1/L2 sector
+    // operation per lane and slot).
+    const int32_t* i_idx = a.idx + ray * a.K;
+    float* o_len = a.out_len + ray * a.K;
+    float* o_w = a.out_weight + ray * a.K;
+    const bool vec = (a.K & 3) == 0;
+    if (cnt == 0) {
+        // empty pixel: padding only
+        for (int k0 = 0; k0 < a.K; k0 += 4) {
+            if (vec) {
+                *reinterpret_cast<float4*>(o_len + k0) = make_float4(kEmptyLen, kEmptyLen, kEmptyLen, kEmptyLen);
+                *reinterpret_cast<float4*>(o_w + k0) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.out_act != nullptr) {
+                    *reinterpret_cast<float4*>(a.out_act + ray * a.K + k0) = make_float4(kEmptyLen, kEmptyLen, kEmptyLen, kEmptyLen);
+                    *reinterpret_cast<float4*>(a.out_dsd + ray * a.K + k0) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                for (int k = k0; k < min(k0 + 4, a.K); ++k) {
+                    o_len[k] = kEmptyLen; o_w[k] = 0.f;
+                    if (a.out_act != nullptr) { a.out_act[ray * a.K + k] = kEmptyLen; a.out_dsd[ray * a.K + k] = 0.f; }
+                }
+            }
+        }
+        return;
+    }
+    const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
+    const float r0 = a.rays[ray * 3 + 0], r1 = a.rays[ray * 3 + 1], r2 = a.rays[ray * 3 + 2];
+    const int pack_off = b * a.N;
+    float s_min = 3.0e38f;
+    for (int k0 = 0; k0 < a.K; k0 += 4) {
+        int gv[4] = {-1, -1, -1, -1};
+        if (vec) {
+            if (k0 < cnt) {
+                const int4 q = *reinterpret_cast<const int4*>(i_idx + k0);
+                gv[0] = q.x; gv[1] = q.y; gv[2] = q.z; gv[3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k0 + j < cnt) gv[j] = i_idx[k0 + j];
+        }
+        float lv[4], av[4], dv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            lv[j] = kEmptyLen; av[j] = kEmptyLen; dv[j] = 0.f;
+            if (k < cnt) {
+                const Hit h = exact_hit<KIND>(a.verts, a.sigmas, gv[j] - pack_off, c0, c1, c2, r0, r1, r2);
+                lv[j] = h.len; av[j] = h.act; dv[j] = h.dsd;
+                const float sk = sqrtf(h.dsd + 1e-10f);                              // Aggregation.py:49
+                s_ls[k * NT + tid] = make_float2(h.len, sk);
+                s_E[k * NT + tid] = expf(-h.act);
+                s_min = fminf(s_min, sk);
+            }
+        }
+        if (vec) {
+            *reinterpret_cast<float4*>(o_len + k0) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+            if (a.out_act != nullptr) {
+                *reinterpret_cast<float4*>(a.out_act + ray * a.K + k0) = make_float4(av[0], av[1], av[2], av[3]);
+                *reinterpret_cast<float4*>(a.out_dsd + ray * a.K + k0) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (k0 + j >= a.K) break;
+                o_len[k0 + j] = lv[j];
+                if (a.out_act != nullptr) { a.out_act[ray * a.K + k0 + j] = av[j]; a.out_dsd[ray * a.K + k0 + j] = dv[j]; }
+            }
+        }
+    }
+    // D_m = sum_k E_k Phi((len_m - len_k) s_k).  The list is sorted by len, so outside the window
+    // |len_m - len_k| * min_k(s_k) < 4 the erf is saturated: Phi = 1 for k < lo(m) (their E_k are
+    // carried in a running prefix sum -- lo(m) only moves forward), Phi = 0 behind the window.
+    // The summation order is the plain k = 0..cnt-1 order of the stand-alone aggregation kernel.
+    {
+        int lo = 0;
+        float SE = 0.f;
+        for (int m0 = 0; m0 < a.K; m0 += 4) {
+            float wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = m0 + j;
+                wv[j] = 0.f;
+                if (m < cnt) {
+                    const float lm = s_ls[m * NT + tid].x;
+                    while (lo < m && (lm - s_ls[lo * NT + tid].x) * s_min >= kErfSat) { SE += s_E[lo * NT + tid]; ++lo; }
+                    float D = SE;
+                    for (int k = lo; k < cnt; ++k) {
+                        const float2 lk = s_ls[k * NT + tid];
+                        const float dl = lm - lk.x;
+                        if (dl * s_min <= -kErfSat) break;
+                        D += s_E[k * NT + tid] * phi(dl * lk.y);
+                    }
+                    const float Em = s_E[m * NT + tid];
+                    wv[j] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
+                }
+            }
+            if (vec) {
+                *reinterpret_cast<float4*>(o_w + m0) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (m0 + j < a.K) o_w[m0 + j] = wv[j];
+            }
+        }
+    }
+}
+
+template <int NT, int KIND>
+static int launch_blend(const BlendArgs& a, cudaStream_t stream) {
+    const size_t smem = (size_t)a.K * NT * 12;
+    if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+    VOGE_CUDA_TRY(cudaFuncSetAttribute(blend_weights_kernel<NT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t warps = (int64_t)a.B * cdiv(a.W, 8) * cdiv(a.H, 4);
+    const int64_t grid = (warps * 32 + NT - 1) / NT;
+    if (grid <= 0 || grid > 2147483647LL) return (int)cudaErrorInvalidValue;
+    blend_weights_kernel<NT, KIND><<<(unsigned)grid, NT, smem, stream>>>(a);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int KIND>
+static int dispatch_blend(const BlendArgs& a, cudaStream_t s) {
+    // 12 K bytes of shared memory per thread: 128-thread CTAs while several of them fit on an SM
+    if (a.K <= 48) return launch_blend<128, KIND>(a, s);
+    if (a.K <= 280) return launch_blend<64, KIND>(a, s);
+    return launch_blend<32, KIND>(a, s);
+}
+
+}  // namespace voge
+
+extern "C" int voge_select_topk(const int32_t* counts, const int64_t* seg_base, const uint32_t* hits, int B, int N, int H, int W, int K, int tile,
+                                int32_t* out_idx, int64_t* out_valid, uint64_t* stats, voge_stream_t stream) {
+    using namespace voge;
+    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+    if (tile < 1 || tile > 16) return (int)cudaErrorInvalidValue;
+    SelectArgs a;
+    a.counts = counts; a.seg_base = seg_base; a.hits = reinterpret_cast<const uint2*>(hits);
+    a.B = B; a.N = N; a.H = H; a.W = W; a.K = K; a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
+    a.out_idx = out_idx; a.out_valid = out_valid; a.stats = reinterpret_cast<unsigned long long*>(stats);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nt = tile_threads(tile);
+    if (nt == 256) return launch_select<128, 256>(a, s);
+    if (nt == 128) return launch_select<128, 128>(a, s);
+    return launch_select<64, 64>(a, s);
+}
+
+extern "C" int voge_blend_weights(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
+                                  const float* rays, const int32_t* idx, const int64_t* valid, float absorptivity,
+                                  int B, int N, int H, int W, int K, float* out_weight, float* out_len,
+                                  float* out_act, float* out_dsd, voge_stream_t stream) {
+    using namespace voge;
+    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+    BlendArgs a;
+    a.verts = verts; a.sigmas = sigmas; a.origins = origins; a.rays = rays; a.idx = idx; a.valid = valid;
+    a.omega = absorptivity; a.B = B; a.N = N; a.H = H; a.W = W; a.K = K;
+    a.out_weight = out_weight; a.out_len = out_len; a.out_act = out_act; a.out_dsd = out_dsd;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (sigma_kind == 1) return dispatch_blend<1>(a, s);
+    if (sigma_kind == 3) return dispatch_blend<3>(a, s);
+    if (sigma_kind == 9) return dispatch_blend<9>(a, s);
+    return (int)cudaErrorInvalidValue;
+}

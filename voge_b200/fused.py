@@ -15,21 +15,26 @@ from . import _C
 TILE_MAX = 16
 
 
+# items (rectangle pixels) per renderer call above which the one-launch top-K kernel is used instead of the
+# trace/select/blend pipeline (which needs 8 bytes of scratch per item)
+MAX_PIPELINE_ITEMS = 1 << 30
+
+
 def choose_tile(bin_size, K, use_ref_bins):
-    """Largest tile (<= 16 px, dividing bin_size when the reference bins apply) whose per-thread top-K
-    lists fit in shared memory."""
+    """Largest tile (<= 16 px, dividing bin_size when the reference bins apply)."""
     import os
     tmax = int(os.environ.get("VOGE_TILE_MAX", TILE_MAX))
     cands = [t for t in range(tmax, 3, -1) if (not use_ref_bins) or bin_size % t == 0]
     if not cands:
         cands = [t for t in range(3, 0, -1) if bin_size % t == 0]
-    for t in cands:
-        px = t * t
-        nt = 256 if px > 128 else (128 if px > 64 else 64)
-        cap = (3 * K + 1) // 2                       # minimum per-pixel hit-buffer depth (csrc/render.cu)
-        if cap * nt * 8 + nt * 24 <= 200 * 1024:
-            return t
-    raise RuntimeError("voge_b200: max_assign=%d is too large for the fused renderer" % K)
+    return cands[0]
+
+
+def single_kernel_fits(tile, K):
+    """Whether the one-launch kernel's per-pixel hit buffers (1.5 K keys, csrc/render.cu) fit in shared memory."""
+    px = tile * tile
+    nt = 256 if px > 128 else (128 if px > 64 else 64)
+    return ((3 * K + 1) // 2) * nt * 8 + nt * 24 <= 200 * 1024
 
 
 class _RenderFused(torch.autograd.Function):
@@ -38,10 +43,13 @@ class _RenderFused(torch.autograd.Function):
                 use_ref_bins, bin_size):
         thr_act = -math.log(thr + 1e-10)                       # RayTracing.py:85
         tile = choose_tile(bin_size, K, use_ref_bins)
-        offsets, tile_list, rects = _C.bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act,
-                                          use_ref_bins, bin_size, tile)
+        offsets, tile_list, rects, item_offsets = _C.bin_views(verts, sigmas, R, T, origins, focal, principal,
+                                                               image_size, thr, thr_act, use_ref_bins, bin_size, tile)
+        if item_offsets.total_items > MAX_PIPELINE_ITEMS and single_kernel_fits(tile, K):
+            item_offsets = None
         idx, weight, tlen, valid, _, _ = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list, rects,
-                                                           thr_act, absorptivity, K, tile, need_act=False)
+                                                           thr_act, absorptivity, K, tile, need_act=False,
+                                                           item_offsets=item_offsets)
         if verts.requires_grad or sigmas.requires_grad:
             # recompute-not-store: only the inputs are kept; the backward re-evaluates the K hits per
             # pixel from idx (the reference saves mus, isigmas (B*N copies), rays, sel_idx and the
