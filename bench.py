@@ -115,6 +115,10 @@ class OpTimer:
             return out
         setattr(module, name, wrapped)
 
+    def add(self, name, e0, e1):
+        """kernel-level entry (voge_b200._lib.kernel_timer protocol): one C-ABI call"""
+        self.events.setdefault(name, []).append((e0, e1))
+
     def summary(self):
         out = {}
         for name, evs in self.events.items():
@@ -394,9 +398,9 @@ def main():
     rays_total = args.views * H * W
 
     timer = OpTimer()
-    for name in ("bin_views", "render_forward", "render_backward_fused", "merge_final_forward",
-                 "merge_final_backward"):
+    for name in ("bin_views", "render_forward"):        # host-side ops that span several launches
         timer.wrap(_C, name)
+    _lib.kernel_timer = timer                           # every C-ABI call (= one kernel launch) individually
 
     targets_dev = [t.to(dev) for t in wl["targets_host"]]
     # ---- warm-up ----
@@ -501,36 +505,83 @@ def main():
             hits += int(r(wl["gm"]).valid_num.sum().item())
         _C.render_forward = orig
     torch.cuda.synchronize()
-    fwd = ops.get("render_forward", {"avg_ms": float("nan"), "launches": 0, "total_ms": 0.0})
-    pairs_per_launch = n_pairs / max(len(wl["renderers"]), 1)
-    achieved = FLOP_PER_PAIR * pairs_per_launch / (fwd["avg_ms"] * 1e-3) / 1e12
+    n_calls = max(len(wl["renderers"]), 1)
+    views_per_launch = count / n_calls
+    rays_per_launch = views_per_launch * H * W
+    pairs_per_launch = n_pairs / n_calls
+    hits_per_launch = hits / n_calls
+    K = args.k
     mp = {}
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    frag_bytes = (12 * args.k + 8) * (count * H * W) / max(len(wl["renderers"]), 1)
-    roofline = {
-        "kernel": "render_fwd_kernel (fused Gaussian-major ray trace + top-K + blend weights)",
-        "bound": "fp32", "achieved": achieved, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["fp32_tflops"],
-        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture (profiles/ncu_r1_final.md:
-        # 301.4 + 505.1 MB for a 2-view launch), scaled to the views of one launch here
-        "traffic": 806.46e6 / 2 * min(args.chunk, count) if (args.n == 1_000_000 and args.hw == 1024) else None,
-        "traffic_source": "profiles/ncu_r1_final.md",
-        "peak_source": "in-run FFMA micro-benchmark (MEASURED_PEAKS.json holds HBM and bf16-GEMM only)",
+    hbm_peak = mp.get("hbm_gbs") or 6531.9     # fallback: B200_PROFILING.md's measured copy bandwidth
+    # dram__bytes_read.sum + dram__bytes_write.sum per VIEW from one `ncu --set full` capture of the C5 scene
+    # (profiles/traffic_r1.json, written from the .ncu-rep by tools/ncu_traffic.py); null for other workloads
+    traffic = {}
+    try:
+        if args.n == 1_000_000 and args.hw == 1024 and args.k == 20:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+    except Exception:
+        traffic = {}
+
+    def kernel_entry(sym, label, bound, work, unit_scale, note):
+        """work = algorithmic FLOP (fp32) or bytes (hbm) per launch; unit_scale 1e12 / 1e9"""
+        o = ops.get(sym)
+        if not o or not o["launches"]:
+            return None
+        ach = work / (o["avg_ms"] * 1e-3) / unit_scale
+        peak = peaks["fp32_tflops"] if bound == "fp32" else hbm_peak
+        tr = traffic.get(sym)
+        return {"kernel": label, "bound": bound, "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s" if bound == "fp32" else "GB/s", "frac": ach / peak,
+                "traffic": (tr * views_per_launch) if tr else None, "avg_launch_ms": o["avg_ms"],
+                "launches_timed": o["launches"], "share_of_step": o["total_ms"] / max(ms_total, 1e-9),
+                "algorithmic_work_per_launch": work, "work": note}
+
+    frag_bytes = (12 * K + 8) * rays_per_launch
+    kernels = [
+        kernel_entry("voge_trace_hits", "trace_hits_kernel (Gaussian-major exact ray trace -> per-pixel hit segments)",
+                     "fp32", FLOP_PER_PAIR * pairs_per_launch, 1e12,
+                     "33 FLOP x N_pairs under the reference's coarse semantics (SURVEY 8d); the kernel evaluates "
+                     "only the items of the culled pixel rectangles (items_evaluated_per_launch)"),
+        kernel_entry("voge_render_backward_fused", "render_bwd_fused_kernel (recompute + analytic blend backward + chain rule)",
+                     "fp32", 110.0 * hits_per_launch + (K * K * 30.0) * rays_per_launch, 1e12,
+                     "110 FLOP per hit + K^2 x 30 FLOP per ray (dense K x K blend backward of the reference, SURVEY 8d)"),
+        kernel_entry("voge_blend_weights", "blend_weights_kernel (exact re-evaluation + windowed erf blend)",
+                     "fp32", 33.0 * hits_per_launch + (K * K * 20.0 + K * 8.0) * rays_per_launch, 1e12,
+                     "33 FLOP per hit + (K^2 x 20 + K x 8) FLOP per ray (SURVEY 8d)"),
+        kernel_entry("voge_select_topk", "select_topk_kernel (register sorting networks)", "hbm",
+                     8.0 * hits_per_launch * 1.6 + (4 * K + 8 + 12) * rays_per_launch, 1e9,
+                     "reads the stored hits (8 B each; ~1.6 stored per selected) + 12 B/pixel of segment tables, "
+                     "writes (4K+8) B/ray"),
+        kernel_entry("voge_merge_final", "merge_fwd_kernel (gather-blend)", "hbm",
+                     (8 * K + 8 + 12) * rays_per_launch, 1e9, "8K B/ray in + 4C B/ray out (SURVEY 8d)"),
+        kernel_entry("voge_merge_final_backward", "merge_bwd_kernel", "hbm",
+                     (8 * K + 8 + 12 + 4 * K) * rays_per_launch, 1e9, "8K B/ray + grad in, 4K B/ray grad_weight out"),
+    ]
+    kernels = [k for k in kernels if k is not None]
+    kernels.sort(key=lambda k: -k["share_of_step"])
+    fwd_ms = ops.get("render_forward", {"avg_ms": float("nan")})["avg_ms"]
+    roofline = dict(kernels[0]) if kernels else {"kernel": None}
+    roofline.update({
+        "peak_source": "in-run FFMA micro-benchmark (MEASURED_PEAKS.json holds HBM and bf16-GEMM only); "
+                       "HBM peak from MEASURED_PEAKS.json" + ("" if mp.get("hbm_gbs") else " (absent: B200_PROFILING.md fallback)"),
+        "traffic_source": "profiles/traffic_r1.json (ncu --set full, per view, scaled to the views of one launch)",
         "sfu_peak_tops": peaks["sfu_tops"],
         "algorithmic_pairs_per_launch": pairs_per_launch, "flop_per_pair": FLOP_PER_PAIR,
-        "reference_bin_size": ref_bin, "avg_launch_ms": fwd["avg_ms"], "launches_timed": fwd["launches"],
-        "pairs_filtered_per_launch": int(stats[0].item()) / max(len(wl["renderers"]), 1),
-        "pairs_refined_per_launch": int(stats[1].item()) / max(len(wl["renderers"]), 1),
-        "pixels_overflowing_hit_buffer": int(stats[2].item()),
-        "hits_per_launch": hits / max(len(wl["renderers"]), 1),
-        "fragment_write_GBps": frag_bytes / (fwd["avg_ms"] * 1e-3) / 1e9,
-        "hbm_peak_GBps": mp.get("hbm_gbs"),
-        "share_of_step": fwd["total_ms"] / max(ms_total, 1e-9),
+        "reference_bin_size": ref_bin,
+        "items_evaluated_per_launch": int(stats[0].item()) / n_calls,
+        "pixels_selected_with_exact_keys": int(stats[2].item()),
+        "hits_per_launch": hits_per_launch,
+        "forward_all_launches_ms": fwd_ms,
+        "forward_algorithmic_tflops": FLOP_PER_PAIR * pairs_per_launch / (fwd_ms * 1e-3) / 1e12,
+        "fragment_write_GBps": frag_bytes / (fwd_ms * 1e-3) / 1e9,
+        "hbm_peak_GBps": hbm_peak,
+        "kernels": kernels,
         "op_breakdown_ms_per_step": {k: v["total_ms"] / args.steps for k, v in ops.items()},
-    }
+    })
     cpu = None
     if not args.no_cpu_baseline:
         c = cpu_port_sample(args)

@@ -214,3 +214,44 @@ def test_sampler_api_roundtrip(oracle):
     assert torch.isfinite(img.grad).all() and gm.verts.grad is not None and torch.isfinite(gm.verts.grad).all()
     wmax = scatter_max_weight(frag, n_vert=200)
     assert np.array_equal(wmax.cpu().numpy(), oracle.scatter_max(frag.vert_weight.detach().cpu(), frag.vert_index.cpu(), 200))
+
+
+@pytest.mark.parametrize("K,hw", [(8, (48, 48)), (20, (64, 64)), (30, (40, 56))])
+def test_forward_pipeline_dense_ties_and_single_kernel(K, hw):
+    """trace_hits -> select_topk -> blend_weights against the one-launch kernel and the op-by-op chain on a
+    scene built to leave the sorting-network fast path: > 64 hits per pixel (exact-key selection), duplicated
+    Gaussians (identical len: ties broken by index), lens spanning many binades."""
+    from voge_b200 import _C
+    from voge_b200.cameras import camera_params
+    from voge_b200.fused import choose_tile
+    from voge_b200.RayTracing import default_bin_size
+    sc = small_scene(seed=23, aniso=True, views=2, n=500, image_size=hw, focal=60.0)
+    sig = sc["sigmas"]
+    sig[:300] *= 0.01                       # wide blobs: every pixel collects a long hit list
+    verts = sc["verts"]
+    verts[300:360] = verts[0:60]            # exact duplicates -> identical (len, act), ordered by index
+    sig[300:360] = sig[0:60]
+    verts[360:380] *= 1e-3                  # Gaussians right at the look-at point ...
+    verts[380:400] = verts[380:400] * 0.02 + sc["R"][0][:, 2] * 0.0   # ... and a tight cluster
+    renderer, gm = _setup(sc, "full", K=K, M=500)
+    a, b = _both(renderer, gm)
+    assert torch.equal(a.vert_index, b.vert_index) and torch.equal(a.vert_hit_length, b.vert_hit_length)
+    assert torch.equal(a.valid_num, b.valid_num)
+    assert torch.allclose(a.vert_weight, b.vert_weight, rtol=1e-5, atol=1e-9, equal_nan=True)
+    # the same fragments from the one-launch kernel, and the counters of the pipeline
+    rays, origins = renderer._rays(hw)
+    R, T, focal, principal = camera_params(renderer.cameras, hw)
+    R, T = R.expand(2, -1, -1).contiguous(), T.expand(2, -1).contiguous()
+    focal, principal = focal.expand(2, -1).contiguous(), principal.expand(2, -1).contiguous()
+    thr_act = -math.log(0.01 + 1e-10)
+    bs = default_bin_size(hw); tile = choose_tile(bs, K, True)
+    off, tl, rects, ioff = _C.bin_views(gm.verts, gm.sigmas, R, T, origins, focal, principal, hw, 0.01, thr_act, True, bs, tile)
+    stats = torch.zeros(4, dtype=torch.int64, device=DEV)
+    p = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile, stats=stats, item_offsets=ioff)
+    s = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile)
+    for x, y in zip(p, s):
+        assert torch.equal(x, y)
+    assert torch.equal(p[0], a.vert_index)
+    assert int(stats[0]) == ioff.total_items > 0          # every item evaluated exactly once
+    assert int(stats[2]) > 0                              # the exact-key selection was exercised
+    assert int(p[3].max()) == K

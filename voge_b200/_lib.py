@@ -50,10 +50,35 @@ SIGNATURES = {
 }
 
 _lib = None
+# optional: an object with `.enabled` and `.add(name, start_event, end_event)`; when enabled every C-ABI
+# call is bracketed by CUDA events on the launching (current) stream (bench.py uses it for per-kernel times)
+kernel_timer = None
+
+
+class _Handle(object):
+    """Thin proxy over the ctypes handle (adds the optional per-call CUDA-event timing)."""
+
+    def __init__(self, h):
+        self._h = h
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        kt = kernel_timer
+        if kt is None or not kt.enabled or name in ("voge_error_string", "voge_version", "voge_trace_threads"):
+            return fn
+
+        def timed(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*args)
+            e1.record()
+            kt.add(name, e0, e1)
+            return r
+        return timed
 
 
 def lib():
-    """Load (once) and return the ctypes handle; raises RuntimeError if the .so is absent."""
+    """Load (once) and return the library handle; raises RuntimeError if the .so is absent."""
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
@@ -65,16 +90,13 @@ def lib():
             fn = getattr(h, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = h
+        _lib = _Handle(h)
     return _lib
 
 
 # number of kernels launched through the C ABI since import (bench.py reports it as gpu_launches)
 KERNELS_PER_CALL = {"rasterize_coarse": 3}
 launch_count = 0
-# optional hook: bench.py installs a callable(name) -> context manager to time individual ops with
-# CUDA events on the launching stream
-timing_hook = None
 
 
 def check(code, what):
