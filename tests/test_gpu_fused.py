@@ -249,8 +249,11 @@ def test_forward_pipeline_dense_ties_and_single_kernel(K, hw):
     stats = torch.zeros(4, dtype=torch.int64, device=DEV)
     p = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile, stats=stats, item_offsets=ioff)
     s = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile)
-    for x, y in zip(p, s):
-        assert torch.equal(x, y)
+    for name, x, y in zip(("idx", "weight", "len", "valid", "act", "dsd"), p, s):
+        if name == "weight":      # same maths, different summation order inside the blend (1-ulp level)
+            assert torch.allclose(x, y, rtol=1e-5, atol=1e-9, equal_nan=True)
+        else:
+            assert torch.equal(x, y), name
     assert torch.equal(p[0], a.vert_index)
     assert int(stats[0]) == ioff.total_items > 0          # every item evaluated exactly once
     assert int(stats[2]) > 0                              # the exact-key selection was exercised

@@ -65,7 +65,8 @@ with torch.no_grad():
         ref = _C.render_forward(verts, sig, origins, rays, off, tl, rects, thr_act, 1.0, K, tile, need_act=False)
         torch.cuda.synchronize()
         for nm, x, y in zip(("idx", "weight", "len", "valid"), out, ref):
-            print("  xcheck", nm, "equal" if torch.equal(x, y) else "DIFFERENT (%d)" % int((x != y).sum()))
+            print("  xcheck", nm, "equal" if torch.equal(x, y) else "DIFFERENT (%d, max rel %.2e)" % (
+                int((x != y).sum()), float(((x - y).abs() / y.abs().clamp_min(1e-30)).max())))
 tot = 0.0
 for nm, ev in times.items():
     ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev) / V

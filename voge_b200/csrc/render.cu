@@ -773,8 +773,10 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
             while (lo < m && (lm - s_ls[lo * NT + tid].x) * s_min >= kErfSat) { SE += s_E[lo * NT + tid]; ++lo; }
             float wg = 0.f;
             if (Em != 0.f) {
-                float D = SE;
-                for (int k = lo; k < cnt; ++k) {
+                float D = fmaf(Em, 0.5f, SE);         // k = m: Phi(0) = 1/2; the loop visits the neighbours only
+                for (int t = lo;; ++t) {
+                    const int k = t + (t >= m ? 1 : 0);
+                    if (k >= cnt) break;
                     const float2 lk = s_ls[k * NT + tid];
                     const float dl = lm - lk.x;
                     if (dl * s_min <= -kErfSat) break;
@@ -816,9 +818,12 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
             const float wgj = s_wg[j * NT + tid];
             const float gDj = -omega * wgj;
             // direct path through the trailing exp(-act_j)  +  rows m behind the window see Phi = 1
-            float gE = wgj / Ej + (total_gD - pref);
+            // i = j: c = 0 => Phi = 1/2 and the two d/d(len_j) terms cancel exactly; the loop visits the
+            // neighbours only (a warp iterates max-over-lanes(neighbours) times)
+            float gE = wgj / Ej + (total_gD - pref) + 0.5f * gDj;
             float gl = 0.f, gd = 0.f;
-            for (int i = lo_j; i <= hi_j; ++i) {
+            for (int t = lo_j; t < hi_j; ++t) {
+                const int i = t + (t >= j ? 1 : 0);
                 const float2 lsi = s_ls[i * NT + tid];
                 const float dl = lsi.x - lj;
                 const float gDi = -omega * s_wg[i * NT + tid];

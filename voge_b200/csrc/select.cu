@@ -295,7 +295,6 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const BlendArgs a) {
     // D_m = sum_k E_k Phi((len_m - len_k) s_k).  The list is sorted by len, so outside the window
     // |len_m - len_k| * min_k(s_k) < 4 the erf is saturated: Phi = 1 for k < lo(m) (their E_k are
     // carried in a running prefix sum -- lo(m) only moves forward), Phi = 0 behind the window.
-    // The summation order is the plain k = 0..cnt-1 order of the stand-alone aggregation kernel.
     {
         int lo = 0;
         float SE = 0.f;
@@ -308,14 +307,18 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const BlendArgs a) {
                 if (m < cnt) {
                     const float lm = s_ls[m * NT + tid].x;
                     while (lo < m && (lm - s_ls[lo * NT + tid].x) * s_min >= kErfSat) { SE += s_E[lo * NT + tid]; ++lo; }
-                    float D = SE;
-                    for (int k = lo; k < cnt; ++k) {
+                    // the k = m term is E_m / 2 exactly; the loop runs over the neighbours only, so a warp
+                    // iterates max-over-lanes(neighbours) times instead of max-over-lanes(neighbours) + 1
+                    const float Em = s_E[m * NT + tid];
+                    float D = fmaf(Em, 0.5f, SE);
+                    for (int t = lo;; ++t) {
+                        const int k = t + (t >= m ? 1 : 0);
+                        if (k >= cnt) break;
                         const float2 lk = s_ls[k * NT + tid];
                         const float dl = lm - lk.x;
                         if (dl * s_min <= -kErfSat) break;
                         D += s_E[k * NT + tid] * phi(dl * lk.y);
                     }
-                    const float Em = s_E[m * NT + tid];
                     wv[j] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
                 }
             }
