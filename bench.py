@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--hw", type=int, default=1024)
     ap.add_argument("--views", type=int, default=64)
-    ap.add_argument("--chunk", type=int, default=8, help="views rendered per renderer call")
+    ap.add_argument("--chunk", type=int, default=16, help="views rendered per renderer call (capped by the views of the rank)")
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
@@ -592,9 +592,9 @@ def main():
             "config": {"workload": "C5 synthetic scale sweep: %d Gaussians (10%% anisotropic, (N,3,3) sigmas), %dx%d, "
                                    "%d views sharded by camera, K=%d, thr=0.01, fwd+bwd to verts/sigmas/colours"
                                    % (args.n, H, W, args.views, args.k),
-                       "views_per_rank": count, "views_per_call": args.chunk,
+                       "views_per_rank": count, "views_per_call": min(args.chunk, count),
                        "l2": "no flush needed: each renderer call streams %.0f MB of fragments (+ %d MB targets), "
-                             ">> 126 MB L2" % (frag_bytes / 1e6, args.chunk * H * W * 12 // 10 ** 6)},
+                             ">> 126 MB L2" % (frag_bytes / 1e6, min(args.chunk, count) * H * W * 12 // 10 ** 6)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "loss": float(loss)}
     if not args.no_ref_gpu:

@@ -170,10 +170,12 @@ int voge_find_nearest_k(const float* len_in, const float* act_in, const float* d
  *   RayTracing.py:33-57 + rasterize_coarse.cu:20-42,:116-130 at `bin_size` px, if use_ref_bins]
  *   AND [conservative projected-ellipsoid bound]; tiles are `tile` x `tile` px (tile <= 16, divides
  *   bin_size).  rects (B,N,2) uint32 out = conservative PIXEL rectangle x0|x1<<16, y0|y1<<16 (inclusive,
- *   empty if x0 > x1); tile_counts (B,TY,TX) int32 must be ZEROED by the caller; tile_items (optional, same
+ *   empty if x0 > x1); tile_counts (B,TY,TX,S) int32, S = voge_bin_sub() counters per tile (entry n is counted in
+ *   counter n % S: L2 serialises atomics on one address), must be ZEROED by the caller; tile_items (optional, same
  *   shape, ZEROED) accumulates the rectangle area inside each tile (the tile's number of ITEMS, trace.cu).
- * voge_bin_fill: scatters Gaussian indices into tile_list using tile_offsets (B*TY*TX+1, int64,
- *   exclusive scan of tile_counts); cursor (B*TY*TX) int32 must be ZEROED by the caller.
+ * voge_bin_fill: scatters Gaussian indices into tile_list using tile_offsets (B*TY*TX*S+1, int64,
+ *   exclusive scan of tile_counts; the S segments of a tile are adjacent); cursor (B*TY*TX*S) int32 must be
+ *   ZEROED by the caller.
  * voge_render_forward: fragments.  out_idx (B,H,W,K) packed b*N+n / -1, out_weight, out_len
  *   (1e10 padded), out_valid (B,H,W) int64; out_act/out_dsd optional (NULL to skip);
  *   rects = the (B,N,2) rectangles of voge_bin_count (pixel units);
@@ -181,6 +183,7 @@ int voge_find_nearest_k(const float* len_in, const float* act_in, const float* d
  * voge_render_backward: d(len,act,dsd) (B,H,W,K) -> grad_verts (N,3), grad_sigmas (compact, NULL to
  *   skip); both ZEROED by the caller and accumulated into.  Only the first valid_num[r] slots of
  *   idx are read (merge_final rewrites -1 -> 0 in place, Aggregation.py:131).                                  */
+int voge_bin_sub(void);   /* counters / list segments per tile (S below) */
 int voge_bin_count(const float* verts, const float* sigmas, int sigma_kind, const float* R,
                    const float* T, const float* origins, const float* focal, const float* principal,
                    int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins,
@@ -199,7 +202,7 @@ int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind,
  *   voge_trace_hits: every item (tile-list entry x pixel of its rectangle inside the tile) is evaluated with
  *       the reference's arithmetic (ray_trace_voge.cu:188-193); hits (act < thr_act, len < 1e10, :197) are
  *       appended as (orderable len bits, local Gaussian index) to the pixel's segment.  The segments of a
- *       tile start at tile_item_offsets[tile] (B*TY*TX+1, int64 = exclusive scan of voge_bin_count's
+ *       tile start at tile_item_offsets[tile*S] (B*TY*TX*S+1, int64 = exclusive scan of voge_bin_count's
  *       tile_items) and hold one slot per rectangle covering the pixel; hits is
  *       (tile_item_offsets[last], 2) uint32 = (orderable len bits, index) pairs.  Out: counts / seg_base (B*TY*TX, NT) per pixel column
  *       (col = ly*tile + lx, NT = voge_trace_threads(tile)).

@@ -43,6 +43,14 @@ foot = cnt > 0
 print("in footprint: mean cnt %.2f  pairs %.2f  p50 %d p90 %d p99 %d max %d" % (
     float(cnt[foot].float().mean()), float(npair[foot].float().mean()),
     int(npair[foot].float().quantile(0.5)), int(npair[foot].float().quantile(0.9)), int(npair[foot].float().quantile(0.99)), int(npair.max())))
+# exact criterion: column k reaches row m iff |l_m - l_k| * s_k < 4
+dle = (ln[..., :, None] - ln[..., None, :]).abs() * sk[..., None, :]        # [m, k] * s_k
+paire = (dle < 4.0) & ok[..., :, None] & ok[..., None, :]
+npe = paire.sum((-1, -2)) - valid
+print("exact-reach ordered pairs: mean %.2f in footprint %.2f" % (float(npe.float().mean()), float(npe[foot].float().mean())))
+wsz_e = paire.sum(-2)                        # per column k: rows in reach (incl self)
+blk_e = wsz_e.view(V, HW // 4, 4, HW // 8, 8, K).permute(0, 1, 3, 2, 4, 5).reshape(V, HW // 4, HW // 8, 32, K)
+print("per warp (column-major, exact reach): sum_k max_lanes(window incl self) %.1f" % float(blk_e.max(3).values.sum(-1).float().mean()))
 # warp-level (8x4 blocks): max over lanes of per-slot window size summed over slots vs max over lanes of total
 wsz = pair.sum(-1)                          # (B,H,W,K) window size incl self
 B = V

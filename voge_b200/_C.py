@@ -300,8 +300,9 @@ def sigma_kind(sigmas):
 
 def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act, use_ref_bins, bin_size,
               tile):
-    """-> (tile_offsets (B*TY*TX+1,) int64, tile_list (total,) int32, rects (B,N,2) int32,
-    tile_item_offsets (B*TY*TX+1,) int64 with .total_items).  One host sync (the two totals)."""
+    """-> (tile_offsets (B*TY*TX*S+1,) int64, tile_list (total,) int32, rects (B,N,2) int32,
+    tile_item_offsets (B*TY*TX*S+1,) int64 with .total_items), S = voge_bin_sub() list segments per tile.
+    One host sync (the two totals)."""
     verts, sigmas = f32c(verts), f32c(sigmas)
     R, T, origins, focal, principal = f32c(R), f32c(T), f32c(origins), f32c(focal), f32c(principal)
     B, N = int(R.shape[0]), int(verts.shape[0])
@@ -312,7 +313,8 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
         rects = torch.empty((B, N, 2), dtype=torch.int32, device=dev)
         # row 0: list entries per tile, row 1: items (rectangle pixels) per tile; one leading zero column so
         # that the inclusive scan is the exclusive offset table
-        counts = torch.zeros((2, B * TY * TX + 1), dtype=torch.int32, device=dev)
+        S = int(lib().voge_bin_sub())
+        counts = torch.zeros((2, B * TY * TX * S + 1), dtype=torch.int32, device=dev)
         check(lib().voge_bin_count(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(R), ptr(T), ptr(origins),
                                    ptr(focal), ptr(principal), B, N, H, W, float(thr), float(thr_act),
                                    int(bool(use_ref_bins)), int(bin_size), int(tile), ptr(rects), ptr(counts[0, 1:]),
@@ -321,7 +323,7 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
         totals = offsets[:, -1].tolist()
         total, total_items = int(totals[0]), int(totals[1])
         tile_list = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
-        cursor = torch.zeros((B * TY * TX,), dtype=torch.int32, device=dev)
+        cursor = torch.zeros((B * TY * TX * S,), dtype=torch.int32, device=dev)
         check(lib().voge_bin_fill(ptr(rects), ptr(offsets[0]), ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
                                   stream_of(verts)), "bin_fill")
     item_offsets = offsets[1]
@@ -354,7 +356,7 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
                   "render_forward")
             return idx, weight, tlen, valid, act, dsd
         nt = int(lib().voge_trace_threads(int(tile)))
-        n_tiles = int(tile_offsets.numel()) - 1
+        n_tiles = (int(tile_offsets.numel()) - 1) // int(lib().voge_bin_sub())
         total_items = int(item_offsets.total_items)
         counts = torch.empty((n_tiles * nt,), dtype=torch.int32, device=dev)
         seg_base = torch.empty((n_tiles * nt,), dtype=torch.int64, device=dev)

@@ -37,6 +37,7 @@ SIGNATURES = {
     "voge_ray_trace_ray": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "voge_ray_trace_ray_backward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "voge_find_nearest_k": (_I, [_P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "voge_bin_sub": (_I, []),
     "voge_bin_count": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _P, _P, _P, _P]),
     "voge_bin_fill": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "voge_render_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P,
@@ -64,7 +65,7 @@ class _Handle(object):
     def __getattr__(self, name):
         fn = getattr(self._h, name)
         kt = kernel_timer
-        if kt is None or not kt.enabled or name in ("voge_error_string", "voge_version", "voge_trace_threads"):
+        if kt is None or not kt.enabled or name in ("voge_error_string", "voge_version", "voge_trace_threads", "voge_bin_sub"):
             return fn
 
         def timed(*args):

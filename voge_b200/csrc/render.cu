@@ -189,12 +189,12 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
         } else {
             rc = make_uint2((unsigned)x0 | ((unsigned)x1 << 16), (unsigned)y0 | ((unsigned)y1 << 16));
             const int tx0 = x0 / a.tile, tx1 = x1 / a.tile, ty0 = y0 / a.tile, ty1 = y1 / a.tile;
-            int32_t* cnt = a.tile_counts + (int64_t)b * a.TX * a.TY;
-            int32_t* itm = a.tile_items != nullptr ? a.tile_items + (int64_t)b * a.TX * a.TY : nullptr;
+            int32_t* cnt = a.tile_counts + (int64_t)b * a.TX * a.TY * kBinSub + (g & (kBinSub - 1));
+            int32_t* itm = a.tile_items != nullptr ? a.tile_items + (int64_t)b * a.TX * a.TY * kBinSub + (g & (kBinSub - 1)) : nullptr;
             for (int ty = ty0; ty <= ty1; ++ty)
                 for (int tx = tx0; tx <= tx1; ++tx) {
-                    atomicAdd(cnt + ty * a.TX + tx, 1);
-                    if (itm != nullptr) atomicAdd(itm + ty * a.TX + tx, rect_area_in_tile(rc, tx, ty, a.tile));
+                    atomicAdd(cnt + (ty * a.TX + tx) * kBinSub, 1);
+                    if (itm != nullptr) atomicAdd(itm + (ty * a.TX + tx) * kBinSub, rect_area_in_tile(rc, tx, ty, a.tile));
                 }
         }
         a.rects[(int64_t)b * a.N + g] = rc;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__
         const int tx0 = (rc.x & 0xffff) / tile, tx1 = (rc.x >> 16) / tile, ty0 = (rc.y & 0xffff) / tile, ty1 = (rc.y >> 16) / tile;
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) {
-                const int64_t t = ((int64_t)b * TY + ty) * TX + tx;
+                const int64_t t = (((int64_t)b * TY + ty) * TX + tx) * kBinSub + (g & (kBinSub - 1));
                 const int slot = atomicAdd(cursor + t, 1);
                 tile_list[tile_offsets[t] + slot] = g;
             }
@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 4)) render_fwd_kernel(con
     s_lim[tid] = pack_key(kEmptyLen, 0);
 
     const int64_t tile_id = ((int64_t)b * a.TY + ty) * a.TX + tx;
-    const int64_t beg = a.tile_offsets[tile_id];
-    const int n = (int)(a.tile_offsets[tile_id + 1] - beg);
+    const int64_t beg = a.tile_offsets[tile_id * kBinSub];
+    const int n = (int)(a.tile_offsets[(tile_id + 1) * kBinSub] - beg);
     const int32_t* list = a.tile_list + beg;
     __syncthreads();
 
@@ -889,6 +889,8 @@ extern "C" int voge_render_backward_fused(const float* verts, const float* sigma
     return by_threads(std::integral_constant<int, 9>{});
 }
 
+extern "C" int voge_bin_sub(void) { return voge::kBinSub; }
+
 extern "C" int voge_bin_count(const float* verts, const float* sigmas, int sigma_kind, const float* Rm,
                               const float* Tv, const float* origins, const float* focal, const float* principal,
                               int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins, int bin_size,
@@ -905,7 +907,7 @@ extern "C" int voge_bin_count(const float* verts, const float* sigmas, int sigma
     a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
     if (a.TX > 65535 || a.TY > 65535) return (int)cudaErrorInvalidValue;
     a.rects = reinterpret_cast<uint2*>(rects); a.tile_counts = tile_counts; a.tile_items = tile_items;
-    dim3 grid(min(cdiv(N, 256), kNumSMs * 8), B);
+    dim3 grid(cdiv(N, 256), B);   // one Gaussian per thread: the dependent load -> atomic -> store chain is pure latency
     bin_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     VOGE_LAUNCH_CHECK();
     return 0;
@@ -915,7 +917,7 @@ extern "C" int voge_bin_fill(const uint32_t* rects, const int64_t* tile_offsets,
                              int H, int W, int tile, int32_t* tile_list, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || N <= 0) return 0;
-    dim3 grid(min(cdiv(N, 256), kNumSMs * 8), B);
+    dim3 grid(cdiv(N, 256), B);   // one Gaussian per thread: the dependent load -> atomic -> store chain is pure latency
     bin_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(rects), tile_offsets, cursor,
                                                              B, N, cdiv(W, tile), cdiv(H, tile), tile, tile_list);
     VOGE_LAUNCH_CHECK();

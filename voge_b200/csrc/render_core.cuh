@@ -96,6 +96,11 @@ __host__ __device__ __forceinline__ int rect_area_in_tile(uint2 rc, int tx, int 
     return max(xh - xl + 1, 0) * max(yh - yl + 1, 0);
 }
 
+// Every tile owns kBinSub counters / list segments (entry g goes to segment g % kBinSub): L2 serialises atomics
+// on one address, and a C5 tile receives several hundred entries per view.  The segments of a tile are
+// adjacent, so a tile's list is tile_offsets[tile * kBinSub] .. tile_offsets[(tile + 1) * kBinSub].
+constexpr int kBinSub = 8;
+
 // threads per tile CTA (= pixel columns per tile in the per-tile hit tables)
 static inline int tile_threads(int tile) {
     const int px = tile * tile;

@@ -30,10 +30,10 @@ struct TraceArgs {
     const float* sigmas;
     const float* origins;              // (B,3)
     const float* rays;                 // (B,H,W,3)
-    const int64_t* tile_offsets;       // (B*TY*TX + 1) into tile_list
+    const int64_t* tile_offsets;       // (B*TY*TX*kBinSub + 1) into tile_list
     const int32_t* tile_list;          // local Gaussian indices
     const uint2* rects;                // (B,N) conservative pixel rectangles from bin_count_kernel
-    const int64_t* tile_item_offsets;  // (B*TY*TX + 1) exclusive scan of tile_items
+    const int64_t* tile_item_offsets;  // (B*TY*TX*kBinSub + 1) exclusive scan of tile_items
     float thr_act;
     int B, N, H, W, tile, TX, TY;
     int32_t* counts;                   // out (B*TY*TX, NT): hits stored per pixel column (col = ly*tile + lx)
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     s_cnt[tid] = 0;
     for (int i = tid; i < 17 * 17; i += NT) s_diff[i] = 0;
 
-    const int64_t beg = a.tile_offsets[tile_id];
-    const int n = (int)(a.tile_offsets[tile_id + 1] - beg);
+    const int64_t beg = a.tile_offsets[tile_id * kBinSub];
+    const int n = (int)(a.tile_offsets[(tile_id + 1) * kBinSub] - beg);
     const int32_t* list = a.tile_list + beg;
     const int warp = tid >> 5, lane = tid & 31;
     const int px0 = tx * tile, py0 = ty * tile;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     int cover = 0;
     if (tid < tile * tile)
         for (int y = 0; y <= ly; ++y) cover += s_rowp[y * 16 + lx];
-    const int64_t tile_base = a.tile_item_offsets[tile_id];
+    const int64_t tile_base = a.tile_item_offsets[tile_id * kBinSub];
     {
         const int2 sc = block_scan<NT>(cover, s_wsum, lane, warp);
         s_base[tid] = sc.x - cover;
