@@ -181,22 +181,37 @@ def test_fused_edge_cases(oracle):
     assert torch.isfinite(covp.grad).all() and covp.grad.abs().sum() > 0
 
 
-def test_camera_gradients_use_op_by_op_path():
-    """rays / origins that require grad (pose optimisation) fall back to the op-by-op chain, whose
-    _RayTraceVoGE backward returns grad_rays (reference RayTracing.py:179-206)."""
+@pytest.mark.parametrize("kind", ["iso", "full"])
+def test_camera_gradients_fused_match_op_by_op(kind):
+    """Pose optimisation: rays / origins that require grad go through the fused path too; its backward emits
+    d/d(rays), d/d(origins) (reference grad_rays, RayTracing.py:179-206 / ray_trace_voge.cu:283-332), which
+    autograd carries on to R, T and the focal length through the ray generator."""
     from voge_b200.cameras import PerspectiveCameras
     from voge_b200.Meshes import GaussianMeshesNaive
-    from voge_b200.Renderer import GaussianRenderer, GaussianRenderSettings, get_silhouette
-    sc = small_scene(seed=17, aniso=False, n=150)
-    Rp = sc["R"].to(DEV).requires_grad_(True)
-    Tp = sc["T"].to(DEV).requires_grad_(True)
-    cams = PerspectiveCameras(focal_length=sc["focal"], principal_point=(sc["principal"],), R=Rp, T=Tp, in_ndc=False,
-                              image_size=(sc["image_size"],), device=DEV)
-    r = GaussianRenderer(cams, GaussianRenderSettings(image_size=sc["image_size"], max_assign=6, max_point_per_bin=150)).to(DEV)
-    f = r(GaussianMeshesNaive(sc["verts"].to(DEV), sc["sigmas"][:, 0, 0].contiguous().to(DEV)))
-    get_silhouette(f).sum().backward()
-    assert Rp.grad is not None and torch.isfinite(Rp.grad).all() and Rp.grad.abs().sum() > 0
-    assert Tp.grad is not None and torch.isfinite(Tp.grad).all() and Tp.grad.abs().sum() > 0
+    from voge_b200.Renderer import GaussianRenderer, GaussianRenderSettings, get_silhouette, to_white_background
+    sc = small_scene(seed=17, aniso=(kind == "full"), n=150, views=2)
+    H, W = sc["image_size"]
+    sig = sc["sigmas"] if kind == "full" else sc["sigmas"][:, 0, 0].contiguous()
+    colors = sc["colors"].to(DEV)
+    target = torch.rand(2, H, W, 3, generator=torch.Generator().manual_seed(3)).to(DEV)
+    grads = {}
+    for fused in (True, False):
+        Rp = sc["R"].to(DEV).requires_grad_(True)
+        Tp = sc["T"].to(DEV).requires_grad_(True)
+        fp = torch.full((2, 2), float(sc["focal"]), device=DEV, requires_grad=True)
+        cams = PerspectiveCameras(focal_length=fp, principal_point=(sc["principal"],), R=Rp, T=Tp, in_ndc=False,
+                                  image_size=((H, W),), device=DEV)
+        r = GaussianRenderer(cams, GaussianRenderSettings(image_size=(H, W), max_assign=6, max_point_per_bin=150)).to(DEV)
+        r.use_fused = fused
+        vp = sc["verts"].to(DEV).requires_grad_(True)
+        f = r(GaussianMeshesNaive(vp, sig.to(DEV)))
+        loss = ((to_white_background(f, colors) - target) ** 2).mean() + 1e-2 * get_silhouette(f).mean() \
+            + 1e-3 * f.vert_hit_length.clamp(max=100).mean()
+        loss.backward()
+        grads[fused] = (Rp.grad.clone(), Tp.grad.clone(), fp.grad.clone(), vp.grad.clone())
+    for name, a, b in zip(("R", "T", "focal", "verts"), grads[True], grads[False]):
+        assert torch.isfinite(a).all() and a.abs().sum() > 0, name
+        assert (a - b).abs().max() <= 2e-4 * b.abs().max() + 1e-10, (name, float((a - b).abs().max()), float(b.abs().max()))
 
 
 def test_sampler_api_roundtrip(oracle):

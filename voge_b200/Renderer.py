@@ -102,8 +102,6 @@ class GaussianRenderer(nn.Module):
     def _fusable(self, verts, sigmas, rays, origins):
         if not (verts.is_cuda and verts.dim() == 3 and verts.shape[0] == 1 and verts.dtype == torch.float32):
             return False
-        if rays.requires_grad or origins.requires_grad:   # camera gradients: op-by-op path
-            return False
         return sigmas.dim() in (1, 2, 3)
 
     def _forward_fused(self, verts, sigmas, rays, origins):

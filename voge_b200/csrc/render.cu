@@ -654,11 +654,14 @@ struct FusedBwdArgs {
     int B, N, H, W, K;
     float* grad_packed;      // (N, 4 | 8 | 12) for kind 1 | 3 | 9: [d verts(3), d sigma...] in float4 units
     int need_sigma;
+    float* grad_rays;        // optional (B,H,W,3), written in full: d/d(ray direction) (pose optimisation)
+    float* grad_origins;     // optional (B,3), zeroed by the caller: d/d(ray origin) = -sum over the view's hits of d/d(mu')
 };
 
+template <bool CAM>
 __device__ __forceinline__ void geom_grad_accumulate(const FusedBwdArgs& a, int g, float m0, float m1, float m2,
                                                      const float* S, float d0, float d1, float d2, float ksk,
-                                                     float msk, float gl, float ga, float gd) {
+                                                     float msk, float gl, float ga, float gd, float* cam_acc) {
     const float g_ksk = (ga * msk - gl) * msk / (ksk * ksk) + gd;   // ray_trace_voge.cu:324-326
     const float g_msk = (gl - 2.f * ga * msk) / ksk;
     const float g_msm = ga;
@@ -674,6 +677,15 @@ __device__ __forceinline__ void geom_grad_accumulate(const FusedBwdArgs& a, int 
     const float gv0 = g_msk * Sd0 + g_msm * (Sm0 + Stm0);
     const float gv1 = g_msk * Sd1 + g_msm * (Sm1 + Stm1);
     const float gv2 = g_msk * Sd2 + g_msm * (Sm2 + Stm2);
+    if (CAM) {
+        // d/d(ray) = g_ksk (S + S^T) d + g_msk S^T mu  (ray_trace_voge.cu:41-91); d/d(origin) = -d/d(mu')
+        const float Std0 = S[0] * d0 + S[3] * d1 + S[6] * d2, Std1 = S[1] * d0 + S[4] * d1 + S[7] * d2,
+                    Std2 = S[2] * d0 + S[5] * d1 + S[8] * d2;
+        cam_acc[0] += g_ksk * (Sd0 + Std0) + g_msk * Stm0;
+        cam_acc[1] += g_ksk * (Sd1 + Std1) + g_msk * Stm1;
+        cam_acc[2] += g_ksk * (Sd2 + Std2) + g_msk * Stm2;
+        cam_acc[3] -= gv0; cam_acc[4] -= gv1; cam_acc[5] -= gv2;
+    }
     const float dv[3] = {d0, d1, d2}, mv[3] = {m0, m1, m2};
     if (a.kind == 1) {
         const float tr = g_ksk * (d0 * d0 + d1 * d1 + d2 * d2) + g_msk * (m0 * d0 + m1 * d1 + m2 * d2) +
@@ -704,7 +716,7 @@ __device__ __forceinline__ void geom_grad_accumulate(const FusedBwdArgs& a, int 
     }
 }
 
-template <int NT, int KIND>
+template <int NT, int KIND, bool CAM>
 __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const size_t A = (size_t)a.K * NT;
@@ -721,13 +733,15 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
     const int b = (int)(wid / per_view);
     const int wb = (int)(wid % per_view);
     const int xi = (wb % bw) * 8 + (lane & 7), yi = (wb / bw) * 4 + (lane >> 3);
-    if (xi >= a.W || yi >= a.H) return;
-    const int64_t r = ((int64_t)b * a.H + yi) * a.W + xi;
-    const int cnt = (int)min((int64_t)a.K, a.valid[r]);
-    if (cnt == 0) return;
+    const bool live = xi < a.W && yi < a.H;
+    if (!CAM && !live) return;       // with camera gradients every lane stays for the warp reduction at the end
+    const int64_t r = live ? ((int64_t)b * a.H + yi) * a.W + xi : 0;
+    const int cnt = live ? (int)min((int64_t)a.K, a.valid[r]) : 0;
+    if (!CAM && cnt == 0) return;
     const float d0 = a.rays[r * 3 + 0], d1 = a.rays[r * 3 + 1], d2 = a.rays[r * 3 + 2];
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
     const float omega = a.omega;
+    float cam_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d/d(ray) of this pixel, d/d(origin) partial sum
     const int32_t* i_idx = a.idx + r * a.K;
     const float* i_gw = a.g_weight + r * a.K;
     const int pack_off = b * a.N;
@@ -849,7 +863,21 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
             const Prod9 pm = exact_row_products(m0, m1, m2, S);
             const float ksk = exact_contract(pd, d0, d1, d2);
             const float msk = exact_contract(pm, d0, d1, d2);
-            geom_grad_accumulate(a, g, m0, m1, m2, S, d0, d1, d2, ksk, msk, gl, ga, gd);
+            geom_grad_accumulate<CAM>(a, g, m0, m1, m2, S, d0, d1, d2, ksk, msk, gl, ga, gd, cam_acc);
+        }
+    }
+    if (CAM) {
+        if (a.grad_rays != nullptr && live) {
+            a.grad_rays[r * 3 + 0] = cam_acc[0]; a.grad_rays[r * 3 + 1] = cam_acc[1]; a.grad_rays[r * 3 + 2] = cam_acc[2];
+        }
+        if (a.grad_origins != nullptr) {
+            __syncwarp();
+#pragma unroll
+            for (int q = 3; q < 6; ++q) {
+                float v = cam_acc[q];          // the 32 lanes of a warp belong to one view
+                for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_down_sync(0xffffffffu, v, sft);
+                if (lane == 0) atomicAdd(a.grad_origins + 3 * b + (q - 3), v);
+            }
         }
     }
 }
@@ -860,15 +888,16 @@ extern "C" int voge_render_backward_fused(const float* verts, const float* sigma
                                           const float* origins, const float* rays, const int32_t* idx,
                                           const int64_t* valid, const float* grad_weight,
                                           const float* grad_len_out, float absorptivity, int B, int N, int H,
-                                          int W, int K, float* grad_packed, int need_sigma,
-                                          voge_stream_t stream) {
+                                          int W, int K, float* grad_packed, int need_sigma, float* grad_rays,
+                                          float* grad_origins, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
     FusedBwdArgs a{verts, sigmas, sigma_kind, origins, rays, idx, valid, grad_weight, grad_len_out, absorptivity,
-                   B, N, H, W, K, grad_packed, need_sigma};
+                   B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins};
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     const int64_t warps = (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
     cudaStream_t s = (cudaStream_t)stream;
+    const bool cam = grad_rays != nullptr || grad_origins != nullptr;
     auto launch = [&](auto kernel, int nt) -> int {
         const size_t smem = (size_t)K * nt * 16;
         if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
@@ -878,15 +907,19 @@ extern "C" int voge_render_backward_fused(const float* verts, const float* sigma
         VOGE_LAUNCH_CHECK();
         return 0;
     };
-    auto by_threads = [&](auto kind_tag) -> int {
+    auto by_threads = [&](auto kind_tag, auto cam_tag) -> int {
         constexpr int KIND = decltype(kind_tag)::value;
-        if (K <= 56) return launch(render_bwd_fused_kernel<128, KIND>, 128);
-        if (K <= 200) return launch(render_bwd_fused_kernel<64, KIND>, 64);
-        return launch(render_bwd_fused_kernel<32, KIND>, 32);
+        constexpr bool CAM = decltype(cam_tag)::value;
+        if (K <= 56) return launch(render_bwd_fused_kernel<128, KIND, CAM>, 128);
+        if (K <= 200) return launch(render_bwd_fused_kernel<64, KIND, CAM>, 64);
+        return launch(render_bwd_fused_kernel<32, KIND, CAM>, 32);
     };
-    if (sigma_kind == 1) return by_threads(std::integral_constant<int, 1>{});
-    if (sigma_kind == 3) return by_threads(std::integral_constant<int, 3>{});
-    return by_threads(std::integral_constant<int, 9>{});
+    auto by_kind = [&](auto cam_tag) -> int {
+        if (sigma_kind == 1) return by_threads(std::integral_constant<int, 1>{}, cam_tag);
+        if (sigma_kind == 3) return by_threads(std::integral_constant<int, 3>{}, cam_tag);
+        return by_threads(std::integral_constant<int, 9>{}, cam_tag);
+    };
+    return cam ? by_kind(std::true_type{}) : by_kind(std::false_type{});
 }
 
 extern "C" int voge_bin_sub(void) { return voge::kBinSub; }

@@ -3,7 +3,8 @@
 
 Forward : per-view tile culling (voge_bin_count / voge_bin_fill) -> voge_render_forward
 Backward: voge_render_backward_fused -- recompute the hits, analytic blend backward, chain rule straight
-          into (N,3) / compact-sigma gradients for all views of the batch (the reference materialises
+          into (N,3) / compact-sigma gradients for all views of the batch, plus d/d(rays), d/d(origins) when
+          the camera requires grad (the reference materialises
           (B*N,3) and (B*N,3,3) gradient tensors and differentiates ~15 PyTorch ops over (R,K,K)).
 """
 import math
@@ -50,7 +51,7 @@ class _RenderFused(torch.autograd.Function):
         idx, weight, tlen, valid, _, _ = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list, rects,
                                                            thr_act, absorptivity, K, tile, need_act=False,
                                                            item_offsets=item_offsets)
-        if verts.requires_grad or sigmas.requires_grad:
+        if verts.requires_grad or sigmas.requires_grad or origins.requires_grad or rays.requires_grad:
             # recompute-not-store: only the inputs are kept; the backward re-evaluates the K hits per
             # pixel from idx (the reference saves mus, isigmas (B*N copies), rays, sel_idx and the
             # PyTorch aggregation saves ~10 (R,K,K) tensors)
@@ -70,10 +71,12 @@ class _RenderFused(torch.autograd.Function):
         verts, sigmas, origins, rays = ctx.saved_tensors
         if g_weight is None:
             g_weight = torch.zeros(ctx.idx.shape, dtype=torch.float32, device=ctx.idx.device)
-        g_verts, g_sig = _C.render_backward_fused(verts, sigmas, origins, rays, ctx.idx, ctx.valid,
-                                                  g_weight.contiguous(), g_len_out, ctx.absorptivity,
-                                                  need_sigma=ctx.needs_input_grad[1])
-        return (g_verts, g_sig) + (None,) * 12
+        # camera gradients (pose optimisation): d/d(origins), d/d(rays) come out of the same kernel and flow
+        # on to R, T, focal through the ray generator's autograd graph (voge_b200/cameras.py)
+        g_verts, g_sig, g_rays, g_org = _C.render_backward_fused(
+            verts, sigmas, origins, rays, ctx.idx, ctx.valid, g_weight.contiguous(), g_len_out, ctx.absorptivity,
+            need_sigma=ctx.needs_input_grad[1], need_rays=ctx.needs_input_grad[3], need_origins=ctx.needs_input_grad[2])
+        return (g_verts, g_sig, g_org, g_rays) + (None,) * 10
 
 
 def render_fused(verts, sigmas, origins, rays, R, T, focal, principal, image_size, thr, absorptivity, K,
