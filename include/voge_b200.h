@@ -198,7 +198,10 @@ int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind,
                         int32_t* out_idx, float* out_weight, float* out_len, int64_t* out_valid,
                         float* out_act, float* out_dsd, uint64_t* stats, voge_stream_t stream);
 /* ---- forward pipeline of the fused renderer (csrc/trace.cu, csrc/select.cu) ----------------------------
- * Same fragments as voge_render_forward, in three launches and without any per-pixel capacity limit:
+ * Same fragments as voge_render_forward, in three launches and without any per-pixel capacity limit.
+ * These kernels (and voge_render_backward_fused) read the Gaussians from packed 16-byte-aligned records
+ * written by voge_pack_gaussians: out (N, 4 | 8 | 12) floats for sigma_kind 1 | 3 | 9 =
+ * [x,y,z,2s] | [x,y,z,2s0, 2s1,2s2,0,0] | [x,y,z, 2S00..2S22] (S = 2 sigma, Renderer.py:137):
  *   voge_trace_hits: every item (tile-list entry x pixel of its rectangle inside the tile) is evaluated with
  *       the reference's arithmetic (ray_trace_voge.cu:188-193); hits (act < thr_act, len < 1e10, :197) are
  *       appended as (orderable len bits, local Gaussian index) to the pixel's segment.  The segments of a
@@ -213,7 +216,9 @@ int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind,
  *   stats optional 4 x uint64 ([0] items evaluated, [2] pixels selected with the exact 64-bit keys), zeroed
  *   by the caller.                                                                                         */
 int voge_trace_threads(int tile);
-int voge_trace_hits(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
+int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int N, float* out,
+                        voge_stream_t stream);
+int voge_trace_hits(const float* gauss, int sigma_kind, const float* origins,
                     const float* rays, const int64_t* tile_offsets, const int32_t* tile_list,
                     const uint32_t* rects, const int64_t* tile_item_offsets, float thr_act, int B, int N,
                     int H, int W, int tile, int32_t* counts, int64_t* seg_base, uint32_t* hits,
@@ -221,7 +226,7 @@ int voge_trace_hits(const float* verts, const float* sigmas, int sigma_kind, con
 int voge_select_topk(const int32_t* counts, const int64_t* seg_base, const uint32_t* hits,
                      int B, int N, int H, int W, int K, int tile,
                      int32_t* out_idx, int64_t* out_valid, uint64_t* stats, voge_stream_t stream);
-int voge_blend_weights(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
+int voge_blend_weights(const float* gauss, int sigma_kind, const float* origins,
                        const float* rays, const int32_t* idx, const int64_t* valid, float absorptivity,
                        int B, int N, int H, int W, int K, float* out_weight, float* out_len,
                        float* out_act, float* out_dsd, voge_stream_t stream);
@@ -242,7 +247,7 @@ int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind
  * Camera gradients (pose optimisation, reference grad_rays of ray_trace_voge.cu:283-332): grad_rays (B,H,W,3),
  * optional, written in full; grad_origins (B,3), optional, ZEROED by the caller (= -sum of d/d(mu') over the
  * view's hits, since mu' = verts - origin, Renderer.py:130).                                        */
-int voge_render_backward_fused(const float* verts, const float* sigmas, int sigma_kind,
+int voge_render_backward_fused(const float* gauss, int sigma_kind,
                                const float* origins, const float* rays, const int32_t* idx,
                                const int64_t* valid_num, const float* grad_weight,
                                const float* grad_len_out, float absorptivity,

@@ -331,8 +331,18 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
     return offsets[0], tile_list, rects, item_offsets
 
 
+def pack_gaussians(verts, sigmas):
+    """-> (N, 4 | 8 | 12) f32 records [x, y, z, S = 2 sigma ...] (16-byte aligned) read by the fused kernels."""
+    verts, sigmas = f32c(verts), f32c(sigmas)
+    N, kind = int(verts.shape[0]), sigma_kind(sigmas)
+    with torch.cuda.device(verts.device):
+        out = torch.empty((N, {1: 4, 3: 8, 9: 12}[kind]), dtype=torch.float32, device=verts.device)
+        check(lib().voge_pack_gaussians(ptr(verts), ptr(sigmas), kind, N, ptr(out), stream_of(verts)), "pack_gaussians")
+    return out
+
+
 def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects, thr_act, absorptivity, K, tile,
-                   need_act=True, stats=None, item_offsets=None):
+                   need_act=True, stats=None, item_offsets=None, gauss=None):
     """Fragments of the fused renderer.  With item_offsets (bin_views' fourth result): trace_hits ->
     select_topk -> blend_weights, no per-pixel capacity limit.  Without: the one-launch shared-memory top-K
     kernel (voge_render_forward) -- same results, kept for cross-checks and very large item counts."""
@@ -355,19 +365,21 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
                                             ptr(tlen), ptr(valid), ptr(act), ptr(dsd), ptr(stats), st),
                   "render_forward")
             return idx, weight, tlen, valid, act, dsd
+        if gauss is None:
+            gauss = pack_gaussians(verts, sigmas)
         nt = int(lib().voge_trace_threads(int(tile)))
         n_tiles = (int(tile_offsets.numel()) - 1) // int(lib().voge_bin_sub())
         total_items = int(item_offsets.total_items)
         counts = torch.empty((n_tiles * nt,), dtype=torch.int32, device=dev)
         seg_base = torch.empty((n_tiles * nt,), dtype=torch.int64, device=dev)
         hits = torch.empty((max(total_items, 1), 2), dtype=torch.int32, device=dev)
-        check(lib().voge_trace_hits(ptr(verts), ptr(sigmas), skind, ptr(origins), ptr(rays), ptr(tile_offsets),
+        check(lib().voge_trace_hits(ptr(gauss), skind, ptr(origins), ptr(rays), ptr(tile_offsets),
                                     ptr(tile_list), ptr(rects), ptr(item_offsets), float(thr_act), B, N, H, W,
                                     int(tile), ptr(counts), ptr(seg_base), ptr(hits), ptr(stats), st),
               "trace_hits")
         check(lib().voge_select_topk(ptr(counts), ptr(seg_base), ptr(hits), B, N, H, W, K, int(tile),
                                      ptr(idx), ptr(valid), ptr(stats), st), "select_topk")
-        check(lib().voge_blend_weights(ptr(verts), ptr(sigmas), skind, ptr(origins), ptr(rays), ptr(idx), ptr(valid),
+        check(lib().voge_blend_weights(ptr(gauss), skind, ptr(origins), ptr(rays), ptr(idx), ptr(valid),
                                        float(absorptivity), B, N, H, W, K, ptr(weight), ptr(tlen), ptr(act), ptr(dsd),
                                        st), "blend_weights")
     return idx, weight, tlen, valid, act, dsd
@@ -390,7 +402,7 @@ def render_backward(verts, sigmas, origins, rays, idx, valid, g_len, g_act, g_ds
 
 
 def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_len_out, absorptivity,
-                          need_sigma=True, need_rays=False, need_origins=False):
+                          need_sigma=True, need_rays=False, need_origins=False, gauss=None):
     """-> (g_verts, g_sigmas | None, g_rays (B,H,W,3) | None, g_origins (B,3) | None)"""
     verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
     idx, g_weight = i32c(idx), f32c(g_weight)
@@ -401,10 +413,12 @@ def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_
     width = {1: 4, 3: 8, 9: 12}[kind]
     dev = verts.device
     with torch.cuda.device(dev):
+        if gauss is None:
+            gauss = pack_gaussians(verts, sigmas)
         packed = torch.zeros((N, width), dtype=torch.float32, device=dev)
         g_rays = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev) if need_rays else None
         g_org = torch.zeros((B, 3), dtype=torch.float32, device=dev) if need_origins else None
-        check(lib().voge_render_backward_fused(ptr(verts), ptr(sigmas), kind, ptr(origins), ptr(rays),
+        check(lib().voge_render_backward_fused(ptr(gauss), kind, ptr(origins), ptr(rays),
                                                ptr(idx), ptr(valid), ptr(g_weight), ptr(g_len_out),
                                                float(absorptivity), B, N, H, W, K, ptr(packed), int(bool(need_sigma)),
                                                ptr(g_rays), ptr(g_org), stream_of(verts)), "render_backward_fused")

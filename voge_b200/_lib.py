@@ -43,10 +43,11 @@ SIGNATURES = {
     "voge_render_forward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _F, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P,
                                  _P, _P, _P]),
     "voge_trace_threads": (_I, [_I]),
-    "voge_trace_hits": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "voge_pack_gaussians": (_I, [_P, _P, _I, _I, _P, _P]),
+    "voge_trace_hits": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "voge_select_topk": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "voge_blend_weights": (_I, [_P, _P, _I, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "voge_render_backward_fused": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "voge_blend_weights": (_I, [_P, _I, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "voge_render_backward_fused": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
     "voge_render_backward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
 }
 

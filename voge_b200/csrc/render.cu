@@ -641,8 +641,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(const RenderBwdArgs a) 
 // analytically inside the depth window where the erf is not saturated, and the chain rule of
 // ray_trace_voge.cu:324-330 is applied straight into the (N,.) parameter gradients.
 struct FusedBwdArgs {
-    const float* verts;
-    const float* sigmas;
+    const float* gauss;      // packed records (voge_pack_gaussians)
     int kind;
     const float* origins;
     const float* rays;
@@ -767,7 +766,7 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
                 const int g = gv[j] - pack_off;
                 Hit h;
                 h.len = kEmptyLen; h.act = kEmptyLen; h.dsd = 0.f;
-                if (g >= 0 && g < a.N) h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, d0, d1, d2);
+                if (g >= 0 && g < a.N) h = exact_hit_packed<KIND>(a.gauss, g, c0, c1, c2, d0, d1, d2);
                 const float sk = sqrtf(h.dsd + 1e-10f);
                 s_ls[k * NT + tid] = make_float2(h.len, sk);
                 s_E[k * NT + tid] = expf(-h.act);
@@ -815,10 +814,9 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
 #pragma unroll
             for (int q = 0; q < 9; ++q) S[q] = 0.f;
             if (g_ok) {
-                load_S<KIND>(a.sigmas, g, S);
-                m0 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
-                m1 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
-                m2 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
+                float v0, v1, v2;
+                load_gauss<KIND>(a.gauss, g, v0, v1, v2, S);
+                m0 = __fsub_rn(v0, c0); m1 = __fsub_rn(v1, c1); m2 = __fsub_rn(v2, c2);
             }
             const float2 lsj = s_ls[j * NT + tid];
             const float lj = lsj.x, sj = lsj.y;
@@ -884,7 +882,7 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
 
 }  // namespace voge
 
-extern "C" int voge_render_backward_fused(const float* verts, const float* sigmas, int sigma_kind,
+extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
                                           const float* origins, const float* rays, const int32_t* idx,
                                           const int64_t* valid, const float* grad_weight,
                                           const float* grad_len_out, float absorptivity, int B, int N, int H,
@@ -892,7 +890,7 @@ extern "C" int voge_render_backward_fused(const float* verts, const float* sigma
                                           float* grad_origins, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
-    FusedBwdArgs a{verts, sigmas, sigma_kind, origins, rays, idx, valid, grad_weight, grad_len_out, absorptivity,
+    FusedBwdArgs a{gauss, sigma_kind, origins, rays, idx, valid, grad_weight, grad_len_out, absorptivity,
                    B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins};
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     const int64_t warps = (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
@@ -920,6 +918,38 @@ extern "C" int voge_render_backward_fused(const float* verts, const float* sigma
         return by_threads(std::integral_constant<int, 9>{}, cam_tag);
     };
     return cam ? by_kind(std::true_type{}) : by_kind(std::false_type{});
+}
+
+namespace voge {
+__global__ void __launch_bounds__(256) pack_gaussians_kernel(const float* __restrict__ verts, const float* __restrict__ sigmas,
+                                                             int kind, int N, float* __restrict__ out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const float x = verts[3 * (int64_t)g], y = verts[3 * (int64_t)g + 1], z = verts[3 * (int64_t)g + 2];
+    float S[9];
+    load_S_dyn(kind, sigmas, g, S);                     // S = 2 sigma (Renderer.py:137), exact in fp32
+    float4* o = reinterpret_cast<float4*>(out);
+    if (kind == 1) {
+        o[g] = make_float4(x, y, z, S[0]);
+    } else if (kind == 3) {
+        o[2 * (int64_t)g] = make_float4(x, y, z, S[0]);
+        o[2 * (int64_t)g + 1] = make_float4(S[4], S[8], 0.f, 0.f);
+    } else {
+        o[3 * (int64_t)g] = make_float4(x, y, z, S[0]);
+        o[3 * (int64_t)g + 1] = make_float4(S[1], S[2], S[3], S[4]);
+        o[3 * (int64_t)g + 2] = make_float4(S[5], S[6], S[7], S[8]);
+    }
+}
+}  // namespace voge
+
+extern "C" int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int N, float* out,
+                                   voge_stream_t stream) {
+    using namespace voge;
+    if (N <= 0) return 0;
+    if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
+    pack_gaussians_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(verts, sigmas, sigma_kind, N, out);
+    VOGE_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int voge_bin_sub(void) { return voge::kBinSub; }

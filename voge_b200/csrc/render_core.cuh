@@ -96,6 +96,44 @@ __host__ __device__ __forceinline__ int rect_area_in_tile(uint2 rc, int tx, int 
     return max(xh - xl + 1, 0) * max(yh - yl + 1, 0);
 }
 
+// ---- packed per-Gaussian records (voge_pack_gaussians) ------------------------------------------------
+// One 16-byte-aligned record per Gaussian, [x, y, z | S = 2 sigma ...]: kind 1 -> 4 floats (x,y,z,s),
+// kind 3 -> 8 floats (x,y,z,s0 | s1,s2,-,-), kind 9 -> 12 floats (x,y,z,S00 | S01..S11 | S12..S22).  A hit then
+// costs 1 / 2 / 3 vector loads instead of 4 / 6 / 12 scalar ones (every lane of a warp gathers a different
+// Gaussian, so each load instruction is one L1 tag lookup per lane).
+template <int KIND>
+struct GaussWidth {
+    static constexpr int v = (KIND == 9) ? 12 : (KIND == 3 ? 8 : 4);
+};
+
+template <int KIND>
+__device__ __forceinline__ void load_gauss(const float* __restrict__ gp, int g, float& v0, float& v1, float& v2, float* S) {
+    const float4* p = reinterpret_cast<const float4*>(gp) + (int64_t)g * (GaussWidth<KIND>::v / 4);
+    const float4 a = __ldg(p);
+    v0 = a.x; v1 = a.y; v2 = a.z;
+    if (KIND == 1) {
+        S[0] = a.w; S[4] = a.w; S[8] = a.w;
+        S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
+    } else if (KIND == 3) {
+        const float4 b = __ldg(p + 1);
+        S[0] = a.w; S[4] = b.x; S[8] = b.y;
+        S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
+    } else {
+        const float4 b = __ldg(p + 1), c = __ldg(p + 2);
+        S[0] = a.w; S[1] = b.x; S[2] = b.y; S[3] = b.z; S[4] = b.w; S[5] = c.x; S[6] = c.y; S[7] = c.z; S[8] = c.w;
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ Hit exact_hit_packed(const float* __restrict__ gp, int g, float c0, float c1, float c2,
+                                                float d0, float d1, float d2) {
+    float v0, v1, v2, S[9];
+    load_gauss<KIND>(gp, g, v0, v1, v2, S);
+    const float m0 = __fsub_rn(v0, c0), m1 = __fsub_rn(v1, c1), m2 = __fsub_rn(v2, c2);   // verts - ray_origin, Renderer.py:130
+    if (KIND == 9) return exact_pair(m0, m1, m2, S, d0, d1, d2);
+    return exact_pair_diag(m0, m1, m2, S[0], S[4], S[8], d0, d1, d2);
+}
+
 // Every tile owns kBinSub counters / list segments (entry g goes to segment g % kBinSub): L2 serialises atomics
 // on one address, and a C5 tile receives several hundred entries per view.  The segments of a tile are
 // adjacent, so a tile's list is tile_offsets[tile * kBinSub] .. tile_offsets[(tile + 1) * kBinSub].

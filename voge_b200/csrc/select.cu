@@ -187,8 +187,7 @@ static int launch_select(const SelectArgs& a, cudaStream_t stream) {
 
 // ---- blend -------------------------------------------------------------------------------------------------
 struct BlendArgs {
-    const float* verts;
-    const float* sigmas;
+    const float* gauss;           // packed records (voge_pack_gaussians)
     const float* origins;
     const float* rays;
     const int32_t* idx;           // (B,H,W,K) packed, first valid[r] slots
@@ -269,7 +268,7 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const BlendArgs a) {
             const int k = k0 + j;
             lv[j] = kEmptyLen; av[j] = kEmptyLen; dv[j] = 0.f;
             if (k < cnt) {
-                const Hit h = exact_hit<KIND>(a.verts, a.sigmas, gv[j] - pack_off, c0, c1, c2, r0, r1, r2);
+                const Hit h = exact_hit_packed<KIND>(a.gauss, gv[j] - pack_off, c0, c1, c2, r0, r1, r2);
                 lv[j] = h.len; av[j] = h.act; dv[j] = h.dsd;
                 const float sk = sqrtf(h.dsd + 1e-10f);                              // Aggregation.py:49
                 s_ls[k * NT + tid] = make_float2(h.len, sk);
@@ -372,14 +371,14 @@ extern "C" int voge_select_topk(const int32_t* counts, const int64_t* seg_base, 
     return launch_select<64, 64>(a, s);
 }
 
-extern "C" int voge_blend_weights(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
+extern "C" int voge_blend_weights(const float* gauss, int sigma_kind, const float* origins,
                                   const float* rays, const int32_t* idx, const int64_t* valid, float absorptivity,
                                   int B, int N, int H, int W, int K, float* out_weight, float* out_len,
                                   float* out_act, float* out_dsd, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
     BlendArgs a;
-    a.verts = verts; a.sigmas = sigmas; a.origins = origins; a.rays = rays; a.idx = idx; a.valid = valid;
+    a.gauss = gauss; a.origins = origins; a.rays = rays; a.idx = idx; a.valid = valid;
     a.omega = absorptivity; a.B = B; a.N = N; a.H = H; a.W = W; a.K = K;
     a.out_weight = out_weight; a.out_len = out_len; a.out_act = out_act; a.out_dsd = out_dsd;
     cudaStream_t s = (cudaStream_t)stream;

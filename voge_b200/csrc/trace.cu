@@ -26,8 +26,7 @@
 namespace voge {
 
 struct TraceArgs {
-    const float* verts;
-    const float* sigmas;
+    const float* gauss;                // packed records (voge_pack_gaussians)
     const float* origins;              // (B,3)
     const float* rays;                 // (B,H,W,3)
     const int64_t* tile_offsets;       // (B*TY*TX*kBinSub + 1) into tile_list
@@ -169,11 +168,9 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
         if (base + tid < n) {
             const int g = __ldg(list + base + tid);
             const uint2 rc = a.rects[(int64_t)b * a.N + g];
-            const float m0 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);       // verts - ray_origin, Renderer.py:130
-            const float m1 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
-            const float m2 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
-            float S[9];
-            load_S<KIND>(a.sigmas, g, S);
+            float v0, v1, v2, S[9];
+            load_gauss<KIND>(a.gauss, g, v0, v1, v2, S);
+            const float m0 = __fsub_rn(v0, c0), m1 = __fsub_rn(v1, c1), m2 = __fsub_rn(v2, c2);   // verts - ray_origin, Renderer.py:130
             const int xl = max((int)(rc.x & 0xffffu), px0), xh = min((int)(rc.x >> 16), pxe);
             const int yl = max((int)(rc.y & 0xffffu), py0), yh = min((int)(rc.y >> 16), pye);
             const int w = xh - xl + 1, h = yh - yl + 1;
@@ -328,7 +325,7 @@ static int dispatch_trace(const TraceArgs& a, cudaStream_t s) {
 
 extern "C" int voge_trace_threads(int tile) { return voge::tile_threads(tile); }
 
-extern "C" int voge_trace_hits(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
+extern "C" int voge_trace_hits(const float* gauss, int sigma_kind, const float* origins,
                                const float* rays, const int64_t* tile_offsets, const int32_t* tile_list,
                                const uint32_t* rects, const int64_t* tile_item_offsets, float thr_act, int B, int N,
                                int H, int W, int tile, int32_t* counts, int64_t* seg_base, uint32_t* hits,
@@ -336,7 +333,7 @@ extern "C" int voge_trace_hits(const float* verts, const float* sigmas, int sigm
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     TraceArgs a;
-    a.verts = verts; a.sigmas = sigmas; a.origins = origins; a.rays = rays; a.tile_offsets = tile_offsets;
+    a.gauss = gauss; a.origins = origins; a.rays = rays; a.tile_offsets = tile_offsets;
     a.tile_list = tile_list; a.rects = reinterpret_cast<const uint2*>(rects); a.tile_item_offsets = tile_item_offsets;
     a.thr_act = thr_act; a.B = B; a.N = N; a.H = H; a.W = W; a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
     a.counts = counts; a.seg_base = seg_base; a.hits = reinterpret_cast<uint2*>(hits);

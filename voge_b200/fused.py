@@ -48,9 +48,10 @@ class _RenderFused(torch.autograd.Function):
                                                                image_size, thr, thr_act, use_ref_bins, bin_size, tile)
         if item_offsets.total_items > MAX_PIPELINE_ITEMS and single_kernel_fits(tile, K):
             item_offsets = None
+        gauss = _C.pack_gaussians(verts, sigmas)     # (N, 4|8|12) aligned records shared by forward and backward
         idx, weight, tlen, valid, _, _ = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list, rects,
                                                            thr_act, absorptivity, K, tile, need_act=False,
-                                                           item_offsets=item_offsets)
+                                                           item_offsets=item_offsets, gauss=gauss)
         if verts.requires_grad or sigmas.requires_grad or origins.requires_grad or rays.requires_grad:
             # recompute-not-store: only the inputs are kept; the backward re-evaluates the K hits per
             # pixel from idx (the reference saves mus, isigmas (B*N copies), rays, sel_idx and the
@@ -60,7 +61,7 @@ class _RenderFused(torch.autograd.Function):
             # vert_index in place (-1 -> 0, reference Aggregation.py:131; the reference clones the
             # tensor for that reason, Renderer.py:145).  They are kept outside autograd's version
             # tracking instead of cloned: the backward only reads the first valid_num slots.
-            ctx.idx, ctx.valid = idx, valid
+            ctx.idx, ctx.valid, ctx.gauss = idx, valid, gauss
         ctx.absorptivity = float(absorptivity)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(idx, valid)
@@ -75,7 +76,8 @@ class _RenderFused(torch.autograd.Function):
         # on to R, T, focal through the ray generator's autograd graph (voge_b200/cameras.py)
         g_verts, g_sig, g_rays, g_org = _C.render_backward_fused(
             verts, sigmas, origins, rays, ctx.idx, ctx.valid, g_weight.contiguous(), g_len_out, ctx.absorptivity,
-            need_sigma=ctx.needs_input_grad[1], need_rays=ctx.needs_input_grad[3], need_origins=ctx.needs_input_grad[2])
+            need_sigma=ctx.needs_input_grad[1], need_rays=ctx.needs_input_grad[3], need_origins=ctx.needs_input_grad[2],
+            gauss=ctx.gauss)
         return (g_verts, g_sig, g_org, g_rays) + (None,) * 10
 
 
