@@ -107,10 +107,12 @@ int voge_aggregation_backward(const float* act, const float* len, const float* d
  *   sil = min(sum_k weight[r,k], 1);  mask = (mask_thr > 0) ? (sil > mask_thr) : sil;
  *   out = min(out + (1 - mask) * background, 1).
  * idx_mod > 0 maps packed indices (b*N+n) onto attr rows with idx % idx_mod; attr has n_attr
- * rows and indices >= n_attr are ignored (the reference asserts on the host, :120).        */
+ * rows and indices >= n_attr are ignored (the reference asserts on the host, :120).
+ * attr_padded4 != 0 (C <= 4 only): attr is an (n_attr,4) zero-padded table, fetched with one 16-byte
+ * load per hit (every lane of a warp gathers a different row).                              */
 int voge_merge_final(const float* attr, const float* weight, const int32_t* idx,
                      const int64_t* valid_num, const float* background, float mask_thr,
-                     int64_t R, int K, int C, int idx_mod, int n_attr,
+                     int64_t R, int K, int C, int idx_mod, int n_attr, int attr_padded4,
                      float* out, voge_stream_t stream);
 
 /* Backward of voge_merge_final: grad_attr must be ZEROED by the caller and is accumulated into;
@@ -121,7 +123,7 @@ int voge_merge_final_backward(const float* attr, const float* weight, const int3
                               const int64_t* valid_num, const float* background,
                               float mask_thr, const float* out, const float* grad_out,
                               int64_t R, int K, int C, int idx_mod, int n_attr, int packed4,
-                              float* grad_attr, float* grad_weight, voge_stream_t stream);
+                              int attr_padded4, float* grad_attr, float* grad_weight, voge_stream_t stream);
 
 /* ---- sampling (inverse rendering) --------------------------------------------------------
  * Replaces `sample_voge` (ext.cpp:14 -> SampleVoge, sample_voge.cu:95-134, kernel :35-66):

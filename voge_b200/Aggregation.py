@@ -84,9 +84,13 @@ def aggregation(sel_idx: torch.Tensor, sel_act: torch.Tensor, sel_len: torch.Ten
 class _MergeFinal(torch.autograd.Function):
     @staticmethod
     def forward(ctx, vert_attr, weight, vert_assign, valid_num, background, mask_thr, idx_mod):
-        out = _C.merge_final_forward(vert_attr, weight, vert_assign, valid_num, background, mask_thr, idx_mod)
+        # attribute rows padded to 16 bytes once per call: the kernels gather one row per (pixel, k)
+        attr4 = _C.pad_attr4(vert_attr) if (vert_attr.is_cuda and vert_attr.dim() == 2 and vert_attr.shape[1] <= 4
+                                            and vert_attr.dtype == torch.float32) else None
+        out = _C.merge_final_forward(vert_attr, weight, vert_assign, valid_num, background, mask_thr, idx_mod,
+                                     attr4=attr4)
         ctx.save_for_backward(vert_attr, weight, vert_assign, valid_num, background)
-        ctx.mask_thr, ctx.idx_mod = mask_thr, idx_mod
+        ctx.mask_thr, ctx.idx_mod, ctx.attr4 = mask_thr, idx_mod, attr4
         return out
 
     @staticmethod
@@ -94,7 +98,8 @@ class _MergeFinal(torch.autograd.Function):
         vert_attr, weight, vert_assign, valid_num, background = ctx.saved_tensors
         g_attr, g_w = _C.merge_final_backward(vert_attr, weight, vert_assign, valid_num, grad_out.contiguous(),
                                               background, ctx.mask_thr, ctx.idx_mod,
-                                              need_attr=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1])
+                                              need_attr=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1],
+                                              attr4=ctx.attr4)
         return g_attr, g_w, None, None, None, None, None
 
 

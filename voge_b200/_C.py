@@ -247,7 +247,18 @@ def aggregation_backward(sel_act, sel_len, sel_dsd, grad_weight, absorptivity):
     return g_act, g_len, g_dsd
 
 
-def merge_final_forward(attr, weight, idx, valid_num, background=None, mask_thr=-1.0, idx_mod=0):
+def pad_attr4(attr):
+    """(n, C <= 4) attribute table -> (n, 4) zero-padded rows (one 16-byte gather per hit in the kernels)."""
+    attr = f32c(attr)
+    if attr.shape[1] == 4:
+        return attr
+    out = torch.zeros((attr.shape[0], 4), dtype=torch.float32, device=attr.device)
+    out[:, :attr.shape[1]] = attr
+    return out
+
+
+def merge_final_forward(attr, weight, idx, valid_num, background=None, mask_thr=-1.0, idx_mod=0, attr4=None):
+    """attr4: optional pad_attr4(attr) (used instead of attr when C <= 4)."""
     require_cuda(attr, weight, idx, valid_num)
     attr, weight, idx = f32c(attr), f32c(weight), i32c(idx)
     valid_num = valid_num.to(torch.int64).contiguous()
@@ -257,13 +268,15 @@ def merge_final_forward(attr, weight, idx, valid_num, background=None, mask_thr=
     with torch.cuda.device(dev):
         out = torch.empty(tuple(idx.shape[:-1]) + (C,), dtype=torch.float32, device=dev)
         bg = f32c(background) if background is not None else None
-        check(lib().voge_merge_final(ptr(attr), ptr(weight), ptr(idx), ptr(valid_num), ptr(bg), float(mask_thr),
-                                     R, K, C, int(idx_mod), int(attr.shape[0]), ptr(out), stream_of(attr)), "merge_final")
+        p4 = attr4 is not None and C <= 4
+        check(lib().voge_merge_final(ptr(attr4 if p4 else attr), ptr(weight), ptr(idx), ptr(valid_num), ptr(bg),
+                                     float(mask_thr), R, K, C, int(idx_mod), int(attr.shape[0]), int(p4), ptr(out),
+                                     stream_of(attr)), "merge_final")
     return out
 
 
 def merge_final_backward(attr, weight, idx, valid_num, grad_out, background=None, mask_thr=-1.0, idx_mod=0,
-                         need_attr=True, need_weight=True):
+                         need_attr=True, need_weight=True, attr4=None):
     attr, weight, idx, grad_out = f32c(attr), f32c(weight), i32c(idx), f32c(grad_out)
     valid_num = valid_num.to(torch.int64).contiguous()
     K, C = int(idx.shape[-1]), int(attr.shape[-1])
@@ -277,9 +290,10 @@ def merge_final_backward(attr, weight, idx, valid_num, grad_out, background=None
             g_attr = torch.zeros_like(attr) if need_attr else None
         g_w = torch.empty_like(weight) if need_weight else None
         bg = f32c(background) if background is not None else None
-        check(lib().voge_merge_final_backward(ptr(attr), ptr(weight), ptr(idx), ptr(valid_num), ptr(bg),
+        p4 = attr4 is not None and C <= 4 and (packed4 or g_attr is None)
+        check(lib().voge_merge_final_backward(ptr(attr4 if p4 else attr), ptr(weight), ptr(idx), ptr(valid_num), ptr(bg),
                                               float(mask_thr), None, ptr(grad_out), R, K, C, int(idx_mod),
-                                              int(attr.shape[0]), int(packed4), ptr(g_attr), ptr(g_w),
+                                              int(attr.shape[0]), int(packed4), int(p4), ptr(g_attr), ptr(g_w),
                                               stream_of(attr)), "merge_final_backward")
         if packed4:
             g_attr = g_attr[:, :C].contiguous()

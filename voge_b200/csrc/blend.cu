@@ -245,7 +245,21 @@ __device__ __forceinline__ Row4 load_row4(const float* __restrict__ wrow, const 
     return o;
 }
 
-template <int C, bool VEC>
+// attribute row of Gaussian g: one 16-byte load from a float4-padded table (P4), C scalar loads otherwise
+template <int C, bool P4>
+__device__ __forceinline__ void load_attr(const float* __restrict__ attr, int g, float* av) {
+    if (P4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(attr) + g);
+        const float t[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int c = 0; c < C; ++c) av[c] = t[c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) av[c] = __ldg(attr + (int64_t)g * C + c);
+    }
+}
+
+template <int C, bool VEC, bool P4>
 __global__ void __launch_bounds__(256) merge_fwd_small_kernel(const float* __restrict__ attr,
                                                               const float* __restrict__ weight,
                                                               const int32_t* __restrict__ idx,
@@ -270,8 +284,10 @@ __global__ void __launch_bounds__(256) merge_fwd_small_kernel(const float* __res
             int g = max(row.g[j], 0);            // Aggregation.py:131  vert_assign += (vert_assign < 0)
             if (idx_mod > 0) g %= idx_mod;
             if (k + j < nv && g < n_attr) {
+                float av[C];
+                load_attr<C, P4>(attr, g, av);
 #pragma unroll
-                for (int c = 0; c < C; ++c) acc[c] = fmaf(row.w[j], __ldg(attr + (int64_t)g * C + c), acc[c]);
+                for (int c = 0; c < C; ++c) acc[c] = fmaf(row.w[j], av[c], acc[c]);
             }
         }
     }
@@ -285,7 +301,7 @@ __global__ void __launch_bounds__(256) merge_fwd_small_kernel(const float* __res
     for (int c = 0; c < C; ++c) out[r * C + c] = acc[c];
 }
 
-template <int C, bool VEC>
+template <int C, bool VEC, bool P4>
 __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __restrict__ attr,
                                                               const float* __restrict__ weight,
                                                               const int32_t* __restrict__ idx,
@@ -316,8 +332,10 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
                 int g = max(row.g[j], 0);
                 if (idx_mod > 0) g %= idx_mod;
                 if (k + j < nv && g < n_attr) {
+                    float av[C];
+                    load_attr<C, P4>(attr, g, av);
 #pragma unroll
-                    for (int c = 0; c < C; ++c) acc[c] = fmaf(row.w[j], __ldg(attr + (int64_t)g * C + c), acc[c]);
+                    for (int c = 0; c < C; ++c) acc[c] = fmaf(row.w[j], av[c], acc[c]);
                 }
             }
         }
@@ -340,9 +358,11 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
             if (idx_mod > 0) g %= idx_mod;
             if (k + j < nv && g < n_attr) {
                 float v[4] = {0.f, 0.f, 0.f, 0.f};
+                float av[C];
+                load_attr<C, P4>(attr, g, av);
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    gw = fmaf(go[c], __ldg(attr + (int64_t)g * C + c), gw);
+                    gw = fmaf(go[c], av[c], gw);
                     v[c] = row.w[j] * go[c];
                 }
                 if (g_attr4 != nullptr && row.w[j] != 0.f)
@@ -413,7 +433,7 @@ extern "C" int voge_aggregation_backward(const float* act, const float* len, con
 
 extern "C" int voge_merge_final(const float* attr, const float* weight, const int32_t* idx,
                                 const int64_t* valid_num, const float* background, float mask_thr,
-                                int64_t R, int K, int C, int idx_mod, int n_attr, float* out,
+                                int64_t R, int K, int C, int idx_mod, int n_attr, int attr_padded4, float* out,
                                 voge_stream_t stream) {
     using namespace voge;
     if (R <= 0 || C <= 0) return 0;
@@ -422,18 +442,25 @@ extern "C" int voge_merge_final(const float* attr, const float* weight, const in
         cudaStream_t s = (cudaStream_t)stream;
 #define VOGE_MF(CC)                                                                                                 \
     do {                                                                                                            \
-        if (K % 4 == 0)                                                                                             \
-            merge_fwd_small_kernel<CC, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,        \
-                                                                  mask_thr, R, K, idx_mod, n_attr, out);            \
+        if (K % 4 == 0 && attr_padded4)                                                                             \
+            merge_fwd_small_kernel<CC, true, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,  \
+                                                                        mask_thr, R, K, idx_mod, n_attr, out);      \
+        else if (K % 4 == 0)                                                                                        \
+            merge_fwd_small_kernel<CC, true, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
+                                                                         mask_thr, R, K, idx_mod, n_attr, out);     \
+        else if (attr_padded4)                                                                                      \
+            merge_fwd_small_kernel<CC, false, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
+                                                                         mask_thr, R, K, idx_mod, n_attr, out);     \
         else                                                                                                        \
-            merge_fwd_small_kernel<CC, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,       \
-                                                                   mask_thr, R, K, idx_mod, n_attr, out);           \
+            merge_fwd_small_kernel<CC, false, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,\
+                                                                          mask_thr, R, K, idx_mod, n_attr, out);    \
     } while (0)
         if (C == 1) VOGE_MF(1); else if (C == 2) VOGE_MF(2); else if (C == 3) VOGE_MF(3); else VOGE_MF(4);
 #undef VOGE_MF
         VOGE_LAUNCH_CHECK();
         return 0;
     }
+    if (attr_padded4) return (int)cudaErrorInvalidValue;     // padded tables only for C <= 4
     const int64_t total = R * C;
     merge_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         attr, weight, idx, valid_num, background, mask_thr, R, K, C, idx_mod, n_attr, out);
@@ -445,24 +472,34 @@ extern "C" int voge_merge_final_backward(const float* attr, const float* weight,
                                          const int64_t* valid_num, const float* background,
                                          float mask_thr, const float* out, const float* grad_out,
                                          int64_t R, int K, int C, int idx_mod, int n_attr, int packed4,
-                                         float* grad_attr, float* grad_weight, voge_stream_t stream) {
+                                         int attr_padded4, float* grad_attr, float* grad_weight,
+                                         voge_stream_t stream) {
     using namespace voge;
     (void)out;
     if (R <= 0 || C <= 0) return 0;
+    if (attr_padded4 && !(C <= 4 && (packed4 || grad_attr == nullptr))) return (int)cudaErrorInvalidValue;
     if (background != nullptr && C > kMaxBgChannels) return (int)cudaErrorInvalidValue;
     if (C <= 4 && (packed4 || grad_attr == nullptr)) {
         const unsigned grid = (unsigned)((R + 255) / 256);
         cudaStream_t s = (cudaStream_t)stream;
 #define VOGE_MB(CC)                                                                                                 \
     do {                                                                                                            \
-        if (K % 4 == 0)                                                                                             \
-            merge_bwd_small_kernel<CC, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,        \
-                                                                  mask_thr, grad_out, R, K, idx_mod, n_attr,       \
-                                                                  grad_attr, grad_weight);                          \
+        if (K % 4 == 0 && attr_padded4)                                                                             \
+            merge_bwd_small_kernel<CC, true, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,  \
+                                                                        mask_thr, grad_out, R, K, idx_mod, n_attr, \
+                                                                        grad_attr, grad_weight);                    \
+        else if (K % 4 == 0)                                                                                        \
+            merge_bwd_small_kernel<CC, true, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
+                                                                         mask_thr, grad_out, R, K, idx_mod, n_attr,\
+                                                                         grad_attr, grad_weight);                   \
+        else if (attr_padded4)                                                                                      \
+            merge_bwd_small_kernel<CC, false, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
+                                                                         mask_thr, grad_out, R, K, idx_mod, n_attr,\
+                                                                         grad_attr, grad_weight);                   \
         else                                                                                                        \
-            merge_bwd_small_kernel<CC, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,       \
-                                                                   mask_thr, grad_out, R, K, idx_mod, n_attr,      \
-                                                                   grad_attr, grad_weight);                         \
+            merge_bwd_small_kernel<CC, false, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,\
+                                                                          mask_thr, grad_out, R, K, idx_mod, n_attr,\
+                                                                          grad_attr, grad_weight);                  \
     } while (0)
         if (C == 1) VOGE_MB(1); else if (C == 2) VOGE_MB(2); else if (C == 3) VOGE_MB(3); else VOGE_MB(4);
 #undef VOGE_MB

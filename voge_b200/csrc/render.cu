@@ -780,7 +780,12 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
     {
         int lo = 0;
         float SE = 0.f;
+        float4 gw4 = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int m = 0; m < cnt; ++m) {
+            // the (K,) rows are read 16 bytes at a time: a scalar load at a 4K-byte lane stride costs a full
+            // L1 tag lookup per lane
+            if (vec && (m & 3) == 0) gw4 = *reinterpret_cast<const float4*>(i_gw + m);
+            const float gwm = vec ? ((m & 2) ? ((m & 1) ? gw4.w : gw4.z) : ((m & 1) ? gw4.y : gw4.x)) : i_gw[m];
             const float Em = s_E[m * NT + tid];
             const float lm = s_ls[m * NT + tid].x;
             while (lo < m && (lm - s_ls[lo * NT + tid].x) * s_min >= kErfSat) { SE += s_E[lo * NT + tid]; ++lo; }
@@ -795,7 +800,7 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
                     if (dl * s_min <= -kErfSat) break;
                     D += s_E[k * NT + tid] * phi(dl * lk.y);
                 }
-                wg = expf(-(D * omega)) * Em * kInvExpMinusHalf * i_gw[m];
+                wg = expf(-(D * omega)) * Em * kInvExpMinusHalf * gwm;
             }
             s_wg[m * NT + tid] = wg;
             total_gD -= omega * wg;       // gD_m = dL/dD_m = -omega w_m dL/dw_m
@@ -806,9 +811,12 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
     {
         int lo_j = 0, hi_j = -1;
         float pref = 0.f;                 // sum of gD_m over m <= hi_j
+        int4 ix4 = make_int4(-1, -1, -1, -1);
         for (int j = 0; j < cnt; ++j) {
             // the Gaussian's record is fetched first: the gathers overlap with the window loop below
-            const int g = i_idx[j] - pack_off;
+            if (vec && (j & 3) == 0) ix4 = *reinterpret_cast<const int4*>(i_idx + j);
+            const int gp = vec ? ((j & 2) ? ((j & 1) ? ix4.w : ix4.z) : ((j & 1) ? ix4.y : ix4.x)) : i_idx[j];
+            const int g = gp - pack_off;
             const bool g_ok = g >= 0 && g < a.N;
             float S[9], m0 = 0.f, m1 = 0.f, m2 = 0.f;
 #pragma unroll
