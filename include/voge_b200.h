@@ -246,12 +246,14 @@ int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind
  * [d verts(3) | d sigma] padded to float4 units so that 16-byte vector reductions can be used:
  * kind 1: (N,4) = [gx,gy,gz,gsigma]; kind 3: (N,8) = [gx,gy,gz,0,gs0,gs1,gs2,0];
  * kind 9: (N,12) = [gx,gy,gz,gs00..gs22].  ZEROED by the caller, accumulated into.
+ * weight: optional (B,H,W,K) = the forward's out_weight (an output the caller holds anyway); when given the
+ * kernel skips re-evaluating the blend weights (NULL: recompute them from the hits).
  * Camera gradients (pose optimisation, reference grad_rays of ray_trace_voge.cu:283-332): grad_rays (B,H,W,3),
  * optional, written in full; grad_origins (B,3), optional, ZEROED by the caller (= -sum of d/d(mu') over the
  * view's hits, since mu' = verts - origin, Renderer.py:130).                                        */
 int voge_render_backward_fused(const float* gauss, int sigma_kind,
                                const float* origins, const float* rays, const int32_t* idx,
-                               const int64_t* valid_num, const float* grad_weight,
+                               const int64_t* valid_num, const float* grad_weight, const float* weight,
                                const float* grad_len_out, float absorptivity,
                                int B, int N, int H, int W, int K,
                                float* grad_packed, int need_sigma, float* grad_rays, float* grad_origins,

@@ -416,11 +416,12 @@ def render_backward(verts, sigmas, origins, rays, idx, valid, g_len, g_act, g_ds
 
 
 def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_len_out, absorptivity,
-                          need_sigma=True, need_rays=False, need_origins=False, gauss=None):
+                          need_sigma=True, need_rays=False, need_origins=False, gauss=None, weight=None):
     """-> (g_verts, g_sigmas | None, g_rays (B,H,W,3) | None, g_origins (B,3) | None)"""
     verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
     idx, g_weight = i32c(idx), f32c(g_weight)
     g_len_out = f32c(g_len_out) if g_len_out is not None else None
+    weight = f32c(weight) if weight is not None else None
     B, H, W, K = (int(s) for s in idx.shape)
     N = int(verts.shape[0])
     kind = sigma_kind(sigmas)
@@ -433,7 +434,7 @@ def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_
         g_rays = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev) if need_rays else None
         g_org = torch.zeros((B, 3), dtype=torch.float32, device=dev) if need_origins else None
         check(lib().voge_render_backward_fused(ptr(gauss), kind, ptr(origins), ptr(rays),
-                                               ptr(idx), ptr(valid), ptr(g_weight), ptr(g_len_out),
+                                               ptr(idx), ptr(valid), ptr(g_weight), ptr(weight), ptr(g_len_out),
                                                float(absorptivity), B, N, H, W, K, ptr(packed), int(bool(need_sigma)),
                                                ptr(g_rays), ptr(g_org), stream_of(verts)), "render_backward_fused")
     g_verts = packed[:, :3].contiguous()

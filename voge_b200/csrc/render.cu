@@ -648,6 +648,7 @@ struct FusedBwdArgs {
     const int32_t* idx;
     const int64_t* valid;
     const float* g_weight;   // (B,H,W,K)
+    const float* weight;     // optional (B,H,W,K): the forward's blend weights (Fragments.vert_weight); NULL = recompute
     const float* g_len_out;  // optional (B,H,W,K): gradient arriving on Fragments.vert_hit_length
     float omega;
     int B, N, H, W, K;
@@ -777,7 +778,33 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
     // ---- pass 1: weights.  w_m = e^.5 exp(-omega D_m) E_m, D_m = sum_k E_k Phi((len_m - len_k) s_k);
     // sorted lens => Phi = 1 below the window |len_m - len_k| s_min < 4 (running prefix of E), 0 above ----
     float total_gD = 0.f;
-    {
+    if (a.weight != nullptr) {
+        // the forward's weights are an output that autograd keeps alive anyway: w_m dL/dw_m needs no erf sums
+        const float* i_w = a.weight + r * a.K;
+        for (int m0 = 0; m0 < cnt; m0 += 4) {
+            float wv[4], gv[4];
+            if (vec) {
+                const float4 w4 = *reinterpret_cast<const float4*>(i_w + m0);
+                const float4 g4 = *reinterpret_cast<const float4*>(i_gw + m0);
+                wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+                gv[0] = g4.x; gv[1] = g4.y; gv[2] = g4.z; gv[3] = g4.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    wv[j] = (m0 + j < cnt) ? i_w[m0 + j] : 0.f;
+                    gv[j] = (m0 + j < cnt) ? i_gw[m0 + j] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (m0 + j < cnt) {
+                    const float wg = wv[j] * gv[j];
+                    s_wg[(m0 + j) * NT + tid] = wg;
+                    total_gD -= omega * wg;       // gD_m = dL/dD_m = -omega w_m dL/dw_m
+                }
+            }
+        }
+    } else {
         int lo = 0;
         float SE = 0.f;
         float4 gw4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -892,13 +919,13 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
 
 extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
                                           const float* origins, const float* rays, const int32_t* idx,
-                                          const int64_t* valid, const float* grad_weight,
+                                          const int64_t* valid, const float* grad_weight, const float* weight,
                                           const float* grad_len_out, float absorptivity, int B, int N, int H,
                                           int W, int K, float* grad_packed, int need_sigma, float* grad_rays,
                                           float* grad_origins, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
-    FusedBwdArgs a{gauss, sigma_kind, origins, rays, idx, valid, grad_weight, grad_len_out, absorptivity,
+    FusedBwdArgs a{gauss, sigma_kind, origins, rays, idx, valid, grad_weight, weight, grad_len_out, absorptivity,
                    B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins};
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     const int64_t warps = (int64_t)B * cdiv(W, 8) * cdiv(H, 4);

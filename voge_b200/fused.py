@@ -53,10 +53,10 @@ class _RenderFused(torch.autograd.Function):
                                                            thr_act, absorptivity, K, tile, need_act=False,
                                                            item_offsets=item_offsets, gauss=gauss)
         if verts.requires_grad or sigmas.requires_grad or origins.requires_grad or rays.requires_grad:
-            # recompute-not-store: only the inputs are kept; the backward re-evaluates the K hits per
-            # pixel from idx (the reference saves mus, isigmas (B*N copies), rays, sel_idx and the
-            # PyTorch aggregation saves ~10 (R,K,K) tensors)
-            ctx.save_for_backward(verts, sigmas, origins, rays)
+            # recompute-not-store: only the inputs and the returned weights (which the caller's Fragments keep
+            # alive anyway) are saved; the backward re-evaluates the K hits per pixel from idx (the reference
+            # saves mus, isigmas (B*N copies), rays, sel_idx and the PyTorch aggregation ~10 (R,K,K) tensors)
+            ctx.save_for_backward(verts, sigmas, origins, rays, weight)
             # idx / valid are handed out as Fragments.vert_index / valid_num and merge_final rewrites
             # vert_index in place (-1 -> 0, reference Aggregation.py:131; the reference clones the
             # tensor for that reason, Renderer.py:145).  They are kept outside autograd's version
@@ -69,7 +69,7 @@ class _RenderFused(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_weight, _g_idx, _g_valid, g_len_out):
-        verts, sigmas, origins, rays = ctx.saved_tensors
+        verts, sigmas, origins, rays, weight = ctx.saved_tensors
         if g_weight is None:
             g_weight = torch.zeros(ctx.idx.shape, dtype=torch.float32, device=ctx.idx.device)
         # camera gradients (pose optimisation): d/d(origins), d/d(rays) come out of the same kernel and flow
@@ -77,7 +77,7 @@ class _RenderFused(torch.autograd.Function):
         g_verts, g_sig, g_rays, g_org = _C.render_backward_fused(
             verts, sigmas, origins, rays, ctx.idx, ctx.valid, g_weight.contiguous(), g_len_out, ctx.absorptivity,
             need_sigma=ctx.needs_input_grad[1], need_rays=ctx.needs_input_grad[3], need_origins=ctx.needs_input_grad[2],
-            gauss=ctx.gauss)
+            gauss=ctx.gauss, weight=weight)
         return (g_verts, g_sig, g_org, g_rays) + (None,) * 10
 
 
