@@ -333,8 +333,9 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
                                    ptr(focal), ptr(principal), B, N, H, W, float(thr), float(thr_act),
                                    int(bool(use_ref_bins)), int(bin_size), int(tile), ptr(rects), ptr(counts[0, 1:]),
                                    ptr(counts[1, 1:]), stream_of(verts)), "bin_count")
-        offsets = torch.cumsum(counts, 1, dtype=torch.int64)
-        totals = offsets[:, -1].tolist()
+        # two 1-D scans (cub DeviceScan); a (2, n) scan along dim 1 runs one thread block per row
+        offsets = (torch.cumsum(counts[0], 0, dtype=torch.int64), torch.cumsum(counts[1], 0, dtype=torch.int64))
+        totals = torch.stack([offsets[0][-1], offsets[1][-1]]).tolist()
         total, total_items = int(totals[0]), int(totals[1])
         tile_list = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
         cursor = torch.zeros((B * TY * TX * S,), dtype=torch.int32, device=dev)
