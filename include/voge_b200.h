@@ -118,7 +118,8 @@ int voge_merge_final(const float* attr, const float* weight, const int32_t* idx,
 /* Backward of voge_merge_final: grad_attr must be ZEROED by the caller and is accumulated into;
  * its layout is (n_attr,C), or -- packed4 != 0 and C <= 4 -- (n_attr,4) zero-padded rows so that one
  * 16-byte vector reduction per hit can be used.  grad_weight (R,K) is written in full.
- * Either may be NULL.                                                                       */
+ * Either may be NULL.  out: optional (R,C) = the forward's output; with it the composite is re-evaluated
+ * only for pixels whose output saturated at 1 (the min(x,1) subgradient needs x there).    */
 int voge_merge_final_backward(const float* attr, const float* weight, const int32_t* idx,
                               const int64_t* valid_num, const float* background,
                               float mask_thr, const float* out, const float* grad_out,

@@ -89,17 +89,17 @@ class _MergeFinal(torch.autograd.Function):
                                             and vert_attr.dtype == torch.float32) else None
         out = _C.merge_final_forward(vert_attr, weight, vert_assign, valid_num, background, mask_thr, idx_mod,
                                      attr4=attr4)
-        ctx.save_for_backward(vert_attr, weight, vert_assign, valid_num, background)
+        ctx.save_for_backward(vert_attr, weight, vert_assign, valid_num, background, out)
         ctx.mask_thr, ctx.idx_mod, ctx.attr4 = mask_thr, idx_mod, attr4
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        vert_attr, weight, vert_assign, valid_num, background = ctx.saved_tensors
+        vert_attr, weight, vert_assign, valid_num, background, out = ctx.saved_tensors
         g_attr, g_w = _C.merge_final_backward(vert_attr, weight, vert_assign, valid_num, grad_out.contiguous(),
                                               background, ctx.mask_thr, ctx.idx_mod,
                                               need_attr=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1],
-                                              attr4=ctx.attr4)
+                                              attr4=ctx.attr4, out=out)
         return g_attr, g_w, None, None, None, None, None
 
 

@@ -276,7 +276,7 @@ def merge_final_forward(attr, weight, idx, valid_num, background=None, mask_thr=
 
 
 def merge_final_backward(attr, weight, idx, valid_num, grad_out, background=None, mask_thr=-1.0, idx_mod=0,
-                         need_attr=True, need_weight=True, attr4=None):
+                         need_attr=True, need_weight=True, attr4=None, out=None):
     attr, weight, idx, grad_out = f32c(attr), f32c(weight), i32c(idx), f32c(grad_out)
     valid_num = valid_num.to(torch.int64).contiguous()
     K, C = int(idx.shape[-1]), int(attr.shape[-1])
@@ -292,7 +292,8 @@ def merge_final_backward(attr, weight, idx, valid_num, grad_out, background=None
         bg = f32c(background) if background is not None else None
         p4 = attr4 is not None and C <= 4 and (packed4 or g_attr is None)
         check(lib().voge_merge_final_backward(ptr(attr4 if p4 else attr), ptr(weight), ptr(idx), ptr(valid_num), ptr(bg),
-                                              float(mask_thr), None, ptr(grad_out), R, K, C, int(idx_mod),
+                                              float(mask_thr), ptr(f32c(out)) if out is not None else None, ptr(grad_out),
+                                              R, K, C, int(idx_mod),
                                               int(attr.shape[0]), int(packed4), int(p4), ptr(g_attr), ptr(g_w),
                                               stream_of(attr)), "merge_final_backward")
         if packed4:

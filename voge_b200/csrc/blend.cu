@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
                                                               const int32_t* __restrict__ idx,
                                                               const int64_t* __restrict__ valid_num,
                                                               const float* __restrict__ background, float mask_thr,
-                                                              const float* __restrict__ g_out, int64_t R, int K,
+                                                              const float* __restrict__ g_out,
+                                                              const float* __restrict__ fwd_out, int64_t R, int K,
                                                               int idx_mod, int n_attr, float* __restrict__ g_attr4,
                                                               float* __restrict__ g_weight) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,22 +321,41 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
     for (int c = 0; c < C; ++c) go[c] = g_out[r * C + c];
     float g_sumw = 0.f;
     if (background != nullptr) {
+        // min(x, 1) backward needs the unclamped composite x only where the forward output saturated:
+        // out < 1 means x = out and the factor is 1.  With the forward's output at hand the gather-blend is
+        // re-run for saturated pixels only (e.g. empty pixels on a white background: the tie x == 1).
+        bool need_acc = fwd_out == nullptr;
+        if (!need_acc) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) need_acc = need_acc || !(fwd_out[r * C + c] < 1.f);
+        }
         float acc[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[c] = 0.f;
         float wsum = 0.f;
-        for (int k = 0; k < K; k += 4) {
-            const Row4 row = load_row4<VEC>(wrow, irow, k, K);
+        if (need_acc) {
+            for (int k = 0; k < K; k += 4) {
+                const Row4 row = load_row4<VEC>(wrow, irow, k, K);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                wsum += row.w[j];
-                int g = max(row.g[j], 0);
-                if (idx_mod > 0) g %= idx_mod;
-                if (k + j < nv && g < n_attr) {
-                    float av[C];
-                    load_attr<C, P4>(attr, g, av);
+                for (int j = 0; j < 4; ++j) {
+                    wsum += row.w[j];
+                    int g = max(row.g[j], 0);
+                    if (idx_mod > 0) g %= idx_mod;
+                    if (k + j < nv && g < n_attr) {
+                        float av[C];
+                        load_attr<C, P4>(attr, g, av);
 #pragma unroll
-                    for (int c = 0; c < C; ++c) acc[c] = fmaf(row.w[j], av[c], acc[c]);
+                        for (int c = 0; c < C; ++c) acc[c] = fmaf(row.w[j], av[c], acc[c]);
+                    }
+                }
+            }
+        } else {
+            for (int k = 0; k < K; k += 4) {
+                if (VEC) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
+                    wsum += w4.x; wsum += w4.y; wsum += w4.z; wsum += w4.w;
+                } else {
+                    for (int j = 0; j < 4 && k + j < K; ++j) wsum += wrow[k + j];
                 }
             }
         }
@@ -343,7 +363,7 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
         const float mask = mask_thr > 0.f ? (sil > mask_thr ? 1.f : 0.f) : sil;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            go[c] *= min1_grad(acc[c] + (1.f - mask) * background[c]);
+            if (need_acc) go[c] *= min1_grad(acc[c] + (1.f - mask) * background[c]);
             if (!(mask_thr > 0.f)) g_sumw -= go[c] * background[c];
         }
         g_sumw *= min1_grad(wsum);
@@ -475,7 +495,6 @@ extern "C" int voge_merge_final_backward(const float* attr, const float* weight,
                                          int attr_padded4, float* grad_attr, float* grad_weight,
                                          voge_stream_t stream) {
     using namespace voge;
-    (void)out;
     if (R <= 0 || C <= 0) return 0;
     if (attr_padded4 && !(C <= 4 && (packed4 || grad_attr == nullptr))) return (int)cudaErrorInvalidValue;
     if (background != nullptr && C > kMaxBgChannels) return (int)cudaErrorInvalidValue;
@@ -486,19 +505,19 @@ extern "C" int voge_merge_final_backward(const float* attr, const float* weight,
     do {                                                                                                            \
         if (K % 4 == 0 && attr_padded4)                                                                             \
             merge_bwd_small_kernel<CC, true, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,  \
-                                                                        mask_thr, grad_out, R, K, idx_mod, n_attr, \
+                                                                        mask_thr, grad_out, out, R, K, idx_mod, n_attr, \
                                                                         grad_attr, grad_weight);                    \
         else if (K % 4 == 0)                                                                                        \
             merge_bwd_small_kernel<CC, true, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
-                                                                         mask_thr, grad_out, R, K, idx_mod, n_attr,\
+                                                                         mask_thr, grad_out, out, R, K, idx_mod, n_attr,\
                                                                          grad_attr, grad_weight);                   \
         else if (attr_padded4)                                                                                      \
             merge_bwd_small_kernel<CC, false, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
-                                                                         mask_thr, grad_out, R, K, idx_mod, n_attr,\
+                                                                         mask_thr, grad_out, out, R, K, idx_mod, n_attr,\
                                                                          grad_attr, grad_weight);                   \
         else                                                                                                        \
             merge_bwd_small_kernel<CC, false, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,\
-                                                                          mask_thr, grad_out, R, K, idx_mod, n_attr,\
+                                                                          mask_thr, grad_out, out, R, K, idx_mod, n_attr,\
                                                                           grad_attr, grad_weight);                  \
     } while (0)
         if (C == 1) VOGE_MB(1); else if (C == 2) VOGE_MB(2); else if (C == 3) VOGE_MB(3); else VOGE_MB(4);

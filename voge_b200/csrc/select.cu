@@ -24,22 +24,35 @@ struct SelectArgs {
     unsigned long long* stats;    // optional: [2] pixels selected with the exact 64-bit keys
 };
 
-// Batcher's odd-even merge sort on N registers (N a power of two): 63 / 191 / 543 compare-exchanges for
-// N = 16 / 32 / 64, each a VIMNMX pair on 32-bit keys.  The comparator list is built at compile time and
-// applied through a fold expression, so every register index is a literal (no local-memory array).
+// Batcher's odd-even merge sort on N registers: the network of the next power of two without the comparators
+// that touch the (implicit, +inf) inputs above N -- 63 / 191 / 384 / 543 compare-exchanges for N = 16 / 32 / 48 /
+// 64, each a VIMNMX pair on 32-bit keys.  The comparator list is built at compile time and applied through a
+// fold expression, so every register index is a literal (no local-memory array).
+constexpr int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+template <typename F>
+constexpr void odd_even_comparators(int N, F&& f) {
+    const int P = next_pow2(N);
+    for (int p = 1; p < P; p <<= 1)
+        for (int k = p; k >= 1; k >>= 1)
+            for (int j = k % p; j + k < P; j += 2 * k)
+                for (int i = 0; i < k; ++i)
+                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p) && i + j + k < N) f(i + j, i + j + k);
+}
+
+constexpr int odd_even_count(int N) {
+    int n = 0;
+    odd_even_comparators(N, [&](int, int) { ++n; });
+    return n;
+}
+
 template <int N>
 struct OddEvenNet {
-    static constexpr int kMax = (N <= 16) ? 63 : (N <= 32 ? 191 : 543);
+    static constexpr int kMax = odd_even_count(N);
     short lo[kMax], hi[kMax];
     int n;
     constexpr OddEvenNet() : lo{}, hi{}, n(0) {
-        for (int p = 1; p < N; p <<= 1)
-            for (int k = p; k >= 1; k >>= 1)
-                for (int j = k % p; j + k < N; j += 2 * k)
-                    for (int i = 0; i < k; ++i)
-                        if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
-                            lo[n] = (short)(i + j); hi[n] = (short)(i + j + k); ++n;
-                        }
+        odd_even_comparators(N, [&](int a, int b) { lo[n] = (short)a; hi[n] = (short)b; ++n; });
     }
 };
 
