@@ -163,7 +163,7 @@ def fit_step(wl, targets_dev, n_views_total):
     for renderer, tgt in zip(wl["renderers"], targets_dev):
         frag = renderer(gm)
         img = to_white_background(frag, col)
-        loss = ((img - tgt) ** 2).sum() / (n_views_total * wl["H"] * wl["W"] * 3)
+        loss = torch.nn.functional.mse_loss(img, tgt, reduction="sum") / (n_views_total * wl["H"] * wl["W"] * 3)
         loss.backward()
         total = loss.detach() if total is None else total + loss.detach()
     allreduce_gradients([gm.verts, gm.sigmas, col])
@@ -466,7 +466,7 @@ def main():
                 main.wait_event(e)
                 frag = renderer(gm)
                 img = to_white_background(frag, col)
-                loss_c = ((img - tgt) ** 2).sum() / (args.views * H * W * 3)
+                loss_c = torch.nn.functional.mse_loss(img, tgt, reduction="sum") / (args.views * H * W * 3)
                 loss_c.backward()
                 total = loss_c.detach() if total is None else total + loss_c.detach()
             allreduce_gradients([gm.verts, gm.sigmas, col])

@@ -869,24 +869,27 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
             // neighbours only (a warp iterates max-over-lanes(neighbours) times)
             float gE = wgj / Ej + (total_gD - pref) + 0.5f * gDj;
             float gl = 0.f, gd = 0.f;
+            const float inv2sj = 0.5f / sj;
+            const float gDjk = gDj * kInvSqrtPi, Ejk = Ej * kInvSqrtPi;
             for (int t = lo_j; t < hi_j; ++t) {
                 const int i = t + (t >= j ? 1 : 0);
                 const float2 lsi = s_ls[i * NT + tid];
                 const float dl = lsi.x - lj;
                 const float gDi = -omega * s_wg[i * NT + tid];
-                // row i, column j:  c = (len_i - len_j) s_j
+                // row i, column j:  c = (len_i - len_j) s_j.  exp(-c^2), |c| < 4, through ex2.approx (2 ulp):
+                // these terms are the erf-slope corrections of the gradient, three orders below its tolerance
                 const float c = dl * sj;
                 if (c >= kErfSat) {
                     gE += gDi;
                 } else if (c > -kErfSat) {
                     gE += gDi * phi(c);
-                    const float gc = gDi * Ej * expf(-c * c) * kInvSqrtPi;
+                    const float gc = gDi * Ejk * __expf(-c * c);
                     gl -= gc * sj;
-                    gd += gc * dl / (2.f * sj);
+                    gd += gc * dl * inv2sj;
                 }
                 // row j, column i:  c' = (len_j - len_i) s_i  ->  d/d len_j
                 const float c2_ = -dl * lsi.y;
-                if (fabsf(c2_) < kErfSat) gl += gDj * s_E[i * NT + tid] * expf(-c2_ * c2_) * kInvSqrtPi * lsi.y;
+                if (fabsf(c2_) < kErfSat) gl += gDjk * s_E[i * NT + tid] * __expf(-c2_ * c2_) * lsi.y;
             }
             const float ga = -Ej * gE;
             if (a.g_len_out != nullptr) gl += a.g_len_out[r * a.K + j];
@@ -915,6 +918,207 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
     }
 }
 
+// Two threads per pixel (adjacent lanes; a warp covers a 4x4 pixel block): the per-pixel arrays in shared
+// memory bound the resident pixels per SM, and with one thread per pixel that left 20 warps of serial,
+// latency-bound work.  The pair shares the arrays; thread `sub` owns the slots k = sub, sub + 2, ... in every pass.
+template <int NT, int KIND, bool CAM>
+__global__ void __launch_bounds__(NT) render_bwd_pair_kernel(const FusedBwdArgs a) {
+    constexpr int NP = NT / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t A = (size_t)a.K * NP;
+    float2* s_ls = reinterpret_cast<float2*>(smem_raw);   // (len, s = sqrt(dsd + 1e-10))
+    float* s_E = reinterpret_cast<float*>(s_ls + A);      // exp(-act)
+    float* s_wg = s_E + A;                                // w_m * dL/dw_m
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, sub = lane & 1, col = tid >> 1;
+    const unsigned pair_mask = 3u << (lane & 30);
+    const int bw = (a.W + 3) / 4, bh = (a.H + 3) / 4;
+    const int64_t wid = ((int64_t)blockIdx.x * NT + tid) >> 5;
+    const int64_t per_view = (int64_t)bw * bh;
+    if (wid >= per_view * a.B) return;
+    const int b = (int)(wid / per_view);
+    const int wb = (int)(wid % per_view);
+    const int pp = lane >> 1;
+    const int xi = (wb % bw) * 4 + (pp & 3), yi = (wb / bw) * 4 + (pp >> 2);
+    const bool live = xi < a.W && yi < a.H;
+    if (!CAM && !live) return;       // with camera gradients every lane stays for the warp reduction at the end
+    const int64_t r = live ? ((int64_t)b * a.H + yi) * a.W + xi : 0;
+    const int cnt = live ? (int)min((int64_t)a.K, a.valid[r]) : 0;
+    if (!CAM && cnt == 0) return;
+    const float d0 = a.rays[r * 3 + 0], d1 = a.rays[r * 3 + 1], d2 = a.rays[r * 3 + 2];
+    const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
+    const float omega = a.omega;
+    float cam_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d/d(ray), d/d(origin) partial sums of this thread's slots
+    const int32_t* i_idx = a.idx + r * a.K;
+    const float* i_gw = a.g_weight + r * a.K;
+    const int pack_off = b * a.N;
+    const bool vec = (a.K & 3) == 0;
+
+    // ---- pass 0: recompute this thread's hits (bit-faithful); w_m dL/dw_m from the forward's weights ----
+    float s_min = 3.0e38f, total_gD = 0.f;
+    for (int k0 = 0; k0 < cnt; k0 += 4) {
+        int gv[2] = {-1, -1};
+        float wv[2] = {0.f, 0.f}, gwv[2] = {0.f, 0.f};
+        if (vec) {
+            const int4 q = *reinterpret_cast<const int4*>(i_idx + k0);
+            const float4 g4 = *reinterpret_cast<const float4*>(i_gw + k0);
+            gv[0] = sub ? q.y : q.x; gv[1] = sub ? q.w : q.z;
+            gwv[0] = sub ? g4.y : g4.x; gwv[1] = sub ? g4.w : g4.z;
+            if (a.weight != nullptr) {
+                const float4 w4 = *reinterpret_cast<const float4*>(a.weight + r * a.K + k0);
+                wv[0] = sub ? w4.y : w4.x; wv[1] = sub ? w4.w : w4.z;
+            }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int k = k0 + sub + 2 * jj;
+                if (k < cnt) {
+                    gv[jj] = i_idx[k]; gwv[jj] = i_gw[k];
+                    if (a.weight != nullptr) wv[jj] = a.weight[r * a.K + k];
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int k = k0 + sub + 2 * jj;
+            if (k < cnt) {
+                const int g = gv[jj] - pack_off;
+                Hit h;
+                h.len = kEmptyLen; h.act = kEmptyLen; h.dsd = 0.f;
+                if (g >= 0 && g < a.N) h = exact_hit_packed<KIND>(a.gauss, g, c0, c1, c2, d0, d1, d2);
+                const float sk = sqrtf(h.dsd + 1e-10f);
+                s_ls[k * NP + col] = make_float2(h.len, sk);
+                s_E[k * NP + col] = expf(-h.act);
+                s_min = fminf(s_min, sk);
+                if (a.weight != nullptr) {
+                    const float wg = wv[jj] * gwv[jj];
+                    s_wg[k * NP + col] = wg;
+                    total_gD -= omega * wg;       // gD_m = dL/dD_m = -omega w_m dL/dw_m
+                } else {
+                    s_wg[k * NP + col] = gwv[jj];  // upstream gradient, turned into w g below
+                }
+            }
+        }
+    }
+    s_min = fminf(s_min, __shfl_xor_sync(pair_mask, s_min, 1));
+    __syncwarp(pair_mask);
+    if (a.weight == nullptr) {
+        // ---- pass 1 (no saved weights): w_m = e^.5 exp(-omega D_m) E_m, D_m = sum_k E_k Phi((len_m - len_k) s_k);
+        // sorted lens => Phi = 1 below the window |len_m - len_k| s_min < 4 (running prefix of E), 0 above ----
+        int lo = 0;
+        float SE = 0.f;
+        for (int m = sub; m < cnt; m += 2) {
+            const float Em = s_E[m * NP + col];
+            const float lm = s_ls[m * NP + col].x;
+            while (lo < m && (lm - s_ls[lo * NP + col].x) * s_min >= kErfSat) { SE += s_E[lo * NP + col]; ++lo; }
+            float wg = 0.f;
+            if (Em != 0.f) {
+                float D = fmaf(Em, 0.5f, SE);         // k = m: Phi(0) = 1/2; the loop visits the neighbours only
+                for (int t = lo;; ++t) {
+                    const int k = t + (t >= m ? 1 : 0);
+                    if (k >= cnt) break;
+                    const float2 lk = s_ls[k * NP + col];
+                    const float dl = lm - lk.x;
+                    if (dl * s_min <= -kErfSat) break;
+                    D += s_E[k * NP + col] * phi(dl * lk.y);
+                }
+                wg = expf(-(D * omega)) * Em * kInvExpMinusHalf * s_wg[m * NP + col];
+            }
+            s_wg[m * NP + col] = wg;
+            total_gD -= omega * wg;
+        }
+        __syncwarp(pair_mask);
+    }
+    total_gD += __shfl_xor_sync(pair_mask, total_gD, 1);
+    // ---- pass 2: per slot j gather every contribution inside its (symmetric) window [lo_j, hi_j] in
+    // registers and apply the chain rule of ray_trace_voge.cu:324-330 at once ----
+    {
+        int lo_j = 0, hi_j = -1;
+        float pref = 0.f;                 // sum of gD_m over m <= hi_j
+        int4 ix4 = make_int4(-1, -1, -1, -1);
+        for (int j = sub; j < cnt; j += 2) {
+            // the Gaussian's record is fetched first: the gathers overlap with the window loop below
+            if (vec && (j & 3) == sub) ix4 = *reinterpret_cast<const int4*>(i_idx + (j & ~3));
+            const int gp = vec ? ((j & 2) ? ((j & 1) ? ix4.w : ix4.z) : ((j & 1) ? ix4.y : ix4.x)) : i_idx[j];
+            const int g = gp - pack_off;
+            const bool g_ok = g >= 0 && g < a.N;
+            float S[9], m0 = 0.f, m1 = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) S[q] = 0.f;
+            if (g_ok) {
+                float v0, v1, v2;
+                load_gauss<KIND>(a.gauss, g, v0, v1, v2, S);
+                m0 = __fsub_rn(v0, c0); m1 = __fsub_rn(v1, c1); m2 = __fsub_rn(v2, c2);
+            }
+            const float2 lsj = s_ls[j * NP + col];
+            const float lj = lsj.x, sj = lsj.y;
+            while (lo_j < j && (lj - s_ls[lo_j * NP + col].x) * s_min >= kErfSat) ++lo_j;
+            while (hi_j + 1 < cnt && (s_ls[(hi_j + 1) * NP + col].x - lj) * s_min < kErfSat) {
+                ++hi_j;
+                pref -= omega * s_wg[hi_j * NP + col];
+            }
+            const float Ej = s_E[j * NP + col];
+            if (Ej == 0.f) continue;
+            const float wgj = s_wg[j * NP + col];
+            const float gDj = -omega * wgj;
+            // direct path through the trailing exp(-act_j)  +  rows m behind the window see Phi = 1
+            // i = j: c = 0 => Phi = 1/2 and the two d/d(len_j) terms cancel exactly; the loop visits the
+            // neighbours only (a warp iterates max-over-lanes(neighbours) times)
+            float gE = wgj / Ej + (total_gD - pref) + 0.5f * gDj;
+            float gl = 0.f, gd = 0.f;
+            const float inv2sj = 0.5f / sj;
+            const float gDjk = gDj * kInvSqrtPi, Ejk = Ej * kInvSqrtPi;
+            for (int t = lo_j; t < hi_j; ++t) {
+                const int i = t + (t >= j ? 1 : 0);
+                const float2 lsi = s_ls[i * NP + col];
+                const float dl = lsi.x - lj;
+                const float gDi = -omega * s_wg[i * NP + col];
+                // row i, column j:  c = (len_i - len_j) s_j.  exp(-c^2), |c| < 4, through ex2.approx (2 ulp):
+                // these terms are the erf-slope corrections of the gradient, three orders below its tolerance
+                const float c = dl * sj;
+                if (c >= kErfSat) {
+                    gE += gDi;
+                } else if (c > -kErfSat) {
+                    gE += gDi * phi(c);
+                    const float gc = gDi * Ejk * __expf(-c * c);
+                    gl -= gc * sj;
+                    gd += gc * dl * inv2sj;
+                }
+                // row j, column i:  c' = (len_j - len_i) s_i  ->  d/d len_j
+                const float c2_ = -dl * lsi.y;
+                if (fabsf(c2_) < kErfSat) gl += gDjk * s_E[i * NP + col] * __expf(-c2_ * c2_) * lsi.y;
+            }
+            const float ga = -Ej * gE;
+            if (a.g_len_out != nullptr) gl += a.g_len_out[r * a.K + j];
+            if (ga == 0.f && gl == 0.f && gd == 0.f) continue;
+            if (!g_ok) continue;
+            const Prod9 pd = exact_row_products(d0, d1, d2, S);
+            const Prod9 pm = exact_row_products(m0, m1, m2, S);
+            const float ksk = exact_contract(pd, d0, d1, d2);
+            const float msk = exact_contract(pm, d0, d1, d2);
+            geom_grad_accumulate<CAM>(a, g, m0, m1, m2, S, d0, d1, d2, ksk, msk, gl, ga, gd, cam_acc);
+        }
+    }
+    if (CAM) {
+        __syncwarp();
+        if (a.grad_rays != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) cam_acc[q] += __shfl_xor_sync(0xffffffffu, cam_acc[q], 1);
+            if (live && sub == 0) {
+                a.grad_rays[r * 3 + 0] = cam_acc[0]; a.grad_rays[r * 3 + 1] = cam_acc[1]; a.grad_rays[r * 3 + 2] = cam_acc[2];
+            }
+        }
+        if (a.grad_origins != nullptr) {
+#pragma unroll
+            for (int q = 3; q < 6; ++q) {
+                float v = cam_acc[q];          // the 32 lanes of a warp belong to one view
+                for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_down_sync(0xffffffffu, v, sft);
+                if (lane == 0) atomicAdd(a.grad_origins + 3 * b + (q - 3), v);
+            }
+        }
+    }
+}
+
 }  // namespace voge
 
 extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
@@ -928,14 +1132,16 @@ extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
     FusedBwdArgs a{gauss, sigma_kind, origins, rays, idx, valid, grad_weight, weight, grad_len_out, absorptivity,
                    B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins};
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
-    const int64_t warps = (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
     cudaStream_t s = (cudaStream_t)stream;
     const bool cam = grad_rays != nullptr || grad_origins != nullptr;
-    auto launch = [&](auto kernel, int nt) -> int {
-        const size_t smem = (size_t)K * nt * 16;
+    auto launch = [&](auto kernel, int nt, int per_pixel) -> int {
+        // per_pixel = 2: two threads per pixel, 4x4 pixel blocks per warp; 1: 8x4 blocks
+        const int64_t warps = per_pixel == 2 ? (int64_t)B * cdiv(W, 4) * cdiv(H, 4) : (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
+        const size_t smem = (size_t)K * (nt / per_pixel) * 16;
         if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
         VOGE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t grid = (warps * 32 + nt - 1) / nt;
+        if (grid > 2147483647LL) return (int)cudaErrorInvalidValue;
         kernel<<<(unsigned)grid, nt, smem, s>>>(a);
         VOGE_LAUNCH_CHECK();
         return 0;
@@ -943,9 +1149,9 @@ extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
     auto by_threads = [&](auto kind_tag, auto cam_tag) -> int {
         constexpr int KIND = decltype(kind_tag)::value;
         constexpr bool CAM = decltype(cam_tag)::value;
-        if (K <= 56) return launch(render_bwd_fused_kernel<128, KIND, CAM>, 128);
-        if (K <= 200) return launch(render_bwd_fused_kernel<64, KIND, CAM>, 64);
-        return launch(render_bwd_fused_kernel<32, KIND, CAM>, 32);
+        if (K <= 112) return launch(render_bwd_pair_kernel<128, KIND, CAM>, 128, 2);
+        if (K <= 200) return launch(render_bwd_fused_kernel<64, KIND, CAM>, 64, 1);
+        return launch(render_bwd_fused_kernel<32, KIND, CAM>, 32, 1);
     };
     auto by_kind = [&](auto cam_tag) -> int {
         if (sigma_kind == 1) return by_threads(std::integral_constant<int, 1>{}, cam_tag);
