@@ -345,6 +345,110 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const BlendArgs a) {
     }
 }
 
+// Two threads per pixel (adjacent lanes; a warp covers a 4x4 pixel block), as in the fused backward: the
+// per-pixel arrays in shared memory bound the resident pixels, so the pair doubles the warps that hide the
+// latency of the gathers and of the serial blend loops.  Thread `sub` owns the slots k = sub, sub + 2, ...;
+// the (K,) rows are still written as 16-byte vectors after a two-value exchange inside the pair (K % 4 == 0).
+template <int NT, int KIND>
+__global__ void __launch_bounds__(NT) blend_pair_kernel(const BlendArgs a) {
+    constexpr int NP = NT / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s_ls = reinterpret_cast<float2*>(smem_raw);                 // [K][NP] (len, sqrt(dsd + 1e-10))
+    float* s_E = reinterpret_cast<float*>(s_ls + (size_t)a.K * NP);     // [K][NP] exp(-act)
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, sub = lane & 1, col = tid >> 1;
+    const unsigned pair_mask = 3u << (lane & 30);
+    const int bw = (a.W + 3) / 4, bh = (a.H + 3) / 4;
+    const int64_t wid = ((int64_t)blockIdx.x * NT + tid) >> 5;
+    const int64_t per_view = (int64_t)bw * bh;
+    if (wid >= per_view * a.B) return;
+    const int b = (int)(wid / per_view);
+    const int wb = (int)(wid % per_view);
+    const int pp = lane >> 1;
+    const int xi = (wb % bw) * 4 + (pp & 3), yi = (wb / bw) * 4 + (pp >> 2);
+    if (xi >= a.W || yi >= a.H) return;
+    const int64_t ray = ((int64_t)b * a.H + yi) * a.W + xi;
+    const int cnt = (int)min((int64_t)a.K, a.valid[ray]);
+    const int32_t* i_idx = a.idx + ray * a.K;
+    float* o_len = a.out_len + ray * a.K;
+    float* o_w = a.out_weight + ray * a.K;
+    float* o_act = a.out_act != nullptr ? a.out_act + ray * a.K : nullptr;
+    float* o_dsd = a.out_dsd != nullptr ? a.out_dsd + ray * a.K : nullptr;
+    if (cnt == 0) {
+        // empty pixel: padding only (thread 0 of the pair: len / dsd rows, thread 1: weight / act rows)
+        const float4 e4 = make_float4(kEmptyLen, kEmptyLen, kEmptyLen, kEmptyLen), z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < a.K; k += 4) {
+            if (sub == 0) { *reinterpret_cast<float4*>(o_len + k) = e4; if (o_dsd != nullptr) *reinterpret_cast<float4*>(o_dsd + k) = z4; }
+            else { *reinterpret_cast<float4*>(o_w + k) = z4; if (o_act != nullptr) *reinterpret_cast<float4*>(o_act + k) = e4; }
+        }
+        return;
+    }
+    const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
+    const float r0 = a.rays[ray * 3 + 0], r1 = a.rays[ray * 3 + 1], r2 = a.rays[ray * 3 + 2];
+    const int pack_off = b * a.N;
+    float s_min = 3.0e38f;
+    // ---- exact (len, act, dsd) of this thread's slots ----
+    for (int k0 = 0; k0 < a.K; k0 += 4) {
+        float lv[2] = {kEmptyLen, kEmptyLen}, av[2] = {kEmptyLen, kEmptyLen}, dv[2] = {0.f, 0.f};
+        if (k0 < cnt) {
+            const int4 q = *reinterpret_cast<const int4*>(i_idx + k0);
+            const int gv[2] = {sub ? q.y : q.x, sub ? q.w : q.z};
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int k = k0 + sub + 2 * jj;
+                if (k < cnt) {
+                    const Hit h = exact_hit_packed<KIND>(a.gauss, gv[jj] - pack_off, c0, c1, c2, r0, r1, r2);
+                    lv[jj] = h.len; av[jj] = h.act; dv[jj] = h.dsd;
+                    const float sk = sqrtf(h.dsd + 1e-10f);                              // Aggregation.py:49
+                    s_ls[k * NP + col] = make_float2(h.len, sk);
+                    s_E[k * NP + col] = expf(-h.act);
+                    s_min = fminf(s_min, sk);
+                }
+            }
+        }
+        // thread 0 holds slots (k0, k0+2), thread 1 (k0+1, k0+3): exchange and write whole rows of four
+        const float pl0 = __shfl_xor_sync(pair_mask, lv[0], 1), pl1 = __shfl_xor_sync(pair_mask, lv[1], 1);
+        if (sub == 0) *reinterpret_cast<float4*>(o_len + k0) = make_float4(lv[0], pl0, lv[1], pl1);
+        if (o_act != nullptr) {
+            const float pa0 = __shfl_xor_sync(pair_mask, av[0], 1), pa1 = __shfl_xor_sync(pair_mask, av[1], 1);
+            const float pd0 = __shfl_xor_sync(pair_mask, dv[0], 1), pd1 = __shfl_xor_sync(pair_mask, dv[1], 1);
+            if (sub == 1) *reinterpret_cast<float4*>(o_act + k0) = make_float4(pa0, av[0], pa1, av[1]);
+            if (sub == 0) *reinterpret_cast<float4*>(o_dsd + k0) = make_float4(dv[0], pd0, dv[1], pd1);
+        }
+    }
+    s_min = fminf(s_min, __shfl_xor_sync(pair_mask, s_min, 1));
+    __syncwarp(pair_mask);
+    // ---- blend weights of this thread's slots (see blend_weights_kernel) ----
+    {
+        int lo = 0;
+        float SE = 0.f;
+        for (int m0 = 0; m0 < a.K; m0 += 4) {
+            float wv[2] = {0.f, 0.f};
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int m = m0 + sub + 2 * jj;
+                if (m < cnt) {
+                    const float lm = s_ls[m * NP + col].x;
+                    while (lo < m && (lm - s_ls[lo * NP + col].x) * s_min >= kErfSat) { SE += s_E[lo * NP + col]; ++lo; }
+                    const float Em = s_E[m * NP + col];
+                    float D = fmaf(Em, 0.5f, SE);
+                    for (int t = lo;; ++t) {
+                        const int k = t + (t >= m ? 1 : 0);
+                        if (k >= cnt) break;
+                        const float2 lk = s_ls[k * NP + col];
+                        const float dl = lm - lk.x;
+                        if (dl * s_min <= -kErfSat) break;
+                        D += s_E[k * NP + col] * phi(dl * lk.y);
+                    }
+                    wv[jj] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
+                }
+            }
+            const float pw0 = __shfl_xor_sync(pair_mask, wv[0], 1), pw1 = __shfl_xor_sync(pair_mask, wv[1], 1);
+            if (sub == 1) *reinterpret_cast<float4*>(o_w + m0) = make_float4(pw0, wv[0], pw1, wv[1]);
+        }
+    }
+}
+
 template <int NT, int KIND>
 static int launch_blend(const BlendArgs& a, cudaStream_t stream) {
     const size_t smem = (size_t)a.K * NT * 12;
@@ -359,7 +463,21 @@ static int launch_blend(const BlendArgs& a, cudaStream_t stream) {
 }
 
 template <int KIND>
+static int launch_blend_pair(const BlendArgs& a, cudaStream_t stream) {
+    constexpr int NT = 128;
+    const size_t smem = (size_t)a.K * (NT / 2) * 12;
+    VOGE_CUDA_TRY(cudaFuncSetAttribute(blend_pair_kernel<NT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t warps = (int64_t)a.B * cdiv(a.W, 4) * cdiv(a.H, 4);
+    const int64_t grid = (warps * 32 + NT - 1) / NT;
+    if (grid <= 0 || grid > 2147483647LL) return (int)cudaErrorInvalidValue;
+    blend_pair_kernel<NT, KIND><<<(unsigned)grid, NT, smem, stream>>>(a);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int KIND>
 static int dispatch_blend(const BlendArgs& a, cudaStream_t s) {
+    if ((a.K & 3) == 0 && a.K <= 128) return launch_blend_pair<KIND>(a, s);
     // 12 K bytes of shared memory per thread: 128-thread CTAs while several of them fit on an SM
     if (a.K <= 48) return launch_blend<128, KIND>(a, s);
     if (a.K <= 280) return launch_blend<64, KIND>(a, s);
