@@ -216,6 +216,10 @@ int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind,
  *       ray_trace_voge.cu:197-213) -> out_idx (B,H,W,K) packed b*N+n / -1, out_valid (B,H,W) int64.
  *   voge_blend_weights: exact re-evaluation of the first valid[r] slots of idx, blend weights
  *       (Aggregation.py:30-107) -> out_weight, out_len (1e10 padded), optional out_act / out_dsd.
+ *   A batch may be processed in groups of views to bound the scratch (8 bytes per item): pass the group's
+ *   slices of rays / origins / rects / offsets / outputs, view_base = index of its first view (packed indices
+ *   are (view_base + b)*N + n) and item_base = tile_item_offsets value of its first tile (subtracted, so
+ *   that `hits` only needs the group's items).
  *   stats optional 4 x uint64 ([0] items evaluated, [2] pixels selected with the exact 64-bit keys), zeroed
  *   by the caller.                                                                                         */
 int voge_trace_threads(int tile);
@@ -223,15 +227,15 @@ int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind,
                         voge_stream_t stream);
 int voge_trace_hits(const float* gauss, int sigma_kind, const float* origins,
                     const float* rays, const int64_t* tile_offsets, const int32_t* tile_list,
-                    const uint32_t* rects, const int64_t* tile_item_offsets, float thr_act, int B, int N,
-                    int H, int W, int tile, int32_t* counts, int64_t* seg_base, uint32_t* hits,
+                    const uint32_t* rects, const int64_t* tile_item_offsets, int64_t item_base, float thr_act,
+                    int B, int N, int H, int W, int tile, int32_t* counts, int64_t* seg_base, uint32_t* hits,
                     uint64_t* stats, voge_stream_t stream);
 int voge_select_topk(const int32_t* counts, const int64_t* seg_base, const uint32_t* hits,
-                     int B, int N, int H, int W, int K, int tile,
+                     int view_base, int B, int N, int H, int W, int K, int tile,
                      int32_t* out_idx, int64_t* out_valid, uint64_t* stats, voge_stream_t stream);
 int voge_blend_weights(const float* gauss, int sigma_kind, const float* origins,
                        const float* rays, const int32_t* idx, const int64_t* valid, float absorptivity,
-                       int B, int N, int H, int W, int K, float* out_weight, float* out_len,
+                       int view_base, int B, int N, int H, int W, int K, float* out_weight, float* out_len,
                        float* out_act, float* out_dsd, voge_stream_t stream);
 int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind,
                          const float* origins, const float* rays, const int32_t* idx,

@@ -270,6 +270,11 @@ def test_forward_pipeline_dense_ties_and_single_kernel(K, hw):
         else:
             assert torch.equal(x, y), name
     assert torch.equal(p[0], a.vert_index)
+    # views traced one group at a time (bounded scratch) give the same fragments
+    g = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile, item_offsets=ioff,
+                          max_group_items=1)
+    for x, y in zip(p, g):
+        assert torch.equal(x, y)
     assert int(stats[0]) == ioff.total_items > 0          # every item evaluated exactly once
     assert int(stats[2]) > 0                              # the exact-key selection was exercised
     assert int(p[3].max()) == K

@@ -336,14 +336,19 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
                                    ptr(counts[1, 1:]), stream_of(verts)), "bin_count")
         # two 1-D scans (cub DeviceScan); a (2, n) scan along dim 1 runs one thread block per row
         offsets = (torch.cumsum(counts[0], 0, dtype=torch.int64), torch.cumsum(counts[1], 0, dtype=torch.int64))
-        totals = torch.stack([offsets[0][-1], offsets[1][-1]]).tolist()
-        total, total_items = int(totals[0]), int(totals[1])
+        # one host sync: total list entries + the item count at every view boundary (views can then be
+        # processed in groups that bound the forward's scratch)
+        per_view = TY * TX * S
+        host = torch.cat([offsets[0][-1:], offsets[1][::per_view]]).tolist()
+        total, view_item_starts = int(host[0]), [int(v) for v in host[1:]]
+        total_items = view_item_starts[-1]
         tile_list = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
         cursor = torch.zeros((B * TY * TX * S,), dtype=torch.int32, device=dev)
         check(lib().voge_bin_fill(ptr(rects), ptr(offsets[0]), ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
                                   stream_of(verts)), "bin_fill")
     item_offsets = offsets[1]
     item_offsets.total_items = total_items
+    item_offsets.view_item_starts = view_item_starts      # B + 1 host ints
     return offsets[0], tile_list, rects, item_offsets
 
 
@@ -358,10 +363,11 @@ def pack_gaussians(verts, sigmas):
 
 
 def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects, thr_act, absorptivity, K, tile,
-                   need_act=True, stats=None, item_offsets=None, gauss=None):
+                   need_act=True, stats=None, item_offsets=None, gauss=None, max_group_items=1 << 29):
     """Fragments of the fused renderer.  With item_offsets (bin_views' fourth result): trace_hits ->
-    select_topk -> blend_weights, no per-pixel capacity limit.  Without: the one-launch shared-memory top-K
-    kernel (voge_render_forward) -- same results, kept for cross-checks and very large item counts."""
+    select_topk -> blend_weights, no per-pixel capacity limit; the views are traced in groups of at most
+    max_group_items items (8 bytes of scratch each).  Without: the one-launch shared-memory top-K kernel
+    (voge_render_forward) -- same results, kept as a cross-check."""
     verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
     B, H, W = int(rays.shape[0]), int(rays.shape[1]), int(rays.shape[2])
     N, K = int(verts.shape[0]), int(K)
@@ -384,19 +390,41 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
         if gauss is None:
             gauss = pack_gaussians(verts, sigmas)
         nt = int(lib().voge_trace_threads(int(tile)))
-        n_tiles = (int(tile_offsets.numel()) - 1) // int(lib().voge_bin_sub())
-        total_items = int(item_offsets.total_items)
-        counts = torch.empty((n_tiles * nt,), dtype=torch.int32, device=dev)
-        seg_base = torch.empty((n_tiles * nt,), dtype=torch.int64, device=dev)
-        hits = torch.empty((max(total_items, 1), 2), dtype=torch.int32, device=dev)
-        check(lib().voge_trace_hits(ptr(gauss), skind, ptr(origins), ptr(rays), ptr(tile_offsets),
-                                    ptr(tile_list), ptr(rects), ptr(item_offsets), float(thr_act), B, N, H, W,
-                                    int(tile), ptr(counts), ptr(seg_base), ptr(hits), ptr(stats), st),
-              "trace_hits")
-        check(lib().voge_select_topk(ptr(counts), ptr(seg_base), ptr(hits), B, N, H, W, K, int(tile),
-                                     ptr(idx), ptr(valid), ptr(stats), st), "select_topk")
+        S = int(lib().voge_bin_sub())
+        tiles_per_view = (int(tile_offsets.numel()) - 1) // S // max(B, 1)
+        starts = getattr(item_offsets, "view_item_starts", None)
+        if starts is None:
+            starts = [0] * B + [int(item_offsets.total_items)]
+            groups = [(0, B)]
+        else:
+            # groups of consecutive views whose items fit the scratch budget (a single view always forms a group)
+            groups, b0 = [], 0
+            while b0 < B:
+                b1 = b0 + 1
+                while b1 < B and starts[b1 + 1] - starts[b0] <= max_group_items:
+                    b1 += 1
+                groups.append((b0, b1))
+                b0 = b1
+        cap = max(max(starts[b1] - starts[b0] for b0, b1 in groups), 1)
+        counts = torch.empty((B * tiles_per_view * nt,), dtype=torch.int32, device=dev)
+        seg_base = torch.empty((B * tiles_per_view * nt,), dtype=torch.int64, device=dev)
+        hits = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+
+        def sl(t, b0, b1, per):        # rows [b0*per, b1*per) of a flat per-view table
+            return t[b0 * per:b1 * per] if t is not None else None
+        for b0, b1 in groups:
+            nb = b1 - b0
+            t_off = tile_offsets[b0 * tiles_per_view * S:]
+            i_off = item_offsets[b0 * tiles_per_view * S:]
+            c_g, s_g = sl(counts, b0, b1, tiles_per_view * nt), sl(seg_base, b0, b1, tiles_per_view * nt)
+            check(lib().voge_trace_hits(ptr(gauss), skind, ptr(origins[b0:b1]), ptr(rays[b0:b1]), ptr(t_off),
+                                        ptr(tile_list), ptr(rects[b0:b1]), ptr(i_off), int(starts[b0]), float(thr_act),
+                                        nb, N, H, W, int(tile), ptr(c_g), ptr(s_g), ptr(hits), ptr(stats), st),
+                  "trace_hits")
+            check(lib().voge_select_topk(ptr(c_g), ptr(s_g), ptr(hits), b0, nb, N, H, W, K, int(tile),
+                                         ptr(idx[b0:b1]), ptr(valid[b0:b1]), ptr(stats), st), "select_topk")
         check(lib().voge_blend_weights(ptr(gauss), skind, ptr(origins), ptr(rays), ptr(idx), ptr(valid),
-                                       float(absorptivity), B, N, H, W, K, ptr(weight), ptr(tlen), ptr(act), ptr(dsd),
+                                       float(absorptivity), 0, B, N, H, W, K, ptr(weight), ptr(tlen), ptr(act), ptr(dsd),
                                        st), "blend_weights")
     return idx, weight, tlen, valid, act, dsd
 

@@ -44,9 +44,9 @@ SIGNATURES = {
                                  _P, _P, _P]),
     "voge_trace_threads": (_I, [_I]),
     "voge_pack_gaussians": (_I, [_P, _P, _I, _I, _P, _P]),
-    "voge_trace_hits": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "voge_select_topk": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
-    "voge_blend_weights": (_I, [_P, _I, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "voge_trace_hits": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _L, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "voge_select_topk": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "voge_blend_weights": (_I, [_P, _I, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "voge_render_backward_fused": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
     "voge_render_backward": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
 }

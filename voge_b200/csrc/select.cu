@@ -19,7 +19,8 @@ struct SelectArgs {
     const int64_t* seg_base;      // (B*TY*TX, TNT)
     const uint2* hits;            // (orderable len bits, local Gaussian index)
     int B, N, H, W, K, tile, TX, TY;
-    int32_t* out_idx;             // (B,H,W,K) packed b*N+g, -1 padded
+    int view_base;                // index of this call's first view in the batch (packed indices are (view_base + b)*N + g)
+    int32_t* out_idx;             // (B,H,W,K) packed, -1 padded
     int64_t* out_valid;           // (B,H,W)
     unsigned long long* stats;    // optional: [2] pixels selected with the exact 64-bit keys
 };
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) select_topk_kernel(const SelectA
     a.out_valid[ray] = min(c, a.K);
     const int64_t base = a.seg_base[tile_id * TNT + col];
     const uint2* hs = a.hits + base;
-    const int pack_off = b * a.N;
+    const int pack_off = (a.view_base + b) * a.N;
     bool done;
     if (wmax <= 16) done = select_network<16>(hs, c, a.K, pack_off, o_idx);
     else if (wmax <= 32) done = select_network<32>(hs, c, a.K, pack_off, o_idx);
@@ -207,6 +208,7 @@ struct BlendArgs {
     const int64_t* valid;         // (B,H,W)
     float omega;
     int B, N, H, W, K;
+    int view_base;                // as in SelectArgs
     float* out_weight;            // (B,H,W,K)
     float* out_len;               // (B,H,W,K), 1e10 padded
     float* out_act;               // optional (B,H,W,K)
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const BlendArgs a) {
     }
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
     const float r0 = a.rays[ray * 3 + 0], r1 = a.rays[ray * 3 + 1], r2 = a.rays[ray * 3 + 2];
-    const int pack_off = b * a.N;
+    const int pack_off = (a.view_base + b) * a.N;
     float s_min = 3.0e38f;
     for (int k0 = 0; k0 < a.K; k0 += 4) {
         int gv[4] = {-1, -1, -1, -1};
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(NT) blend_pair_kernel(const BlendArgs a) {
     }
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
     const float r0 = a.rays[ray * 3 + 0], r1 = a.rays[ray * 3 + 1], r2 = a.rays[ray * 3 + 2];
-    const int pack_off = b * a.N;
+    const int pack_off = (a.view_base + b) * a.N;
     float s_min = 3.0e38f;
     // ---- exact (len, act, dsd) of this thread's slots ----
     for (int k0 = 0; k0 < a.K; k0 += 4) {
@@ -486,7 +488,7 @@ static int dispatch_blend(const BlendArgs& a, cudaStream_t s) {
 
 }  // namespace voge
 
-extern "C" int voge_select_topk(const int32_t* counts, const int64_t* seg_base, const uint32_t* hits, int B, int N, int H, int W, int K, int tile,
+extern "C" int voge_select_topk(const int32_t* counts, const int64_t* seg_base, const uint32_t* hits, int view_base, int B, int N, int H, int W, int K, int tile,
                                 int32_t* out_idx, int64_t* out_valid, uint64_t* stats, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
@@ -494,6 +496,7 @@ extern "C" int voge_select_topk(const int32_t* counts, const int64_t* seg_base, 
     SelectArgs a;
     a.counts = counts; a.seg_base = seg_base; a.hits = reinterpret_cast<const uint2*>(hits);
     a.B = B; a.N = N; a.H = H; a.W = W; a.K = K; a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
+    a.view_base = view_base;
     a.out_idx = out_idx; a.out_valid = out_valid; a.stats = reinterpret_cast<unsigned long long*>(stats);
     cudaStream_t s = (cudaStream_t)stream;
     const int nt = tile_threads(tile);
@@ -504,13 +507,13 @@ extern "C" int voge_select_topk(const int32_t* counts, const int64_t* seg_base, 
 
 extern "C" int voge_blend_weights(const float* gauss, int sigma_kind, const float* origins,
                                   const float* rays, const int32_t* idx, const int64_t* valid, float absorptivity,
-                                  int B, int N, int H, int W, int K, float* out_weight, float* out_len,
+                                  int view_base, int B, int N, int H, int W, int K, float* out_weight, float* out_len,
                                   float* out_act, float* out_dsd, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
     BlendArgs a;
     a.gauss = gauss; a.origins = origins; a.rays = rays; a.idx = idx; a.valid = valid;
-    a.omega = absorptivity; a.B = B; a.N = N; a.H = H; a.W = W; a.K = K;
+    a.omega = absorptivity; a.B = B; a.N = N; a.H = H; a.W = W; a.K = K; a.view_base = view_base;
     a.out_weight = out_weight; a.out_len = out_len; a.out_act = out_act; a.out_dsd = out_dsd;
     cudaStream_t s = (cudaStream_t)stream;
     if (sigma_kind == 1) return dispatch_blend<1>(a, s);

@@ -33,6 +33,7 @@ struct TraceArgs {
     const int32_t* tile_list;          // local Gaussian indices
     const uint2* rects;                // (B,N) conservative pixel rectangles from bin_count_kernel
     const int64_t* tile_item_offsets;  // (B*TY*TX*kBinSub + 1) exclusive scan of tile_items
+    int64_t item_base;                 // subtracted from tile_item_offsets: first slot of this call's views in `hits`
     float thr_act;
     int B, N, H, W, tile, TX, TY;
     int32_t* counts;                   // out (B*TY*TX, NT): hits stored per pixel column (col = ly*tile + lx)
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     int cover = 0;
     if (tid < tile * tile)
         for (int y = 0; y <= ly; ++y) cover += s_rowp[y * 16 + lx];
-    const int64_t tile_base = a.tile_item_offsets[tile_id * kBinSub];
+    const int64_t tile_base = a.tile_item_offsets[tile_id * kBinSub] - a.item_base;
     {
         const int2 sc = block_scan<NT>(cover, s_wsum, lane, warp);
         s_base[tid] = sc.x - cover;
@@ -327,7 +328,7 @@ extern "C" int voge_trace_threads(int tile) { return voge::tile_threads(tile); }
 
 extern "C" int voge_trace_hits(const float* gauss, int sigma_kind, const float* origins,
                                const float* rays, const int64_t* tile_offsets, const int32_t* tile_list,
-                               const uint32_t* rects, const int64_t* tile_item_offsets, float thr_act, int B, int N,
+                               const uint32_t* rects, const int64_t* tile_item_offsets, int64_t item_base, float thr_act, int B, int N,
                                int H, int W, int tile, int32_t* counts, int64_t* seg_base, uint32_t* hits,
                                uint64_t* stats, voge_stream_t stream) {
     using namespace voge;
@@ -335,6 +336,7 @@ extern "C" int voge_trace_hits(const float* gauss, int sigma_kind, const float* 
     TraceArgs a;
     a.gauss = gauss; a.origins = origins; a.rays = rays; a.tile_offsets = tile_offsets;
     a.tile_list = tile_list; a.rects = reinterpret_cast<const uint2*>(rects); a.tile_item_offsets = tile_item_offsets;
+    a.item_base = item_base;
     a.thr_act = thr_act; a.B = B; a.N = N; a.H = H; a.W = W; a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
     a.counts = counts; a.seg_base = seg_base; a.hits = reinterpret_cast<uint2*>(hits);
     a.stats = reinterpret_cast<unsigned long long*>(stats);

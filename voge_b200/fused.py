@@ -16,11 +16,6 @@ from . import _C
 TILE_MAX = 16
 
 
-# items (rectangle pixels) per renderer call above which the one-launch top-K kernel is used instead of the
-# trace/select/blend pipeline (which needs 8 bytes of scratch per item)
-MAX_PIPELINE_ITEMS = 1 << 30
-
-
 def choose_tile(bin_size, K, use_ref_bins):
     """Largest tile (<= 16 px, dividing bin_size when the reference bins apply)."""
     import os
@@ -31,13 +26,6 @@ def choose_tile(bin_size, K, use_ref_bins):
     return cands[0]
 
 
-def single_kernel_fits(tile, K):
-    """Whether the one-launch kernel's per-pixel hit buffers (1.5 K keys, csrc/render.cu) fit in shared memory."""
-    px = tile * tile
-    nt = 256 if px > 128 else (128 if px > 64 else 64)
-    return ((3 * K + 1) // 2) * nt * 8 + nt * 24 <= 200 * 1024
-
-
 class _RenderFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, verts, sigmas, origins, rays, R, T, focal, principal, image_size, thr, absorptivity, K,
@@ -46,8 +34,6 @@ class _RenderFused(torch.autograd.Function):
         tile = choose_tile(bin_size, K, use_ref_bins)
         offsets, tile_list, rects, item_offsets = _C.bin_views(verts, sigmas, R, T, origins, focal, principal,
                                                                image_size, thr, thr_act, use_ref_bins, bin_size, tile)
-        if item_offsets.total_items > MAX_PIPELINE_ITEMS and single_kernel_fits(tile, K):
-            item_offsets = None
         gauss = _C.pack_gaussians(verts, sigmas)     # (N, 4|8|12) aligned records shared by forward and backward
         idx, weight, tlen, valid, _, _ = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list, rects,
                                                            thr_act, absorptivity, K, tile, need_act=False,
