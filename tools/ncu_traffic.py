@@ -4,7 +4,8 @@ the file for roofline.traffic).   usage: ncu_traffic.py report.ncu-rep views out
 import csv, io, json, re, subprocess, sys
 rep, views, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 SYM = [("trace_hits_kernel", "voge_trace_hits"), ("select_topk_kernel", "voge_select_topk"),
-       ("blend_weights_kernel", "voge_blend_weights"), ("render_bwd_fused_kernel", "voge_render_backward_fused"),
+       ("blend_weights_kernel", "voge_blend_weights"), ("blend_pair_kernel", "voge_blend_weights"),
+       ("render_bwd_fused_kernel", "voge_render_backward_fused"), ("render_bwd_pair_kernel", "voge_render_backward_fused"),
        ("merge_fwd", "voge_merge_final"), ("merge_bwd", "voge_merge_final_backward"),
        ("bin_count_kernel", "voge_bin_count"), ("bin_fill_kernel", "voge_bin_fill"),
        ("render_fwd_kernel", "voge_render_forward")]
