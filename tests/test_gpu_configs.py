@@ -72,3 +72,67 @@ def test_c4_two_cuboids_k60(oracle):
     sig = torch.tensor(np.concatenate([s1, s2]), dtype=torch.float32)
     R, T = oracle.look_at_view(4.0, 15.0, 30.0)
     _render_and_check(oracle, verts, sig, R, T, 300.0, (400, 400), K=60, M=1500)
+
+
+def test_c5_full_size_band_and_properties(oracle):
+    """BASELINE.json's metric configuration at full size (1M Gaussians, 1024^2, K=20), one view: a 64-row band
+    of the fragments bit-exact against the CPU oracle (reference coarse bins + fine kernel restatement), and
+    size-independent properties of the whole frame (sorted lens, unique in-range indices, padding, valid_num
+    checksum, determinism, pipeline == one-launch kernel)."""
+    import math
+    from voge_b200 import _C, scenes
+    from voge_b200.cameras import PerspectiveCameras, camera_params
+    from voge_b200.fused import choose_tile
+    from voge_b200.Meshes import GaussianMeshes
+    from voge_b200.RayTracing import default_bin_size
+    from voge_b200.Renderer import GaussianRenderer, GaussianRenderSettings
+    N, HW, K = 1_000_000, 1024, 20
+    verts, sig, _ = scenes.synthetic_scene(N, seed=0)
+    R, T = oracle.look_at_view(3.0, 0.0, 0.0)
+    cams = PerspectiveCameras(focal_length=900.0, principal_point=((HW / 2, HW / 2),), R=R, T=T, in_ndc=False,
+                              image_size=((HW, HW),), device=DEV)
+    renderer = GaussianRenderer(cams, GaussianRenderSettings(image_size=(HW, HW), max_assign=K)).to(DEV)
+    gm = GaussianMeshes(verts.clone(), sig.clone()).to(DEV)
+    with torch.no_grad():
+        frag = renderer(gm)
+        frag2 = renderer(gm)
+    idx, ln, w, valid = frag.vert_index, frag.vert_hit_length, frag.vert_weight, frag.valid_num
+    # determinism (hit order inside a segment is arbitrary, the selection is not)
+    assert torch.equal(idx, frag2.vert_index) and torch.equal(ln, frag2.vert_hit_length) and torch.equal(w, frag2.vert_weight)
+    # properties
+    ok = idx >= 0
+    assert torch.equal(ok.sum(-1), valid) and int(valid.max()) == K and int(valid.sum()) > 5_000_000
+    assert bool(((idx < N) & (idx >= -1)).all())
+    assert bool((ln[~ok] == 1e10).all()) and bool((w[~ok] == 0).all())
+    k = torch.arange(K, device=DEV)
+    assert bool((ok == (k < valid[..., None])).all())                       # valid slots are the leading ones
+    d = ln[..., 1:] - ln[..., :-1]
+    assert bool((d[ok[..., 1:]] >= 0).all())                                # ascending hit lengths
+    srt = torch.sort(torch.where(ok, idx, -1 - k.expand_as(idx)), dim=-1).values
+    assert bool((srt[..., 1:] != srt[..., :-1]).all())                      # a Gaussian hits a pixel at most once
+    assert bool((w >= 0).all()) and bool((w <= math.exp(0.5) + 1e-6).all())
+    # the one-launch kernel gives the same fragments
+    rays, origins = renderer._rays((HW, HW))
+    Rm, Tm, focal, principal = camera_params(cams, (HW, HW))
+    thr_act = -math.log(0.01 + 1e-10)
+    bs = default_bin_size((HW, HW)); tile = choose_tile(bs, K, True)
+    off, tl, rects, _ = _C.bin_views(gm.verts, gm.sigmas, Rm, Tm, origins, focal, principal, (HW, HW), 0.01, thr_act, True, bs, tile)
+    s = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile, need_act=False)
+    assert torch.equal(s[0], idx) and torch.equal(s[2], ln) and torch.equal(s[3], valid)
+    # a band of rows against the CPU oracle: reference coarse bins (bin 32) + fine kernel restatement
+    rows, y0 = 64, 480
+    mus = (verts[None] - origins.cpu()[:, None])
+    isg = (2 * sig)[None]
+    ndc, radii = oracle.coarse_inputs(R, T, 900.0, (HW / 2.0, HW / 2.0), (HW, HW), mus, isg, 0.01)
+    first, nper = torch.zeros(1, dtype=torch.long), torch.full((1,), N)
+    bp, bc = oracle.rasterize_coarse(ndc.reshape(-1, 3), radii.reshape(-1, 2), first, nper, (HW, HW), bs, 8192)
+    assert bc.max() <= 8192
+    bp_sub = torch.from_numpy(bp[:, y0 // bs:(y0 + rows) // bs, :, :int(bc.max())].copy())
+    rays_sub = rays[:, y0:y0 + rows].cpu().contiguous()
+    o_idx, o_len, _, _ = (torch.from_numpy(a) for a in oracle.ray_trace_fine(mus.reshape(-1, 3), isg.reshape(-1, 3, 3), rays_sub,
+                                                                             bp_sub, thr_act, bs, K))
+    g_idx, g_len = idx[:, y0:y0 + rows].cpu(), ln[:, y0:y0 + rows].cpu()
+    same = (g_idx == o_idx).all(-1)
+    # candidate sets can differ only for a Gaussian whose bbox edge is within an ulp of a bin edge
+    assert same.float().mean() > 0.9995
+    assert torch.equal(g_len[same], o_len[same])
