@@ -882,8 +882,9 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
                 if (c >= kErfSat) {
                     gE += gDi;
                 } else if (c > -kErfSat) {
-                    gE += gDi * phi(c);
-                    const float gc = gDi * Ejk * __expf(-c * c);
+                    float ec;
+                    gE += gDi * phi_fast(c, ec);
+                    const float gc = gDi * Ejk * ec;
                     gl -= gc * sj;
                     gd += gc * dl * inv2sj;
                 }
@@ -1020,7 +1021,7 @@ __global__ void __launch_bounds__(NT) render_bwd_pair_kernel(const FusedBwdArgs 
                     const float2 lk = s_ls[k * NP + col];
                     const float dl = lm - lk.x;
                     if (dl * s_min <= -kErfSat) break;
-                    D += s_E[k * NP + col] * phi(dl * lk.y);
+                    D += s_E[k * NP + col] * phi_f(dl * lk.y);
                 }
                 wg = expf(-(D * omega)) * Em * kInvExpMinusHalf * s_wg[m * NP + col];
             }
@@ -1079,8 +1080,9 @@ __global__ void __launch_bounds__(NT) render_bwd_pair_kernel(const FusedBwdArgs 
                 if (c >= kErfSat) {
                     gE += gDi;
                 } else if (c > -kErfSat) {
-                    gE += gDi * phi(c);
-                    const float gc = gDi * Ejk * __expf(-c * c);
+                    float ec;
+                    gE += gDi * phi_fast(c, ec);
+                    const float gc = gDi * Ejk * ec;
                     gl -= gc * sj;
                     gd += gc * dl * inv2sj;
                 }

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const BlendArgs a) {
                         const float2 lk = s_ls[k * NT + tid];
                         const float dl = lm - lk.x;
                         if (dl * s_min <= -kErfSat) break;
-                        D += s_E[k * NT + tid] * phi(dl * lk.y);
+                        D += s_E[k * NT + tid] * phi_f(dl * lk.y);
                     }
                     wv[j] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
                 }
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(NT) blend_pair_kernel(const BlendArgs a) {
                         const float2 lk = s_ls[k * NP + col];
                         const float dl = lm - lk.x;
                         if (dl * s_min <= -kErfSat) break;
-                        D += s_E[k * NP + col] * phi(dl * lk.y);
+                        D += s_E[k * NP + col] * phi_f(dl * lk.y);
                     }
                     wv[jj] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
                 }
