@@ -277,6 +277,15 @@ __global__ void __launch_bounds__(256) merge_fwd_small_kernel(const float* __res
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
     float wsum = 0.f;
     for (int k = 0; k < K; k += 4) {
+        if (k >= nv) {      // behind the valid hits only the silhouette sum needs the weights
+            if (VEC) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
+                wsum += w4.x; wsum += w4.y; wsum += w4.z; wsum += w4.w;
+            } else {
+                for (int j = 0; j < 4 && k + j < K; ++j) wsum += wrow[k + j];
+            }
+            continue;
+        }
         const Row4 row = load_row4<VEC>(wrow, irow, k, K);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -334,7 +343,17 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
         for (int c = 0; c < C; ++c) acc[c] = 0.f;
         float wsum = 0.f;
         if (need_acc) {
+            // index rows only as far as valid hits go (an empty pixel on a white background saturates too)
             for (int k = 0; k < K; k += 4) {
+                if (k >= nv) {
+                    if (VEC) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
+                        wsum += w4.x; wsum += w4.y; wsum += w4.z; wsum += w4.w;
+                    } else {
+                        for (int j = 0; j < 4 && k + j < K; ++j) wsum += wrow[k + j];
+                    }
+                    continue;
+                }
                 const Row4 row = load_row4<VEC>(wrow, irow, k, K);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -369,6 +388,16 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
         g_sumw *= min1_grad(wsum);
     }
     for (int k = 0; k < K; k += 4) {
+        if (k >= nv) {      // behind the valid hits only the silhouette term reaches the weights
+            if (g_weight != nullptr) {
+                if (VEC) {
+                    *reinterpret_cast<float4*>(g_weight + r * K + k) = make_float4(g_sumw, g_sumw, g_sumw, g_sumw);
+                } else {
+                    for (int j = 0; j < 4 && k + j < K; ++j) g_weight[r * K + k + j] = g_sumw;
+                }
+            }
+            continue;
+        }
         const Row4 row = load_row4<VEC>(wrow, irow, k, K);
         float gw4[4];
 #pragma unroll
