@@ -562,6 +562,18 @@ def main():
                      (8 * K + 8 + 12 + 4 * K) * rays_per_launch, 1e9, "8K B/ray + grad in, 4K B/ray grad_weight out"),
     ]
     kernels = [k for k in kernels if k is not None]
+    # SFU (MUFU) side of the ray-trace kernels, SURVEY 8d: 1 rcp per pair forward; K^2 x 2 per ray in the blend backward
+    for k in kernels:
+        sfu_ops = None
+        if k["kernel"].startswith("trace_hits"):
+            sfu_ops = 1.0 * pairs_per_launch
+        elif k["kernel"].startswith("render_bwd"):
+            sfu_ops = (K * K * 2.0) * rays_per_launch + 2.0 * hits_per_launch
+        elif k["kernel"].startswith("blend_weights"):
+            sfu_ops = (K * K * 1.0 + 2.0 * K) * rays_per_launch
+        if sfu_ops is not None:
+            k["sfu_achieved_tops"] = sfu_ops / (k["avg_launch_ms"] * 1e-3) / 1e12
+            k["sfu_frac"] = k["sfu_achieved_tops"] / peaks["sfu_tops"]
     kernels.sort(key=lambda k: -k["share_of_step"])
     fwd_ms = ops.get("render_forward", {"avg_ms": float("nan")})["avg_ms"]
     roofline = dict(kernels[0]) if kernels else {"kernel": None}
