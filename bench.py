@@ -424,7 +424,7 @@ def main():
     timer.enabled = False
     ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
     clocks = sampler.stop() if rank == 0 else None
-    launches = (_lib.launch_count - launches0) // max(args.steps, 1)
+    launches = _lib.launch_count - launches0        # C-ABI kernel launches inside the timed region (all steps)
     ms_step = ms_total / args.steps
     value = rays_total / (ms_step * 1e-3) / 1e6
     ops = timer.summary()
@@ -595,7 +595,7 @@ def main():
         "op_breakdown_ms_per_step": {k: v["total_ms"] / args.steps for k, v in ops.items()},
     })
     cpu = None
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:      # the CPU arm is timed at N=1 only
         c = cpu_port_sample(args)
         cpu = {"value": c["mrays"], "unit": "Mrays/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
     line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -607,9 +607,9 @@ def main():
                        "views_per_rank": count, "views_per_call": min(args.chunk, count),
                        "l2": "no flush needed: each renderer call streams %.0f MB of fragments (+ %d MB targets), "
                              ">> 126 MB L2" % (frag_bytes / 1e6, min(args.chunk, count) * H * W * 12 // 10 ** 6)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(args.steps, 1), "clocks": clocks,
             "loss": float(loss)}
-    if not args.no_ref_gpu:
+    if world == 1 and not args.no_ref_gpu:
         line["ref_gpu"] = ref_gpu_sample(wl, args, dev)
     print(json.dumps(line))
     if world > 1:
