@@ -62,14 +62,65 @@ __device__ __forceinline__ void ref_bin_range(float lo, float hi, int nb, int bi
     b0 = e0; b1 = e1;
 }
 
-// Per-Gaussian worst-case bound on |act_reference - act_true| + filter error (same formula as
-// stage_candidate) and PD check; returns false if the Gaussian must not be culled analytically.
+// Per-Gaussian worst-case bound E on |act_reference - act_exact| over all unit rays, act_exact being the
+// real-arithmetic value msm - msk^2/ksk of the same fp32 inputs.  A pixel outside the projected ellipsoid
+// {act_exact < thr + E} then has act_reference >= thr and can never be a hit, whatever the rounding does.
+// Forward error analysis of exact_pair (common.cuh): every term of the three 9-term forms passes through
+// at most 10 roundings (one product t_ij, nine partial sums), gamma_10 ~ 10 u, u = 2^-24:
+//   |msm - msm*| <= g10 Tmm,  |msk - msk*| <= g10 Um2 |d|,  |ksk - ksk*| <= g10 Us |d|^2,
+//   q = rn(rn(msk^2)/ksk):  |q - q*| <= 2 Qn g10 Um2 / l + Qn^2 g10 Us / l^2 + 2.1 u Qn^2 / l   (first order),
+//   act = rn(msm - q)  =>  E = u [10 Tmm + 20 Qn Um2 / l + 10 Us Qn^2 / l^2 + 2.1 Qn^2 / l + 2 thr] x 1.25
+// with Tmm = sum |mu_i S_ij mu_j|, Um2 = || |S|^T |mu| ||_2, Qn = || S^T mu ||_2, Us >= || |S| ||_2,
+// l = lambda_min(sym S); the factor 1.25 covers the second-order terms, which stay below 1 % of the first-order
+// ones as long as g10 Us / l < 1e-2 (otherwise the Gaussian is not culled analytically).  This is about half
+// the margin of the pixel-major filter (fine_core.cuh), which also has to cover its own re-associated sums.
 __device__ __forceinline__ bool gaussian_margin(const float* mu, const float* S, float thr_act, float& margin) {
-    __align__(16) float tmp[kStageFloats];
-    stage_candidate(tmp, 0, mu, S, thr_act);
-    if (!(tmp[3] > -3.0e38f)) return false;   // flagged "never reject"
-    margin = tmp[11];
-    return margin >= 0.f;
+    const float m0 = mu[0], m1 = mu[1], m2 = mu[2];
+    const float q0 = m0 * S[0] + m1 * S[3] + m2 * S[6];
+    const float q1 = m0 * S[1] + m1 * S[4] + m2 * S[7];
+    const float q2 = m0 * S[2] + m1 * S[5] + m2 * S[8];
+    const float a = S[0], b = S[4], c = S[8];
+    const float s01 = 0.5f * (S[1] + S[3]), s02 = 0.5f * (S[2] + S[6]), s12 = 0.5f * (S[5] + S[7]);
+    // smallest / largest eigenvalue of the symmetric part (closed form, Smith 1961)
+    float lmin, lmax;
+    {
+        const float p1 = s01 * s01 + s02 * s02 + s12 * s12;
+        if (p1 == 0.f) {
+            lmin = fminf(a, fminf(b, c));
+            lmax = fmaxf(a, fmaxf(b, c));
+        } else {
+            const float qq = (a + b + c) * (1.f / 3.f);
+            const float aa = a - qq, bb = b - qq, cc = c - qq;
+            const float p = sqrtf((aa * aa + bb * bb + cc * cc + 2.f * p1) * (1.f / 6.f));
+            const float ip = 1.f / p;
+            const float b00 = aa * ip, b11 = bb * ip, b22 = cc * ip, b01 = s01 * ip, b02 = s02 * ip, b12 = s12 * ip;
+            float r = 0.5f * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+            r = fminf(1.f, fmaxf(-1.f, r));
+            const float phi = acosf(r) * (1.f / 3.f);
+            lmax = qq + 2.f * p * cosf(phi);
+            lmin = qq + 2.f * p * cosf(phi + 2.0943951023931953f);
+        }
+        lmin -= 1e-5f * fabsf(lmax);   // rounding of the closed form itself
+    }
+    if (!(lmin > 0.f)) return false;
+    const float am0 = fabsf(m0), am1 = fabsf(m1), am2 = fabsf(m2);
+    const float c0 = am0 * fabsf(S[0]) + am1 * fabsf(S[3]) + am2 * fabsf(S[6]);   // (|S|^T |mu|)_j
+    const float c1 = am0 * fabsf(S[1]) + am1 * fabsf(S[4]) + am2 * fabsf(S[7]);
+    const float c2 = am0 * fabsf(S[2]) + am1 * fabsf(S[5]) + am2 * fabsf(S[8]);
+    const float Tmm = c0 * am0 + c1 * am1 + c2 * am2;
+    const float Um2 = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
+    const float Qn = sqrtf(q0 * q0 + q1 * q1 + q2 * q2);
+    const float r0 = fabsf(S[0]) + fabsf(S[1]) + fabsf(S[2]), r1 = fabsf(S[3]) + fabsf(S[4]) + fabsf(S[5]),
+                r2 = fabsf(S[6]) + fabsf(S[7]) + fabsf(S[8]);
+    const float k0 = fabsf(S[0]) + fabsf(S[3]) + fabsf(S[6]), k1 = fabsf(S[1]) + fabsf(S[4]) + fabsf(S[7]),
+                k2 = fabsf(S[2]) + fabsf(S[5]) + fabsf(S[8]);
+    const float Us = fmaxf(fmaxf(fmaxf(r0, r1), r2), fmaxf(fmaxf(k0, k1), k2));
+    const float il = 1.f / lmin;
+    if (!(Us * il < 1.6e4f)) return false;                       // g10 Us / l < 1e-2: second-order terms negligible
+    const float bound = 10.f * Tmm + 20.f * Qn * Um2 * il + 10.f * Us * (Qn * il) * (Qn * il) + 2.1f * Qn * Qn * il +
+                        2.f * fabsf(thr_act);
+    margin = 7.4505806e-8f * 1.003f * bound;                     // 1.25 x 2^-24 (x rays within 1e-3 of unit length)
+    return margin >= 0.f && margin < 3.0e38f;
 }
 
 __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
