@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     int2* s_meta_all = reinterpret_cast<int2*>(s_rec_all + 2 * (size_t)NT * REC);          // [2][NT+2] (first item, packed rect)
     unsigned* s_bmask_all = reinterpret_cast<unsigned*>(s_meta_all + 2 * (NT + 2));        // [2][kMaxBlocks] first-item bits
     float* s_ray = reinterpret_cast<float*>(s_bmask_all + 2 * kMaxBlocks);                 // [3][NT]
-    int* s_cnt = reinterpret_cast<int*>(s_ray + 3 * NT);                                   // [NT] hits stored
+    int* s_cnt = reinterpret_cast<int*>(s_ray + 3 * NT);                                   // [NT] next free slot of the pixel's segment (tile-relative)
     int* s_base = s_cnt + NT;                                                              // [NT] segment start within the tile area
     int* s_wsum = s_base + NT;                                                             // [32] scan scratch (two halves)
     unsigned short* s_first_all = reinterpret_cast<unsigned short*>(s_wsum + 32);          // [2][kMaxBlocks] owner of a block's first item
@@ -115,7 +115,6 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
         }
         s_ray[tid] = r0; s_ray[NT + tid] = r1; s_ray[2 * NT + tid] = r2;
     }
-    s_cnt[tid] = 0;
     for (int i = tid; i < 17 * 17; i += NT) s_diff[i] = 0;
 
     const int64_t beg = a.tile_offsets[tile_id * kBinSub];
@@ -153,6 +152,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     {
         const int2 sc = block_scan<NT>(cover, s_wsum, lane, warp);
         s_base[tid] = sc.x - cover;
+        s_cnt[tid] = sc.x - cover;       // the slot counter starts at the segment base: one atomic yields the slot
         a.seg_base[tile_id * NT + tid] = tile_base + (sc.x - cover);
     }
     __syncthreads();   // the records alias s_diff / s_rowp
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
                     const float len = __fdiv_rn(msk[j], ksk[j]);
                     if (len < kEmptyLen) {
                         const int slot = atomicAdd(&s_cnt[cols[j]], 1);
-                        a.hits[tile_base + s_base[cols[j]] + slot] = make_uint2(orderable(len), (unsigned)gg);
+                        a.hits[tile_base + slot] = make_uint2(orderable(len), (unsigned)gg);
                     }
                 }
             }
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
         base += max(taken, 1);
     }
     __syncthreads();
-    a.counts[tile_id * NT + tid] = s_cnt[tid];
+    a.counts[tile_id * NT + tid] = s_cnt[tid] - s_base[tid];
     if (a.stats != nullptr) {
         unsigned long long e = n_eval;
         for (int s = 16; s > 0; s >>= 1) e += __shfl_down_sync(0xffffffffu, e, s);
