@@ -363,7 +363,7 @@ def pack_gaussians(verts, sigmas):
 
 
 def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects, thr_act, absorptivity, K, tile,
-                   need_act=True, stats=None, item_offsets=None, gauss=None, max_group_items=1 << 29):
+                   need_act=True, stats=None, item_offsets=None, gauss=None, max_group_items=1 << 29, debug=None):
     """Fragments of the fused renderer.  With item_offsets (bin_views' fourth result): trace_hits ->
     select_topk -> blend_weights, no per-pixel capacity limit; the views are traced in groups of at most
     max_group_items items (8 bytes of scratch each).  Without: the one-launch shared-memory top-K kernel
@@ -426,6 +426,8 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
         check(lib().voge_blend_weights(ptr(gauss), skind, ptr(origins), ptr(rays), ptr(idx), ptr(valid),
                                        float(absorptivity), 0, B, N, H, W, K, ptr(weight), ptr(tlen), ptr(act), ptr(dsd),
                                        st), "blend_weights")
+        if debug is not None:          # development aid (tools/select_hist.py): the per-pixel hit counts of the trace
+            debug["counts"], debug["threads_per_tile"] = counts, nt
     return idx, weight, tlen, valid, act, dsd
 
 

@@ -245,6 +245,47 @@ __device__ __forceinline__ Row4 load_row4(const float* __restrict__ wrow, const 
     return o;
 }
 
+// Row k..k+3 of a pixel whose first nv slots are valid: behind the valid hits only the weights are read (the
+// silhouette sum needs them), the indices come back as -1.
+template <bool VEC>
+__device__ __forceinline__ Row4 load_row4_nv(const float* __restrict__ wrow, const int32_t* __restrict__ irow, int k, int K,
+                                             int nv) {
+    Row4 o;
+    if (VEC) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
+        int4 i4 = make_int4(-1, -1, -1, -1);
+        if (k < nv) i4 = *reinterpret_cast<const int4*>(irow + k);
+        o.w[0] = w4.x; o.w[1] = w4.y; o.w[2] = w4.z; o.w[3] = w4.w;
+        o.g[0] = i4.x; o.g[1] = i4.y; o.g[2] = i4.z; o.g[3] = i4.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o.w[j] = (k + j < K) ? wrow[k + j] : 0.f;
+            o.g[j] = (k + j < nv) ? irow[k + j] : -1;
+        }
+    }
+    return o;
+}
+
+// g mod d for 0 <= g < 2^31 without the integer-division sequence: with m = floor((2^32 - 1) / d) (computed on the
+// host) q = umulhi(g, m) is floor(g / d) or one less, so one conditional subtraction finishes the remainder.
+struct FastMod {
+    unsigned d, m;     // d == 0: identity
+};
+static inline FastMod make_fastmod(int d) {
+    FastMod f;
+    f.d = d > 0 ? (unsigned)d : 0u;
+    f.m = d > 0 ? 0xffffffffu / (unsigned)d : 0u;
+    return f;
+}
+__device__ __forceinline__ int fold_index(int g, const FastMod f) {
+    g = max(g, 0);                              // Aggregation.py:131  vert_assign += (vert_assign < 0)
+    if (f.d == 0u) return g;
+    unsigned r = (unsigned)g - __umulhi((unsigned)g, f.m) * f.d;
+    if (r >= f.d) r -= f.d;
+    return (int)r;
+}
+
 // attribute row of Gaussian g: one 16-byte load from a float4-padded table (P4), C scalar loads otherwise
 template <int C, bool P4>
 __device__ __forceinline__ void load_attr(const float* __restrict__ attr, int g, float* av) {
@@ -265,7 +306,7 @@ __global__ void __launch_bounds__(256) merge_fwd_small_kernel(const float* __res
                                                               const int32_t* __restrict__ idx,
                                                               const int64_t* __restrict__ valid_num,
                                                               const float* __restrict__ background, float mask_thr,
-                                                              int64_t R, int K, int idx_mod, int n_attr,
+                                                              int64_t R, int K, FastMod idx_mod, int n_attr,
                                                               float* __restrict__ out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
@@ -276,29 +317,28 @@ __global__ void __launch_bounds__(256) merge_fwd_small_kernel(const float* __res
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
     float wsum = 0.f;
+    // the rows of the next four slots are requested before the gathers of the current four are consumed: a pixel
+    // costs one row latency plus K/4 gather latencies instead of K/4 of each
+    Row4 row = load_row4_nv<VEC>(wrow, irow, 0, K, nv);
     for (int k = 0; k < K; k += 4) {
-        if (k >= nv) {      // behind the valid hits only the silhouette sum needs the weights
-            if (VEC) {
-                const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
-                wsum += w4.x; wsum += w4.y; wsum += w4.z; wsum += w4.w;
-            } else {
-                for (int j = 0; j < 4 && k + j < K; ++j) wsum += wrow[k + j];
-            }
-            continue;
-        }
-        const Row4 row = load_row4<VEC>(wrow, irow, k, K);
+        Row4 nxt = row;
+        if (k + 4 < K) nxt = load_row4_nv<VEC>(wrow, irow, k + 4, K, nv);
+        // the four gathers are requested together (predicated loads, no branch between them)
+        float av[4][C];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             wsum += row.w[j];
-            int g = max(row.g[j], 0);            // Aggregation.py:131  vert_assign += (vert_assign < 0)
-            if (idx_mod > 0) g %= idx_mod;
-            if (k + j < nv && g < n_attr) {
-                float av[C];
-                load_attr<C, P4>(attr, g, av);
+            const int g = fold_index(row.g[j], idx_mod);
+            const bool ok = k + j < nv && g < n_attr;
 #pragma unroll
-                for (int c = 0; c < C; ++c) acc[c] = fmaf(row.w[j], av[c], acc[c]);
-            }
+            for (int c = 0; c < C; ++c) av[j][c] = 0.f;
+            if (ok) load_attr<C, P4>(attr, g, av[j]);
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fmaf(row.w[j], av[j][c], acc[c]);
+        row = nxt;
     }
     if (background != nullptr) {
         const float sil = fminf(wsum, 1.f);                                      // Renderer.py:157-159
@@ -318,7 +358,7 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
                                                               const float* __restrict__ background, float mask_thr,
                                                               const float* __restrict__ g_out,
                                                               const float* __restrict__ fwd_out, int64_t R, int K,
-                                                              int idx_mod, int n_attr, float* __restrict__ g_attr4,
+                                                              FastMod idx_mod, int n_attr, float* __restrict__ g_attr4,
                                                               float* __restrict__ g_weight) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
@@ -358,8 +398,7 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     wsum += row.w[j];
-                    int g = max(row.g[j], 0);
-                    if (idx_mod > 0) g %= idx_mod;
+                    const int g = fold_index(row.g[j], idx_mod);
                     if (k + j < nv && g < n_attr) {
                         float av[C];
                         load_attr<C, P4>(attr, g, av);
@@ -387,6 +426,9 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
         }
         g_sumw *= min1_grad(wsum);
     }
+    // software-pipelined rows as in the forward kernel
+    Row4 row;
+    if (nv > 0) row = load_row4<VEC>(wrow, irow, 0, K);
     for (int k = 0; k < K; k += 4) {
         if (k >= nv) {      // behind the valid hits only the silhouette term reaches the weights
             if (g_weight != nullptr) {
@@ -398,25 +440,36 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
             }
             continue;
         }
-        const Row4 row = load_row4<VEC>(wrow, irow, k, K);
+        Row4 nxt = row;
+        if (k + 4 < nv) nxt = load_row4<VEC>(wrow, irow, k + 4, K);
         float gw4[4];
+        // the four gathers are requested together (predicated loads); the reductions need no gathered value and
+        // follow once all loads are in flight
+        float av[4][C];
+        int gs[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int g = fold_index(row.g[j], idx_mod);
+            const bool ok = k + j < nv && g < n_attr;
+            gs[j] = ok ? g : -1;
+#pragma unroll
+            for (int c = 0; c < C; ++c) av[j][c] = 0.f;
+            if (ok) load_attr<C, P4>(attr, g, av[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (g_attr4 != nullptr && gs[j] >= 0 && row.w[j] != 0.f) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < C; ++c) v[c] = row.w[j] * go[c];
+                atomicAdd(reinterpret_cast<float4*>(g_attr4 + 4 * (int64_t)gs[j]), make_float4(v[0], v[1], v[2], v[3]));
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float gw = g_sumw;
-            int g = max(row.g[j], 0);
-            if (idx_mod > 0) g %= idx_mod;
-            if (k + j < nv && g < n_attr) {
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                float av[C];
-                load_attr<C, P4>(attr, g, av);
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    gw = fmaf(go[c], av[c], gw);
-                    v[c] = row.w[j] * go[c];
-                }
-                if (g_attr4 != nullptr && row.w[j] != 0.f)
-                    atomicAdd(reinterpret_cast<float4*>(g_attr4 + 4 * (int64_t)g), make_float4(v[0], v[1], v[2], v[3]));
-            }
+            for (int c = 0; c < C; ++c) gw = fmaf(go[c], av[j][c], gw);    // av == 0 for invalid slots
             gw4[j] = gw;
         }
         if (g_weight != nullptr) {
@@ -428,6 +481,7 @@ __global__ void __launch_bounds__(256) merge_bwd_small_kernel(const float* __res
                     if (k + j < K) g_weight[r * K + k + j] = gw4[j];
             }
         }
+        row = nxt;
     }
 }
 
@@ -489,20 +543,21 @@ extern "C" int voge_merge_final(const float* attr, const float* weight, const in
     if (C <= 4) {
         const unsigned grid = (unsigned)((R + 255) / 256);
         cudaStream_t s = (cudaStream_t)stream;
+        const FastMod fm = make_fastmod(idx_mod);
 #define VOGE_MF(CC)                                                                                                 \
     do {                                                                                                            \
         if (K % 4 == 0 && attr_padded4)                                                                             \
             merge_fwd_small_kernel<CC, true, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,  \
-                                                                        mask_thr, R, K, idx_mod, n_attr, out);      \
+                                                                        mask_thr, R, K, fm, n_attr, out);           \
         else if (K % 4 == 0)                                                                                        \
             merge_fwd_small_kernel<CC, true, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
-                                                                         mask_thr, R, K, idx_mod, n_attr, out);     \
+                                                                         mask_thr, R, K, fm, n_attr, out);          \
         else if (attr_padded4)                                                                                      \
             merge_fwd_small_kernel<CC, false, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
-                                                                         mask_thr, R, K, idx_mod, n_attr, out);     \
+                                                                         mask_thr, R, K, fm, n_attr, out);          \
         else                                                                                                        \
             merge_fwd_small_kernel<CC, false, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,\
-                                                                          mask_thr, R, K, idx_mod, n_attr, out);    \
+                                                                          mask_thr, R, K, fm, n_attr, out);         \
     } while (0)
         if (C == 1) VOGE_MF(1); else if (C == 2) VOGE_MF(2); else if (C == 3) VOGE_MF(3); else VOGE_MF(4);
 #undef VOGE_MF
@@ -530,23 +585,24 @@ extern "C" int voge_merge_final_backward(const float* attr, const float* weight,
     if (C <= 4 && (packed4 || grad_attr == nullptr)) {
         const unsigned grid = (unsigned)((R + 255) / 256);
         cudaStream_t s = (cudaStream_t)stream;
+        const FastMod fm = make_fastmod(idx_mod);
 #define VOGE_MB(CC)                                                                                                 \
     do {                                                                                                            \
         if (K % 4 == 0 && attr_padded4)                                                                             \
             merge_bwd_small_kernel<CC, true, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,  \
-                                                                        mask_thr, grad_out, out, R, K, idx_mod, n_attr, \
+                                                                        mask_thr, grad_out, out, R, K, fm, n_attr,      \
                                                                         grad_attr, grad_weight);                    \
         else if (K % 4 == 0)                                                                                        \
             merge_bwd_small_kernel<CC, true, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
-                                                                         mask_thr, grad_out, out, R, K, idx_mod, n_attr,\
+                                                                         mask_thr, grad_out, out, R, K, fm, n_attr,     \
                                                                          grad_attr, grad_weight);                   \
         else if (attr_padded4)                                                                                      \
             merge_bwd_small_kernel<CC, false, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
-                                                                         mask_thr, grad_out, out, R, K, idx_mod, n_attr,\
+                                                                         mask_thr, grad_out, out, R, K, fm, n_attr,     \
                                                                          grad_attr, grad_weight);                   \
         else                                                                                                        \
             merge_bwd_small_kernel<CC, false, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,\
-                                                                          mask_thr, grad_out, out, R, K, idx_mod, n_attr,\
+                                                                          mask_thr, grad_out, out, R, K, fm, n_attr,     \
                                                                           grad_attr, grad_weight);                  \
     } while (0)
         if (C == 1) VOGE_MB(1); else if (C == 2) VOGE_MB(2); else if (C == 3) VOGE_MB(3); else VOGE_MB(4);
