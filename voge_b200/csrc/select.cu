@@ -122,6 +122,71 @@ __device__ __forceinline__ bool select_network(const uint2* __restrict__ hs, int
     return true;
 }
 
+// Segments of 33..64 hits when K < 32: only the 32 smallest composites are needed, so instead of sorting all 64
+// (543 compare-exchanges) the two halves are sorted separately (2 x 191), min(a[i], b[31 - i]) keeps the 32
+// smallest of their union as a bitonic sequence (32 min) and a bitonic merge (5 x 16 compare-exchanges) sorts
+// them.  A tie between a kept and a dropped key cannot matter: the caller needs K <= 31 entries and a tie
+// inside the kept 32 is detected as usual.
+template <size_t... I>
+__device__ __forceinline__ void bitonic_merge32_impl(unsigned (&r)[32], std::index_sequence<I...>) {
+    // comparator I of stage I / 16 (stride 16 >> stage): the I % 16-th index with the stride bit clear
+    ((void)([&] {
+         constexpr int stride = 16 >> (I / 16);
+         constexpr int q = I % 16;
+         constexpr int lo = ((q / stride) * 2 * stride) + (q % stride);
+         const unsigned x = r[lo], y = r[lo + stride];
+         r[lo] = min(x, y);
+         r[lo + stride] = max(x, y);
+     }()),
+     ...);
+}
+
+__device__ __forceinline__ bool select_network64_top32(const uint2* __restrict__ hs, int c, int K, int pack_off,
+                                                       int32_t* __restrict__ o_idx) {
+    unsigned a[32], b[32];
+    unsigned omin = 0xffffffffu, omax = 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        a[j] = 0xffffffffu; b[j] = 0xffffffffu;
+        if (j < c) { a[j] = __ldg(&hs[j].x); omin = min(omin, a[j]); omax = max(omax, a[j]); }
+        if (j + 32 < c) { b[j] = __ldg(&hs[j + 32].x); omin = min(omin, b[j]); omax = max(omax, b[j]); }
+    }
+    if (c > 0 && omax - omin >= 0x3ffffffu) return false;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < c) a[j] = ((a[j] - omin) << 6) | (unsigned)j;
+        if (j + 32 < c) b[j] = ((b[j] - omin) << 6) | (unsigned)(j + 32);
+    }
+    sort_network<32>(a);
+    sort_network<32>(b);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = min(a[i], b[31 - i]);
+    bitonic_merge32_impl(a, std::make_index_sequence<80>{});
+    const int ck = min(c, 32);
+    bool tie = false;
+#pragma unroll
+    for (int i = 1; i < 32; ++i) tie = tie || ((i < ck) && ((a[i] ^ a[i - 1]) < 64u));
+    if (tie) return false;
+    const int m = min(c, K);
+    const bool vec = (K & 3) == 0;
+#pragma unroll
+    for (int i0 = 0; i0 < 32; i0 += 4) {
+        if (i0 < K) {
+            int v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (i0 + j < m) ? pack_off + (int)__ldg(&hs[a[i0 + j] & 63u].y) : -1;
+            if (vec) {
+                *reinterpret_cast<int4*>(o_idx + i0) = make_int4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (i0 + j < K) o_idx[i0 + j] = v[j];
+            }
+        }
+    }
+    return true;
+}
+
 // exact selection with the full (len, idx) keys: K passes, each extracting the smallest key above the
 // previous one (keys are unique: a Gaussian hits a pixel at most once).  O(K c) loads, any c.
 __device__ __noinline__ void select_exact(const uint2* __restrict__ hs, int c, int K, int pack_off,
@@ -182,6 +247,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) select_topk_kernel(const SelectA
     bool done;
     if (wmax <= 16) done = select_network<16>(hs, c, a.K, pack_off, o_idx);
     else if (wmax <= 32) done = select_network<32>(hs, c, a.K, pack_off, o_idx);
+    else if (c <= 64 && a.K < 32) done = select_network64_top32(hs, c, a.K, pack_off, o_idx);
     else if (c <= 64) done = select_network<64>(hs, c, a.K, pack_off, o_idx);
     else done = false;
     if (!done) {
