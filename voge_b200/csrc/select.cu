@@ -80,14 +80,18 @@ __device__ __forceinline__ void sort_network(unsigned (&r)[N]) {
 // then selects with the full (len, idx) keys).  Writes the (K,) index row, -1 padded.
 template <int N>
 __device__ __forceinline__ bool select_network(const uint2* __restrict__ hs, int c, int K, int pack_off,
-                                               int32_t* __restrict__ o_idx) {
+                                               unsigned* __restrict__ s_y, int lane, int32_t* __restrict__ o_idx) {
     unsigned r[N];
     unsigned omin = 0xffffffffu, omax = 0u;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         r[j] = 0xffffffffu;
         if (j < c) {
-            r[j] = __ldg(&hs[j].x);
+            // the index half of the hit is parked in shared memory ([slot][lane]: conflict-free) so that the
+            // winners' indices need no second trip to a segment that has left L1 by then
+            const uint2 h = __ldg(&hs[j]);
+            r[j] = h.x;
+            s_y[j * 32 + lane] = h.y;
             omin = min(omin, r[j]);
             omax = max(omax, r[j]);
         }
@@ -108,7 +112,7 @@ __device__ __forceinline__ bool select_network(const uint2* __restrict__ hs, int
         if (i0 < K) {
             int v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (i0 + j < m) ? pack_off + (int)__ldg(&hs[r[i0 + j] & 63u].y) : -1;
+            for (int j = 0; j < 4; ++j) v[j] = (i0 + j < m) ? pack_off + (int)s_y[(r[i0 + j] & 63u) * 32 + lane] : -1;
             if (vec) {
                 *reinterpret_cast<int4*>(o_idx + i0) = make_int4(v[0], v[1], v[2], v[3]);
             } else {
@@ -122,11 +126,7 @@ __device__ __forceinline__ bool select_network(const uint2* __restrict__ hs, int
     return true;
 }
 
-// Segments of 33..64 hits when K < 32: only the 32 smallest composites are needed, so instead of sorting all 64
-// (543 compare-exchanges) the two halves are sorted separately (2 x 191), min(a[i], b[31 - i]) keeps the 32
-// smallest of their union as a bitonic sequence (32 min) and a bitonic merge (5 x 16 compare-exchanges) sorts
-// them.  A tie between a kept and a dropped key cannot matter: the caller needs K <= 31 entries and a tie
-// inside the kept 32 is detected as usual.
+// bitonic merge network on 32 registers (5 stages of 16 compare-exchanges): sorts a bitonic sequence ascending
 template <size_t... I>
 __device__ __forceinline__ void bitonic_merge32_impl(unsigned (&r)[32], std::index_sequence<I...>) {
     // comparator I of stage I / 16 (stride 16 >> stage): the I % 16-th index with the stride bit clear
@@ -141,49 +141,71 @@ __device__ __forceinline__ void bitonic_merge32_impl(unsigned (&r)[32], std::ind
      ...);
 }
 
-__device__ __forceinline__ bool select_network64_top32(const uint2* __restrict__ hs, int c, int K, int pack_off,
-                                                       int32_t* __restrict__ o_idx) {
-    unsigned a[32], b[32];
+// Segments of 33..64 hits: TWO adjacent lanes per pixel, 32 slots each (lane `sub` takes slots sub*32 ..), so that
+// the kernel needs the registers of the 32-input network only (twice the resident warps of a 64-input one, a third
+// of the code).  Each lane sorts its half; min / max against the partner's reversed half (lane 0 keeps the 32
+// smallest composites, lane 1 the 32 largest, both bitonic) and a bitonic merge per lane give the sorted 64.
+// Returns false (in both lanes) where the composites are not exact, see select_network.
+__device__ __forceinline__ bool select_pair(const uint2* __restrict__ hs, int c, int K, int pack_off, int sub,
+                                            unsigned pair_mask, unsigned* __restrict__ s_y, int lane,
+                                            int32_t* __restrict__ o_idx) {
+    unsigned r[32];
     unsigned omin = 0xffffffffu, omax = 0u;
+    const int j0 = sub * 32;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        a[j] = 0xffffffffu; b[j] = 0xffffffffu;
-        if (j < c) { a[j] = __ldg(&hs[j].x); omin = min(omin, a[j]); omax = max(omax, a[j]); }
-        if (j + 32 < c) { b[j] = __ldg(&hs[j + 32].x); omin = min(omin, b[j]); omax = max(omax, b[j]); }
+    for (int i = 0; i < 32; ++i) {
+        r[i] = 0xffffffffu;
+        if (j0 + i < c) {
+            const uint2 h = __ldg(&hs[j0 + i]);
+            r[i] = h.x;
+            s_y[i * 32 + lane] = h.y;          // slot j0 + i lives in the column of the lane that loaded it
+            omin = min(omin, r[i]);
+            omax = max(omax, r[i]);
+        }
     }
+    omin = min(omin, __shfl_xor_sync(pair_mask, omin, 1));
+    omax = max(omax, __shfl_xor_sync(pair_mask, omax, 1));
     if (c > 0 && omax - omin >= 0x3ffffffu) return false;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (j < c) a[j] = ((a[j] - omin) << 6) | (unsigned)j;
-        if (j + 32 < c) b[j] = ((b[j] - omin) << 6) | (unsigned)(j + 32);
+    for (int i = 0; i < 32; ++i)
+        if (j0 + i < c) r[i] = ((r[i] - omin) << 6) | (unsigned)(j0 + i);
+    sort_network<32>(r);
+#pragma unroll
+    for (int x = 0; x < 16; ++x) {
+        const unsigned t1 = __shfl_xor_sync(pair_mask, r[31 - x], 1), t2 = __shfl_xor_sync(pair_mask, r[x], 1);
+        r[x] = sub ? max(r[x], t1) : min(r[x], t1);
+        r[31 - x] = sub ? max(r[31 - x], t2) : min(r[31 - x], t2);
     }
-    sort_network<32>(a);
-    sort_network<32>(b);
+    bitonic_merge32_impl(r, std::make_index_sequence<80>{});
+    // ranks sub*32 + i; a tie is two neighbouring ranks below c with equal len bits
+    const unsigned below = __shfl_xor_sync(pair_mask, r[31], 1);      // lane 1: rank 31
+    bool tie = sub && (32 < c) && ((r[0] ^ below) < 64u);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) a[i] = min(a[i], b[31 - i]);
-    bitonic_merge32_impl(a, std::make_index_sequence<80>{});
-    const int ck = min(c, 32);
-    bool tie = false;
-#pragma unroll
-    for (int i = 1; i < 32; ++i) tie = tie || ((i < ck) && ((a[i] ^ a[i - 1]) < 64u));
+    for (int i = 1; i < 32; ++i) tie = tie || ((j0 + i < c) && ((r[i] ^ r[i - 1]) < 64u));
+    tie = __shfl_xor_sync(pair_mask, (int)tie, 1) || tie;
     if (tie) return false;
+    __syncwarp(pair_mask);                                      // the partner's index column is read below
     const int m = min(c, K);
     const bool vec = (K & 3) == 0;
 #pragma unroll
     for (int i0 = 0; i0 < 32; i0 += 4) {
-        if (i0 < K) {
+        if (j0 + i0 < K) {
             int v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (i0 + j < m) ? pack_off + (int)__ldg(&hs[a[i0 + j] & 63u].y) : -1;
+            for (int j = 0; j < 4; ++j) {
+                const unsigned slot = r[i0 + j] & 63u;
+                v[j] = (j0 + i0 + j < m) ? pack_off + (int)s_y[(slot & 31u) * 32 + ((lane & 30) | (int)(slot >> 5))] : -1;
+            }
             if (vec) {
-                *reinterpret_cast<int4*>(o_idx + i0) = make_int4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<int4*>(o_idx + j0 + i0) = make_int4(v[0], v[1], v[2], v[3]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (i0 + j < K) o_idx[i0 + j] = v[j];
+                    if (j0 + i0 + j < K) o_idx[j0 + i0 + j] = v[j];
             }
         }
     }
+    for (int k = 64 + sub; k < K; k += 2) o_idx[k] = -1;
     return true;
 }
 
@@ -206,6 +228,34 @@ __device__ __noinline__ void select_exact(const uint2* __restrict__ hs, int c, i
     for (int k = m; k < K; ++k) o_idx[k] = -1;
 }
 
+// The same selection by a whole warp for ONE pixel: lanes stride over the segment (coalesced loads, L1 hits after
+// the first pass), the lexicographic (len, idx) minimum above the previous key is found with two warp
+// reductions (REDUX.MIN on the len bits, then on the indices of the lanes that hold that len), and the K results
+// are written 32 at a time, one per lane.  O(K c / 32) loads per lane instead of O(K c).
+__device__ __noinline__ void select_exact_warp(const uint2* __restrict__ hs, int c, int K, int pack_off,
+                                               int32_t* __restrict__ o_idx, int lane) {
+    unsigned prev_x = 0u, prev_y = 0u;
+    const int m = min(c, K);
+    int keep = -1;
+    for (int k = 0; k < m; ++k) {
+        unsigned bx = 0xffffffffu, by = 0xffffffffu;
+        for (int j = lane; j < c; j += 32) {
+            const uint2 h = hs[j];
+            const bool above = (k == 0) || h.x > prev_x || (h.x == prev_x && h.y > prev_y);
+            if (above && (h.x < bx || (h.x == bx && h.y < by))) { bx = h.x; by = h.y; }
+        }
+        const unsigned mx = __reduce_min_sync(0xffffffffu, bx);
+        const unsigned my = __reduce_min_sync(0xffffffffu, bx == mx ? by : 0xffffffffu);
+        prev_x = mx; prev_y = my;
+        if ((k & 31) == lane) keep = pack_off + (int)my;
+        if ((k & 31) == 31 || k == m - 1) {
+            const int k0 = k & ~31;
+            if (k0 + lane <= k) o_idx[k0 + lane] = keep;
+        }
+    }
+    for (int k = m + lane; k < K; k += 32) o_idx[k] = -1;
+}
+
 // thread -> pixel of a tile: 8x4 pixel blocks per warp on 16x16 tiles (neighbouring pixels see the same
 // Gaussians), row-major otherwise
 template <int TNT>
@@ -221,38 +271,86 @@ __device__ __forceinline__ void thread_to_pix(int t, int tile, int& lx, int& ly,
     }
 }
 
-template <int NT, int TNT>
-__global__ void __launch_bounds__(NT, 512 / NT) select_topk_kernel(const SelectArgs a) {
-    const int tid = threadIdx.x;
-    constexpr int PARTS = TNT / NT;
-    const int64_t tile_id = blockIdx.x / PARTS;
+// pixel `ti` (thread index within the tile) of tile (b, ty, tx): hit count, segment, ray index.  The kernel
+// re-derives these where it needs them instead of carrying them (registers are what bounds its occupancy).
+struct SelPix {
+    bool live;
+    int c;
+    const uint2* hs;
+    int64_t ray;
+};
+template <int TNT>
+__device__ __forceinline__ SelPix select_pixel(const SelectArgs& a, int64_t tile_id, int ti) {
     const int t = (int)(tile_id % ((int64_t)a.TX * a.TY));
     const int b = (int)(tile_id / ((int64_t)a.TX * a.TY));
     const int tx = t % a.TX, ty = t / a.TX;
     int lx, ly;
     bool in_tile;
-    thread_to_pix<TNT>((blockIdx.x % PARTS) * NT + tid, a.tile, lx, ly, in_tile);
+    thread_to_pix<TNT>(ti, a.tile, lx, ly, in_tile);
     const int col = ly * a.tile + lx;
     const int xi = tx * a.tile + lx, yi = ty * a.tile + ly;
-    const bool live = in_tile && xi < a.W && yi < a.H;
-    const int c = live ? a.counts[tile_id * TNT + col] : 0;
-    const int wmax = __reduce_max_sync(0xffffffffu, c);
-    if (!live) return;
-    const int64_t ray = ((int64_t)b * a.H + yi) * a.W + xi;
-    int32_t* o_idx = a.out_idx + ray * a.K;
-    a.out_valid[ray] = min(c, a.K);
-    const int64_t base = a.seg_base[tile_id * TNT + col];
-    const uint2* hs = a.hits + base;
-    const int pack_off = (a.view_base + b) * a.N;
-    bool done;
-    if (wmax <= 16) done = select_network<16>(hs, c, a.K, pack_off, o_idx);
-    else if (wmax <= 32) done = select_network<32>(hs, c, a.K, pack_off, o_idx);
-    else if (c <= 64 && a.K < 32) done = select_network64_top32(hs, c, a.K, pack_off, o_idx);
-    else if (c <= 64) done = select_network<64>(hs, c, a.K, pack_off, o_idx);
-    else done = false;
-    if (!done) {
-        select_exact(hs, c, a.K, pack_off, o_idx);
-        if (a.stats != nullptr) atomicAdd(a.stats + 2, 1ull);
+    SelPix p;
+    p.live = in_tile && xi < a.W && yi < a.H;
+    p.c = p.live ? a.counts[tile_id * TNT + col] : 0;
+    p.hs = a.hits + (p.live ? a.seg_base[tile_id * TNT + col] : 0);
+    p.ray = p.live ? ((int64_t)b * a.H + yi) * a.W + xi : 0;
+    return p;
+}
+
+template <int NT, int TNT>
+__global__ void __launch_bounds__(NT, 1024 / NT) select_topk_kernel(const SelectArgs a) {
+    __shared__ unsigned s_idx[NT / 32][32 * 32];       // per warp: index halves of the loaded hits, [slot][lane]
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    unsigned* s_y = s_idx[tid >> 5];
+    constexpr int PARTS = TNT / NT;
+    const int64_t tile_id = blockIdx.x / PARTS;
+    const int ti0 = (blockIdx.x % PARTS) * NT + (tid & ~31);      // first pixel of this warp within the tile
+    const int pack_off = (a.view_base + (int)(tile_id / ((int64_t)a.TX * a.TY))) * a.N;
+    bool done = true;
+    int wmax;
+    {
+        const SelPix me = select_pixel<TNT>(a, tile_id, ti0 + lane);
+        wmax = __reduce_max_sync(0xffffffffu, me.c);
+        if (me.live) {
+            a.out_valid[me.ray] = min(me.c, a.K);
+            int32_t* o_idx = a.out_idx + me.ray * a.K;
+            if (wmax <= 16) done = select_network<16>(me.hs, me.c, a.K, pack_off, s_y, lane, o_idx);
+            else if (wmax <= 32) done = select_network<32>(me.hs, me.c, a.K, pack_off, s_y, lane, o_idx);
+        }
+    }
+    if (wmax > 32) {
+        // two lanes per pixel, 16 pixels per pass; pixels with more than 64 hits go to the exact selection
+        const int sub = lane & 1;
+        const unsigned pair_mask = 3u << (lane & 30);
+        unsigned failed[2];
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const SelPix px = select_pixel<TNT>(a, tile_id, ti0 + pass * 16 + (lane >> 1));
+            bool ok = true;
+            if (px.live) ok = px.c <= 64 && select_pair(px.hs, px.c, a.K, pack_off, sub, pair_mask, s_y, lane, a.out_idx + px.ray * a.K);
+            failed[pass] = __ballot_sync(0xffffffffu, !ok);
+            __syncwarp();                                        // pass 1 overwrites the index columns
+        }
+        done = !(((lane < 16 ? failed[0] : failed[1]) >> (2 * (lane & 15))) & 1u);
+    }
+    // pixels the networks could not finish (more than 64 hits, tied lens, lens spanning > 8 binades): a few
+    // per warp are selected by the whole warp, many (a warp inside a very dense region) by their own lanes
+    unsigned slow = __ballot_sync(0xffffffffu, !done);
+    if (slow == 0u) return;
+    if (a.stats != nullptr && lane == 0) atomicAdd(a.stats + 2, (unsigned long long)__popc(slow));
+    if (__popc(slow) > 8) {
+        if (!done) {
+            const SelPix me = select_pixel<TNT>(a, tile_id, ti0 + lane);
+            select_exact(me.hs, me.c, a.K, pack_off, a.out_idx + me.ray * a.K);
+        }
+        return;
+    }
+    while (slow != 0u) {
+        const int p = __ffs(slow) - 1;
+        slow &= slow - 1u;
+        const SelPix px = select_pixel<TNT>(a, tile_id, ti0 + p);
+        select_exact_warp(px.hs, px.c, a.K, pack_off, a.out_idx + px.ray * a.K, lane);
     }
 }
 
