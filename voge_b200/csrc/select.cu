@@ -141,7 +141,7 @@ __device__ __forceinline__ void bitonic_merge32_impl(unsigned (&r)[32], std::ind
      ...);
 }
 
-// Segments of 33..64 hits: TWO adjacent lanes per pixel, 32 slots each (lane `sub` takes slots sub*32 ..), so that
+// Segments of 33..64 hits: TWO adjacent lanes per pixel, 32 slots each, so that
 // the kernel needs the registers of the 32-input network only (twice the resident warps of a 64-input one, a third
 // of the code).  Each lane sorts its half; min / max against the partner's reversed half (lane 0 keeps the 32
 // smallest composites, lane 1 the 32 largest, both bitonic) and a bitonic merge per lane give the sorted 64.
@@ -151,14 +151,16 @@ __device__ __forceinline__ bool select_pair(const uint2* __restrict__ hs, int c,
                                             int32_t* __restrict__ o_idx) {
     unsigned r[32];
     unsigned omin = 0xffffffffu, omax = 0u;
-    const int j0 = sub * 32;
+    const int j0 = sub * 32;                 // first RANK of this lane after the merge
+    // slots are interleaved between the two lanes (lane `sub` loads slots 2 i + sub): the pair's two 8-byte loads
+    // of one instruction are adjacent, i.e. one L1 wavefront instead of two
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
         r[i] = 0xffffffffu;
-        if (j0 + i < c) {
-            const uint2 h = __ldg(&hs[j0 + i]);
+        if (2 * i + sub < c) {
+            const uint2 h = __ldg(&hs[2 * i + sub]);
             r[i] = h.x;
-            s_y[i * 32 + lane] = h.y;          // slot j0 + i lives in the column of the lane that loaded it
+            s_y[i * 32 + lane] = h.y;          // slot 2 i + sub lives in the column of the lane that loaded it
             omin = min(omin, r[i]);
             omax = max(omax, r[i]);
         }
@@ -168,7 +170,7 @@ __device__ __forceinline__ bool select_pair(const uint2* __restrict__ hs, int c,
     if (c > 0 && omax - omin >= 0x3ffffffu) return false;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-        if (j0 + i < c) r[i] = ((r[i] - omin) << 6) | (unsigned)(j0 + i);
+        if (2 * i + sub < c) r[i] = ((r[i] - omin) << 6) | (unsigned)(2 * i + sub);
     sort_network<32>(r);
 #pragma unroll
     for (int x = 0; x < 16; ++x) {
@@ -194,7 +196,7 @@ __device__ __forceinline__ bool select_pair(const uint2* __restrict__ hs, int c,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const unsigned slot = r[i0 + j] & 63u;
-                v[j] = (j0 + i0 + j < m) ? pack_off + (int)s_y[(slot & 31u) * 32 + ((lane & 30) | (int)(slot >> 5))] : -1;
+                v[j] = (j0 + i0 + j < m) ? pack_off + (int)s_y[(slot >> 1) * 32 + ((lane & 30) | (int)(slot & 1u))] : -1;
             }
             if (vec) {
                 *reinterpret_cast<int4*>(o_idx + j0 + i0) = make_int4(v[0], v[1], v[2], v[3]);
