@@ -278,3 +278,49 @@ def test_forward_pipeline_dense_ties_and_single_kernel(K, hw):
     assert int(stats[0]) == ioff.total_items > 0          # every item evaluated exactly once
     assert int(stats[2]) > 0                              # the exact-key selection was exercised
     assert int(p[3].max()) == K
+
+
+@pytest.mark.parametrize("K,hw,scale", [(20, (64, 64), 0.08), (40, (64, 64), 0.08), (60, (48, 80), 0.05), (25, (40, 56), 0.12),
+                                        (64, (64, 64), 0.05)])
+def test_select_topk_hit_count_classes(K, hw, scale):
+    """select_topk over every per-pixel hit-count class -- one lane per pixel (<= 16 / <= 32 hits), two lanes per
+    pixel (33..64, ranks 32.. written by the second lane when K > 32), warp-cooperative and per-lane exact
+    selection (> 64 hits, tied lens) -- for K below / at / above 32 and K % 4 != 0: bit-identical index lists
+    to the op-by-op chain (pixel-major fine kernel with the reference's insertion rule)."""
+    from voge_b200 import _C
+    from voge_b200.cameras import camera_params
+    from voge_b200.fused import choose_tile
+    from voge_b200.RayTracing import default_bin_size
+    sc = small_scene(seed=31, aniso=True, views=2, n=700, image_size=hw, focal=70.0)
+    sig = sc["sigmas"]
+    sig[:450] *= scale                      # wide blobs of graded density: hit lists from a few to > 64 entries
+    verts = sc["verts"]
+    verts[450:470] = verts[0:20]            # duplicates: tied lens inside otherwise ordinary pixels
+    sig[450:470] = sig[0:20]
+    renderer, gm = _setup(sc, "full", K=K, M=700)
+    rays, origins = renderer._rays(hw)
+    R, T, focal, principal = camera_params(renderer.cameras, hw)
+    R, T = R.expand(2, -1, -1).contiguous(), T.expand(2, -1).contiguous()
+    focal, principal = focal.expand(2, -1).contiguous(), principal.expand(2, -1).contiguous()
+    thr_act = -math.log(0.01 + 1e-10)
+    bs = default_bin_size(hw); tile = choose_tile(bs, K, True)
+    off, tl, rects, ioff = _C.bin_views(gm.verts, gm.sigmas, R, T, origins, focal, principal, hw, 0.01, thr_act, True, bs, tile)
+    stats = torch.zeros(4, dtype=torch.int64, device=DEV)
+    dbg = {}
+    p = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile, stats=stats,
+                          item_offsets=ioff, debug=dbg)
+    a, b = _both(renderer, gm)
+    assert torch.equal(a.vert_index, b.vert_index) and torch.equal(a.valid_num, b.valid_num)
+    assert torch.equal(a.vert_hit_length, b.vert_hit_length)
+    assert torch.equal(p[0], b.vert_index) and torch.equal(p[3], b.valid_num)
+    wmax = dbg["counts"].view(-1, 32).max(dim=1).values
+    classes = [int(((wmax >= lo) & (wmax <= hi)).sum()) for lo, hi in ((1, 16), (17, 32), (33, 64), (65, 10 ** 9))]
+    assert classes[2] > 0 and classes[3] > 0 and (classes[0] > 0 or classes[1] > 0), classes
+    assert int(stats[2]) > 0
+    # selected lists are ascending in (len, idx) and padded consistently
+    idx, ln, valid = p[0], p[2], p[3]
+    kk = torch.arange(K, device=DEV).view(1, 1, 1, K)
+    live = kk < valid.unsqueeze(-1)
+    assert bool(((idx >= 0) == live).all())
+    d = ln[..., 1:] - ln[..., :-1]
+    assert bool((d[live[..., 1:]] >= 0).all())
