@@ -8,6 +8,7 @@
 #include "../../include/voge_b200.h"
 #include "common.cuh"
 #include "blend_core.cuh"
+#include "sort_net.h"
 
 namespace voge {
 
@@ -265,25 +266,6 @@ __device__ __forceinline__ Row4 load_row4_nv(const float* __restrict__ wrow, con
         }
     }
     return o;
-}
-
-// g mod d for 0 <= g < 2^31 without the integer-division sequence: with m = floor((2^32 - 1) / d) (computed on the
-// host) q = umulhi(g, m) is floor(g / d) or one less, so one conditional subtraction finishes the remainder.
-struct FastMod {
-    unsigned d, m;     // d == 0: identity
-};
-static inline FastMod make_fastmod(int d) {
-    FastMod f;
-    f.d = d > 0 ? (unsigned)d : 0u;
-    f.m = d > 0 ? 0xffffffffu / (unsigned)d : 0u;
-    return f;
-}
-__device__ __forceinline__ int fold_index(int g, const FastMod f) {
-    g = max(g, 0);                              // Aggregation.py:131  vert_assign += (vert_assign < 0)
-    if (f.d == 0u) return g;
-    unsigned r = (unsigned)g - __umulhi((unsigned)g, f.m) * f.d;
-    if (r >= f.d) r -= f.d;
-    return (int)r;
 }
 
 // attribute row of Gaussian g: one 16-byte load from a float4-padded table (P4), C scalar loads otherwise

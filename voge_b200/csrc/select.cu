@@ -10,6 +10,7 @@
 #include "blend_core.cuh"
 #include "fine_core.cuh"
 #include "render_core.cuh"
+#include "sort_net.h"
 #include <utility>
 
 namespace voge {
@@ -24,55 +25,6 @@ struct SelectArgs {
     int64_t* out_valid;           // (B,H,W)
     unsigned long long* stats;    // optional: [2] pixels selected with the exact 64-bit keys
 };
-
-// Batcher's odd-even merge sort on N registers: the network of the next power of two without the comparators
-// that touch the (implicit, +inf) inputs above N -- 63 / 191 / 384 / 543 compare-exchanges for N = 16 / 32 / 48 /
-// 64, each a VIMNMX pair on 32-bit keys.  The comparator list is built at compile time and applied through a
-// fold expression, so every register index is a literal (no local-memory array).
-constexpr int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
-
-template <typename F>
-constexpr void odd_even_comparators(int N, F&& f) {
-    const int P = next_pow2(N);
-    for (int p = 1; p < P; p <<= 1)
-        for (int k = p; k >= 1; k >>= 1)
-            for (int j = k % p; j + k < P; j += 2 * k)
-                for (int i = 0; i < k; ++i)
-                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p) && i + j + k < N) f(i + j, i + j + k);
-}
-
-constexpr int odd_even_count(int N) {
-    int n = 0;
-    odd_even_comparators(N, [&](int, int) { ++n; });
-    return n;
-}
-
-template <int N>
-struct OddEvenNet {
-    static constexpr int kMax = odd_even_count(N);
-    short lo[kMax], hi[kMax];
-    int n;
-    constexpr OddEvenNet() : lo{}, hi{}, n(0) {
-        odd_even_comparators(N, [&](int a, int b) { lo[n] = (short)a; hi[n] = (short)b; ++n; });
-    }
-};
-
-template <int N, size_t... I>
-__device__ __forceinline__ void sort_network_impl(unsigned (&r)[N], std::index_sequence<I...>) {
-    constexpr OddEvenNet<N> net{};
-    static_assert(net.n == OddEvenNet<N>::kMax, "comparator count");
-    ((void)([&] {
-         const unsigned x = r[net.lo[I]], y = r[net.hi[I]];
-         r[net.lo[I]] = min(x, y);
-         r[net.hi[I]] = max(x, y);
-     }()),
-     ...);
-}
-
-template <int N>
-__device__ __forceinline__ void sort_network(unsigned (&r)[N]) {
-    sort_network_impl<N>(r, std::make_index_sequence<OddEvenNet<N>::kMax>{});
-}
 
 // K smallest keys of a segment of c <= N hits, ascending, through 32-bit composites
 // ((len bits - smallest len bits of the segment) << 6 | slot): exact as long as the segment's lens span less
@@ -126,21 +78,6 @@ __device__ __forceinline__ bool select_network(const uint2* __restrict__ hs, int
     return true;
 }
 
-// bitonic merge network on 32 registers (5 stages of 16 compare-exchanges): sorts a bitonic sequence ascending
-template <size_t... I>
-__device__ __forceinline__ void bitonic_merge32_impl(unsigned (&r)[32], std::index_sequence<I...>) {
-    // comparator I of stage I / 16 (stride 16 >> stage): the I % 16-th index with the stride bit clear
-    ((void)([&] {
-         constexpr int stride = 16 >> (I / 16);
-         constexpr int q = I % 16;
-         constexpr int lo = ((q / stride) * 2 * stride) + (q % stride);
-         const unsigned x = r[lo], y = r[lo + stride];
-         r[lo] = min(x, y);
-         r[lo + stride] = max(x, y);
-     }()),
-     ...);
-}
-
 // Segments of 33..64 hits: TWO adjacent lanes per pixel, 32 slots each, so that
 // the kernel needs the registers of the 32-input network only (twice the resident warps of a 64-input one, a third
 // of the code).  Each lane sorts its half; min / max against the partner's reversed half (lane 0 keeps the 32
@@ -178,7 +115,7 @@ __device__ __forceinline__ bool select_pair(const uint2* __restrict__ hs, int c,
         r[x] = sub ? max(r[x], t1) : min(r[x], t1);
         r[31 - x] = sub ? max(r[31 - x], t2) : min(r[31 - x], t2);
     }
-    bitonic_merge32_impl(r, std::make_index_sequence<80>{});
+    bitonic_merge<32>(r);
     // ranks sub*32 + i; a tie is two neighbouring ranks below c with equal len bits
     const unsigned below = __shfl_xor_sync(pair_mask, r[31], 1);      // lane 1: rank 31
     bool tie = sub && (32 < c) && ((r[0] ^ below) < 64u);
