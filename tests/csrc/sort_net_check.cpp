@@ -1,8 +1,8 @@
 // Host check of voge_b200/csrc/sort_net.h (compiled by tests/test_sort_networks_cpu.py with g++):
 //   * the odd-even networks sort (exhaustive 0/1 inputs for N = 16, random keys + 0/1 samples for N = 32, 48, 64),
 //   * the bitonic merge sorts every bitonic 0/1 sequence of 8 / 16 / 32 elements,
-//   * the lane-pair scheme of select_topk (two lanes sort 32 interleaved slots each, min / max against the
-//     partner's reversed half, bitonic merge per lane) yields the sorted 64 -- lanes simulated in lockstep,
+//   * the lane-pair scheme of select_topk (two lanes sort S = 8 / 16 / 32 interleaved slots each, min / max against
+//     the partner's reversed half, bitonic merge per lane) yields the sorted 2 S -- lanes simulated in lockstep,
 //   * fold_index == max(g, 0) % d.
 #include <algorithm>
 #include <cstdint>
@@ -51,29 +51,30 @@ static int check_bitonic() {
     return bad;
 }
 
-// select_pair (select.cu) with the two lanes of a pixel simulated in lockstep
+// select_pair<S> (select.cu) with the two lanes of a pixel simulated in lockstep
+template <int S>
 static int check_pair(std::mt19937& rng, int samples) {
     int bad = 0;
     for (int s = 0; s < samples; ++s) {
-        const int c = 33 + (int)(rng() % 32u);                 // 33..64 hits
-        unsigned keys[64], ref[64];
-        for (int j = 0; j < 64; ++j) keys[j] = j < c ? (((s & 1) ? (rng() % 50u) : (rng() >> 7)) << 6 | (unsigned)j) : 0xffffffffu;
-        for (int j = 0; j < 64; ++j) ref[j] = keys[j];
-        std::sort(ref, ref + 64);
-        unsigned L[2][32];
+        const int c = (int)(rng() % (unsigned)(2 * S + 1));    // 0 .. 2 S hits
+        unsigned keys[2 * S], ref[2 * S];
+        for (int j = 0; j < 2 * S; ++j) keys[j] = j < c ? (((s & 1) ? (rng() % 50u) : (rng() >> 7)) << 6 | (unsigned)j) : 0xffffffffu;
+        for (int j = 0; j < 2 * S; ++j) ref[j] = keys[j];
+        std::sort(ref, ref + 2 * S);
+        unsigned L[2][S];
         for (int sub = 0; sub < 2; ++sub) {
-            for (int i = 0; i < 32; ++i) L[sub][i] = keys[2 * i + sub];      // interleaved slots
-            sort_network<32>(L[sub]);
+            for (int i = 0; i < S; ++i) L[sub][i] = keys[2 * i + sub];       // interleaved slots
+            sort_network<S>(L[sub]);
         }
-        for (int x = 0; x < 16; ++x) {
+        for (int x = 0; x < S / 2; ++x) {
             // both lanes shuffle before either writes (SIMT lockstep)
-            const unsigned a1 = L[1][31 - x], a2 = L[1][x], b1 = L[0][31 - x], b2 = L[0][x];
-            L[0][x] = net_min(L[0][x], a1); L[0][31 - x] = net_min(L[0][31 - x], a2);
-            L[1][x] = net_max(L[1][x], b1); L[1][31 - x] = net_max(L[1][31 - x], b2);
+            const unsigned a1 = L[1][S - 1 - x], a2 = L[1][x], b1 = L[0][S - 1 - x], b2 = L[0][x];
+            L[0][x] = net_min(L[0][x], a1); L[0][S - 1 - x] = net_min(L[0][S - 1 - x], a2);
+            L[1][x] = net_max(L[1][x], b1); L[1][S - 1 - x] = net_max(L[1][S - 1 - x], b2);
         }
-        bitonic_merge<32>(L[0]);
-        bitonic_merge<32>(L[1]);
-        for (int i = 0; i < 32; ++i) bad += (L[0][i] != ref[i]) + (L[1][i] != ref[32 + i]);
+        bitonic_merge<S>(L[0]);
+        bitonic_merge<S>(L[1]);
+        for (int i = 0; i < S; ++i) bad += (L[0][i] != ref[i]) + (L[1][i] != ref[S + i]);
     }
     return bad;
 }
@@ -92,7 +93,7 @@ int main() {
     bad += check_sort<16>(rng, 3000) + check_sort<32>(rng, 30000) + check_sort<48>(rng, 10000) + check_sort<64>(rng, 10000);
     bad += check_sort<20>(rng, 3000) + check_sort<7>(rng, 3000);
     bad += check_bitonic<8>() + check_bitonic<16>() + check_bitonic<32>();
-    bad += check_pair(rng, 20000);
+    bad += check_pair<8>(rng, 20000) + check_pair<16>(rng, 20000) + check_pair<32>(rng, 20000);
     static_assert(odd_even_count(16) == 63 && odd_even_count(32) == 191 && odd_even_count(64) == 543, "comparator counts");
     {   // fold_index
         const int ds[] = {1, 2, 3, 7, 1000, 35947, 1000000, 999983, 1 << 20, (1 << 30) + 7, 2147483647};

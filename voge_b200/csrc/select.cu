@@ -26,73 +26,27 @@ struct SelectArgs {
     unsigned long long* stats;    // optional: [2] pixels selected with the exact 64-bit keys
 };
 
-// K smallest keys of a segment of c <= N hits, ascending, through 32-bit composites
+// The K smallest keys of a segment, ascending, are found through 32-bit composites
 // ((len bits - smallest len bits of the segment) << 6 | slot): exact as long as the segment's lens span less
-// than 2^26 float steps (8 binades) and no two hits share their len; returns false otherwise (the caller
-// then selects with the full (len, idx) keys).  Writes the (K,) index row, -1 padded.
-template <int N>
-__device__ __forceinline__ bool select_network(const uint2* __restrict__ hs, int c, int K, int pack_off,
-                                               unsigned* __restrict__ s_y, int lane, int32_t* __restrict__ o_idx) {
-    unsigned r[N];
-    unsigned omin = 0xffffffffu, omax = 0u;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        r[j] = 0xffffffffu;
-        if (j < c) {
-            // the index half of the hit is parked in shared memory ([slot][lane]: conflict-free) so that the
-            // winners' indices need no second trip to a segment that has left L1 by then
-            const uint2 h = __ldg(&hs[j]);
-            r[j] = h.x;
-            s_y[j * 32 + lane] = h.y;
-            omin = min(omin, r[j]);
-            omax = max(omax, r[j]);
-        }
-    }
-    if (c > 0 && omax - omin >= 0x3ffffffu) return false;
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-        if (j < c) r[j] = ((r[j] - omin) << 6) | (unsigned)j;
-    sort_network<N>(r);
-    bool tie = false;
-#pragma unroll
-    for (int i = 1; i < N; ++i) tie = tie || ((i < c) && ((r[i] ^ r[i - 1]) < 64u));
-    if (tie) return false;
-    const int m = min(c, K);
-    const bool vec = (K & 3) == 0;
-#pragma unroll
-    for (int i0 = 0; i0 < N; i0 += 4) {
-        if (i0 < K) {
-            int v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (i0 + j < m) ? pack_off + (int)s_y[(r[i0 + j] & 63u) * 32 + lane] : -1;
-            if (vec) {
-                *reinterpret_cast<int4*>(o_idx + i0) = make_int4(v[0], v[1], v[2], v[3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (i0 + j < K) o_idx[i0 + j] = v[j];
-            }
-        }
-    }
-    for (int k = N; k < K; ++k) o_idx[k] = -1;
-    return true;
-}
-
-// Segments of 33..64 hits: TWO adjacent lanes per pixel, 32 slots each, so that
-// the kernel needs the registers of the 32-input network only (twice the resident warps of a 64-input one, a third
-// of the code).  Each lane sorts its half; min / max against the partner's reversed half (lane 0 keeps the 32
-// smallest composites, lane 1 the 32 largest, both bitonic) and a bitonic merge per lane give the sorted 64.
-// Returns false (in both lanes) where the composites are not exact, see select_network.
+// than 2^26 float steps (8 binades) and no two hits share their len; otherwise the caller selects with the full
+// (len, idx) keys.
+// TWO adjacent lanes per pixel, S slots each (segments of up to 2 S hits; S = 8 / 16 / 32 by the longest segment
+// of the warp): the kernel needs the registers of the 32-input network only (twice the resident warps of a
+// 64-input one, a third of the code), and the two lanes load interleaved slots (lane `sub` takes slots
+// 2 i + sub), so the pair's two 8-byte loads of one instruction are adjacent -- one L1 wavefront instead of two.
+// Each lane sorts its half; min / max against the partner's reversed half (lane 0 keeps the S smallest
+// composites, lane 1 the S largest, both bitonic) and a bitonic merge per lane give the sorted 2 S
+// (tests/csrc/sort_net_check.cpp replays the scheme on the CPU).  Returns false (in both lanes) where the
+// composites are not exact, see select_network.
+template <int S>
 __device__ __forceinline__ bool select_pair(const uint2* __restrict__ hs, int c, int K, int pack_off, int sub,
                                             unsigned pair_mask, unsigned* __restrict__ s_y, int lane,
                                             int32_t* __restrict__ o_idx) {
-    unsigned r[32];
+    unsigned r[S];
     unsigned omin = 0xffffffffu, omax = 0u;
-    const int j0 = sub * 32;                 // first RANK of this lane after the merge
-    // slots are interleaved between the two lanes (lane `sub` loads slots 2 i + sub): the pair's two 8-byte loads
-    // of one instruction are adjacent, i.e. one L1 wavefront instead of two
+    const int j0 = sub * S;                  // first RANK of this lane after the merge
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < S; ++i) {
         r[i] = 0xffffffffu;
         if (2 * i + sub < c) {
             const uint2 h = __ldg(&hs[2 * i + sub]);
@@ -106,28 +60,28 @@ __device__ __forceinline__ bool select_pair(const uint2* __restrict__ hs, int c,
     omax = max(omax, __shfl_xor_sync(pair_mask, omax, 1));
     if (c > 0 && omax - omin >= 0x3ffffffu) return false;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
+    for (int i = 0; i < S; ++i)
         if (2 * i + sub < c) r[i] = ((r[i] - omin) << 6) | (unsigned)(2 * i + sub);
-    sort_network<32>(r);
+    sort_network<S>(r);
 #pragma unroll
-    for (int x = 0; x < 16; ++x) {
-        const unsigned t1 = __shfl_xor_sync(pair_mask, r[31 - x], 1), t2 = __shfl_xor_sync(pair_mask, r[x], 1);
+    for (int x = 0; x < S / 2; ++x) {
+        const unsigned t1 = __shfl_xor_sync(pair_mask, r[S - 1 - x], 1), t2 = __shfl_xor_sync(pair_mask, r[x], 1);
         r[x] = sub ? max(r[x], t1) : min(r[x], t1);
-        r[31 - x] = sub ? max(r[31 - x], t2) : min(r[31 - x], t2);
+        r[S - 1 - x] = sub ? max(r[S - 1 - x], t2) : min(r[S - 1 - x], t2);
     }
-    bitonic_merge<32>(r);
-    // ranks sub*32 + i; a tie is two neighbouring ranks below c with equal len bits
-    const unsigned below = __shfl_xor_sync(pair_mask, r[31], 1);      // lane 1: rank 31
-    bool tie = sub && (32 < c) && ((r[0] ^ below) < 64u);
+    bitonic_merge<S>(r);
+    // ranks sub*S + i; a tie is two neighbouring ranks below c with equal len bits
+    const unsigned below = __shfl_xor_sync(pair_mask, r[S - 1], 1);   // lane 1: rank S - 1
+    bool tie = sub && (S < c) && ((r[0] ^ below) < 64u);
 #pragma unroll
-    for (int i = 1; i < 32; ++i) tie = tie || ((j0 + i < c) && ((r[i] ^ r[i - 1]) < 64u));
+    for (int i = 1; i < S; ++i) tie = tie || ((j0 + i < c) && ((r[i] ^ r[i - 1]) < 64u));
     tie = __shfl_xor_sync(pair_mask, (int)tie, 1) || tie;
     if (tie) return false;
     __syncwarp(pair_mask);                                      // the partner's index column is read below
     const int m = min(c, K);
     const bool vec = (K & 3) == 0;
 #pragma unroll
-    for (int i0 = 0; i0 < 32; i0 += 4) {
+    for (int i0 = 0; i0 < S; i0 += 4) {
         if (j0 + i0 < K) {
             int v[4];
 #pragma unroll
@@ -144,7 +98,7 @@ __device__ __forceinline__ bool select_pair(const uint2* __restrict__ hs, int c,
             }
         }
     }
-    for (int k = 64 + sub; k < K; k += 2) o_idx[k] = -1;
+    for (int k = 2 * S + sub; k < K; k += 2) o_idx[k] = -1;
     return true;
 }
 
@@ -253,12 +207,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) select_topk_kernel(const Select
         wmax = __reduce_max_sync(0xffffffffu, me.c);
         if (me.live) {
             a.out_valid[me.ray] = min(me.c, a.K);
-            int32_t* o_idx = a.out_idx + me.ray * a.K;
-            if (wmax <= 16) done = select_network<16>(me.hs, me.c, a.K, pack_off, s_y, lane, o_idx);
-            else if (wmax <= 32) done = select_network<32>(me.hs, me.c, a.K, pack_off, s_y, lane, o_idx);
+            if (wmax == 0) {              // no hit in any pixel of the warp: padding only
+                int32_t* o = a.out_idx + me.ray * a.K;
+                if ((a.K & 3) == 0) {
+                    for (int k = 0; k < a.K; k += 4) *reinterpret_cast<int4*>(o + k) = make_int4(-1, -1, -1, -1);
+                } else {
+                    for (int k = 0; k < a.K; ++k) o[k] = -1;
+                }
+            }
         }
     }
-    if (wmax > 32) {
+    if (wmax == 0) return;
+    {
         // two lanes per pixel, 16 pixels per pass; pixels with more than 64 hits go to the exact selection
         const int sub = lane & 1;
         const unsigned pair_mask = 3u << (lane & 30);
@@ -267,7 +227,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) select_topk_kernel(const Select
         for (int pass = 0; pass < 2; ++pass) {
             const SelPix px = select_pixel<TNT>(a, tile_id, ti0 + pass * 16 + (lane >> 1));
             bool ok = true;
-            if (px.live) ok = px.c <= 64 && select_pair(px.hs, px.c, a.K, pack_off, sub, pair_mask, s_y, lane, a.out_idx + px.ray * a.K);
+            if (px.live) {
+                int32_t* o_idx = a.out_idx + px.ray * a.K;
+                if (wmax <= 16) ok = select_pair<8>(px.hs, px.c, a.K, pack_off, sub, pair_mask, s_y, lane, o_idx);
+                else if (wmax <= 32) ok = select_pair<16>(px.hs, px.c, a.K, pack_off, sub, pair_mask, s_y, lane, o_idx);
+                else ok = px.c <= 64 && select_pair<32>(px.hs, px.c, a.K, pack_off, sub, pair_mask, s_y, lane, o_idx);
+            }
             failed[pass] = __ballot_sync(0xffffffffu, !ok);
             __syncwarp();                                        // pass 1 overwrites the index columns
         }
