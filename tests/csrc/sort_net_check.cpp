@@ -79,6 +79,51 @@ static int check_pair(std::mt19937& rng, int samples) {
     return bad;
 }
 
+// Four lanes per pixel (not in the kernel yet: the next step of DESIGN.md section 8): S slots per lane, slot 4 i + q
+// in lane q.  Round 1 merges lanes (0,1) and (2,3) as in select_pair; round 2 takes min / max against the reversed
+// sequence of the other pair (partner lane q ^ 3), then one cross-lane compare-exchange stage inside each pair
+// (partner q ^ 1, same register) and a bitonic merge per lane.  Lane q ends with ranks q S .. q S + S - 1.
+template <int S>
+static int check_quad(std::mt19937& rng, int samples) {
+    int bad = 0;
+    for (int s = 0; s < samples; ++s) {
+        const int c = (int)(rng() % (unsigned)(4 * S + 1));
+        unsigned keys[4 * S], ref[4 * S];
+        for (int j = 0; j < 4 * S; ++j) keys[j] = j < c ? (((s & 1) ? (rng() % 50u) : (rng() >> 8)) << 7 | (unsigned)j) : 0xffffffffu;
+        for (int j = 0; j < 4 * S; ++j) ref[j] = keys[j];
+        std::sort(ref, ref + 4 * S);
+        unsigned L[4][S], T[4][S];
+        for (int q = 0; q < 4; ++q) {
+            for (int i = 0; i < S; ++i) L[q][i] = keys[4 * i + q];
+            sort_network<S>(L[q]);
+        }
+        auto reversed_exchange = [&](int xor_mask, int max_bit) {          // lockstep: read all, then write all
+            for (int q = 0; q < 4; ++q)
+                for (int x = 0; x < S; ++x) {
+                    const unsigned other = L[q ^ xor_mask][S - 1 - x];
+                    T[q][x] = (q & max_bit) ? net_max(L[q][x], other) : net_min(L[q][x], other);
+                }
+            for (int q = 0; q < 4; ++q)
+                for (int x = 0; x < S; ++x) L[q][x] = T[q][x];
+        };
+        reversed_exchange(1, 1);
+        for (int q = 0; q < 4; ++q) bitonic_merge<S>(L[q]);
+        reversed_exchange(3, 2);
+        for (int q = 0; q < 4; ++q)
+            for (int x = 0; x < S; ++x) {
+                const unsigned other = L[q ^ 1][x];
+                T[q][x] = (q & 1) ? net_max(L[q][x], other) : net_min(L[q][x], other);
+            }
+        for (int q = 0; q < 4; ++q) {
+            for (int x = 0; x < S; ++x) L[q][x] = T[q][x];
+            bitonic_merge<S>(L[q]);
+        }
+        for (int q = 0; q < 4; ++q)
+            for (int i = 0; i < S; ++i) bad += L[q][i] != ref[q * S + i];
+    }
+    return bad;
+}
+
 int main() {
     std::mt19937 rng(1234);
     int bad = 0;
@@ -94,6 +139,7 @@ int main() {
     bad += check_sort<20>(rng, 3000) + check_sort<7>(rng, 3000);
     bad += check_bitonic<8>() + check_bitonic<16>() + check_bitonic<32>();
     bad += check_pair<8>(rng, 20000) + check_pair<16>(rng, 20000) + check_pair<32>(rng, 20000);
+    bad += check_quad<8>(rng, 10000) + check_quad<16>(rng, 10000);
     static_assert(odd_even_count(16) == 63 && odd_even_count(32) == 191 && odd_even_count(64) == 543, "comparator counts");
     {   // fold_index
         const int ds[] = {1, 2, 3, 7, 1000, 35947, 1000000, 999983, 1 << 20, (1 << 30) + 7, 2147483647};
