@@ -163,11 +163,28 @@ int voge_find_nearest_k(const float* len_in, const float* act_in, const float* d
 
 /* ---- fused renderer path (GaussianRenderer.forward, reference VoGE/Renderer.py:102-150) ------
  * Same results as rasterize_coarse -> ray_trace_voge_fine -> aggregation on the renderer's own
- * call pattern, without the per-view (B,N,.) copies, the (B,BH,BW,M) bin table or the (R,K,K)
- * blend tensors.  verts (N,3); sigmas compact: sigma_kind 1 = (N,), 3 = (N,3), 9 = (N,3,3)
- * (inverse covariances, S = 2*sigma, Renderer.py:137); cameras as R (B,3,3) row-vector
- * convention, T (B,3), focal (B,2), principal (B,2) in pixels; origins (B,3) = ray origins;
- * rays (B,H,W,3) unit directions.
+ * call pattern, without the per-view (B,N,.) copies, the (B,BH,BW,M) bin table, the (R,K,K)
+ * blend tensors or (for the closed-form camera) the (B,H,W,3) rays.
+ *
+ * Parameters.  verts (N,3); sigmas compact: sigma_kind 1 = (N,), 3 = (N,3), 9 = (N,3,3);
+ * sigma_mode says how `sigmas` maps to the matrix P of S = 2 P (Renderer.py:134-137):
+ *   0  P = sigmas (inverse covariances, inverse_sigma = False)
+ *   1  P = inverse(sigmas) (covariances, inverse_sigma = True: `2 * torch.inverse(sigmas)`)
+ *   2  P = tril(sigmas) tril(sigmas)^T (Cholesky factor: `to_sym`, demo/EfficientCuboidViaOptimization.py:17-18;
+ *      sigma_kind 9 only)
+ * voge_pack_gaussians writes one 16-byte-aligned record per Gaussian, out (N, 4 | 8 | 12) floats for
+ * sigma_kind 1 | 3 | 9 = [x,y,z,S00] | [x,y,z,S00, S11,S22,0,0] | [x,y,z, S00..S22]; every other kernel of
+ * the path reads these records (`gauss`).  voge_unpack_gradients is the matching gradient epilogue: it
+ * splits the packed gradient records of voge_render_backward_fused into grad_verts (N,3) and grad_sigmas
+ * (shaped like sigmas, NULL to skip) and applies the chain rule of sigma_mode (mode 1: -P^T G P^T; mode 2:
+ * tril((G + G^T) tril(L))) -- replaces autograd through torch.inverse / to_sym.
+ *
+ * Cameras.  R (B,3,3) row-vector convention X_view = X_world R + T, T (B,3), focal (B,2), principal (B,2) in
+ * pixels; origins (B,3) = ray origins.  Rays: either a (B,H,W,3) tensor of unit directions (user-supplied
+ * rays, pytorch3d cameras), or rays = NULL and cam (B,16) = [R row-major (9), fx, fy, px, py, 0,0,0]: the
+ * kernels then generate d = R normalize(-(x+.5-px)/fx, -(y+.5-py)/fy, 1) per pixel in registers
+ * (Renderer.py:124-128; ONE device function, csrc/render_core.cuh: gen_ray).  voge_generate_rays
+ * materialises exactly those rays, (B,H,W,3), for the op-by-op entry points and the oracle.
  *
  * voge_bin_count: per (view, Gaussian) tile rectangle = [reference coarse-bin test of
  *   RayTracing.py:33-57 + rasterize_coarse.cu:20-42,:116-130 at `bin_size` px, if use_ref_bins]
@@ -176,35 +193,25 @@ int voge_find_nearest_k(const float* len_in, const float* act_in, const float* d
  *   empty if x0 > x1); tile_counts (B,TY,TX,S) int32, S = voge_bin_sub() counters per tile (entry n is counted in
  *   counter n % S: L2 serialises atomics on one address), must be ZEROED by the caller; tile_items (optional, same
  *   shape, ZEROED) accumulates the rectangle area inside each tile (the tile's number of ITEMS, trace.cu).
+ *   flags: bit 0 = use the dense-S rounding constants for every Gaussian (default: count the non-zero entries
+ *   of S, DESIGN.md "culling margins").
  * voge_bin_fill: scatters Gaussian indices into tile_list using tile_offsets (B*TY*TX*S+1, int64,
  *   exclusive scan of tile_counts; the S segments of a tile are adjacent); cursor (B*TY*TX*S) int32 must be
- *   ZEROED by the caller.
- * voge_render_forward: fragments.  out_idx (B,H,W,K) packed b*N+n / -1, out_weight, out_len
- *   (1e10 padded), out_valid (B,H,W) int64; out_act/out_dsd optional (NULL to skip);
- *   rects = the (B,N,2) rectangles of voge_bin_count (pixel units);
- *   stats optional 4 x uint64 (pairs evaluated, pairs refined, overflowed pixels, -), zeroed by the caller.
- * voge_render_backward: d(len,act,dsd) (B,H,W,K) -> grad_verts (N,3), grad_sigmas (compact, NULL to
- *   skip); both ZEROED by the caller and accumulated into.  Only the first valid_num[r] slots of
- *   idx are read (merge_final rewrites -1 -> 0 in place, Aggregation.py:131).                                  */
+ *   ZEROED by the caller.                                                                                  */
 int voge_bin_sub(void);   /* counters / list segments per tile (S below) */
-int voge_bin_count(const float* verts, const float* sigmas, int sigma_kind, const float* R,
+int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int sigma_mode, int N,
+                        float* out, voge_stream_t stream);
+int voge_unpack_gradients(const float* grad_packed, const float* gauss, const float* sigmas, int sigma_kind,
+                          int sigma_mode, int N, float* grad_verts, float* grad_sigmas, voge_stream_t stream);
+int voge_generate_rays(const float* cam, int B, int H, int W, float* rays, voge_stream_t stream);
+int voge_bin_count(const float* gauss, int sigma_kind, const float* R,
                    const float* T, const float* origins, const float* focal, const float* principal,
                    int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins,
-                   int bin_size, int tile, uint32_t* rects, int32_t* tile_counts, int32_t* tile_items,
+                   int bin_size, int tile, int flags, uint32_t* rects, int32_t* tile_counts, int32_t* tile_items,
                    voge_stream_t stream);
 int voge_bin_fill(const uint32_t* rects, const int64_t* tile_offsets, int32_t* cursor, int B, int N,
                   int H, int W, int tile, int32_t* tile_list, voge_stream_t stream);
-int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind,
-                        const float* origins, const float* rays, const int64_t* tile_offsets,
-                        const int32_t* tile_list, const uint32_t* rects, float thr_act, float absorptivity,
-                        int B, int N, int H, int W, int K, int tile,
-                        int32_t* out_idx, float* out_weight, float* out_len, int64_t* out_valid,
-                        float* out_act, float* out_dsd, uint64_t* stats, voge_stream_t stream);
 /* ---- forward pipeline of the fused renderer (csrc/trace.cu, csrc/select.cu) ----------------------------
- * Same fragments as voge_render_forward, in three launches and without any per-pixel capacity limit.
- * These kernels (and voge_render_backward_fused) read the Gaussians from packed 16-byte-aligned records
- * written by voge_pack_gaussians: out (N, 4 | 8 | 12) floats for sigma_kind 1 | 3 | 9 =
- * [x,y,z,2s] | [x,y,z,2s0, 2s1,2s2,0,0] | [x,y,z, 2S00..2S22] (S = 2 sigma, Renderer.py:137):
  *   voge_trace_hits: every item (tile-list entry x pixel of its rectangle inside the tile) is evaluated with
  *       the reference's arithmetic (ray_trace_voge.cu:188-193); hits (act < thr_act, len < 1e10, :197) are
  *       appended as (orderable len bits, local Gaussian index) to the pixel's segment.  The segments of a
@@ -217,16 +224,14 @@ int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind,
  *   voge_blend_weights: exact re-evaluation of the first valid[r] slots of idx, blend weights
  *       (Aggregation.py:30-107) -> out_weight, out_len (1e10 padded), optional out_act / out_dsd.
  *   A batch may be processed in groups of views to bound the scratch (8 bytes per item): pass the group's
- *   slices of rays / origins / rects / offsets / outputs, view_base = index of its first view (packed indices
+ *   slices of rays / cam / origins / rects / offsets / outputs, view_base = index of its first view (packed indices
  *   are (view_base + b)*N + n) and item_base = tile_item_offsets value of its first tile (subtracted, so
  *   that `hits` only needs the group's items).
  *   stats optional 4 x uint64 ([0] items evaluated, [2] pixels selected with the exact 64-bit keys), zeroed
  *   by the caller.                                                                                         */
 int voge_trace_threads(int tile);
-int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int N, float* out,
-                        voge_stream_t stream);
 int voge_trace_hits(const float* gauss, int sigma_kind, const float* origins,
-                    const float* rays, const int64_t* tile_offsets, const int32_t* tile_list,
+                    const float* rays, const float* cam, const int64_t* tile_offsets, const int32_t* tile_list,
                     const uint32_t* rects, const int64_t* tile_item_offsets, int64_t item_base, float thr_act,
                     int B, int N, int H, int W, int tile, int32_t* counts, int64_t* seg_base, uint32_t* hits,
                     uint64_t* stats, voge_stream_t stream);
@@ -234,35 +239,32 @@ int voge_select_topk(const int32_t* counts, const int64_t* seg_base, const uint3
                      int view_base, int B, int N, int H, int W, int K, int tile,
                      int32_t* out_idx, int64_t* out_valid, uint64_t* stats, voge_stream_t stream);
 int voge_blend_weights(const float* gauss, int sigma_kind, const float* origins,
-                       const float* rays, const int32_t* idx, const int64_t* valid, float absorptivity,
-                       int view_base, int B, int N, int H, int W, int K, float* out_weight, float* out_len,
-                       float* out_act, float* out_dsd, voge_stream_t stream);
-int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind,
-                         const float* origins, const float* rays, const int32_t* idx,
-                         const int64_t* valid_num,
-                         const float* grad_len, const float* grad_act, const float* grad_dsd,
-                         int B, int N, int H, int W, int K,
-                         float* grad_verts, float* grad_sigmas, voge_stream_t stream);
+                       const float* rays, const float* cam, const int32_t* idx, const int64_t* valid,
+                       float absorptivity, int view_base, int B, int N, int H, int W, int K, float* out_weight,
+                       float* out_len, float* out_act, float* out_dsd, voge_stream_t stream);
 
-/* Fused backward of the renderer: d(weight) (B,H,W,K) and optionally d(hit length) -> grad_verts,
- * grad_sigmas.  Recomputes the hits from idx (first valid_num[r] slots) instead of reading saved
- * act/dsd, differentiates the blend analytically (Aggregation.py:30-79) and applies the chain rule of
- * ray_trace_voge.cu:324-330 in ONE kernel.  grad_packed is ONE buffer of per-Gaussian records
- * [d verts(3) | d sigma] padded to float4 units so that 16-byte vector reductions can be used:
- * kind 1: (N,4) = [gx,gy,gz,gsigma]; kind 3: (N,8) = [gx,gy,gz,0,gs0,gs1,gs2,0];
- * kind 9: (N,12) = [gx,gy,gz,gs00..gs22].  ZEROED by the caller, accumulated into.
+/* Fused backward of the renderer: d(weight) (B,H,W,K) and optionally d(hit length) -> packed parameter
+ * gradients.  Recomputes the hits from idx (first valid_num[r] slots; merge_final rewrites -1 -> 0 in place,
+ * Aggregation.py:131) instead of reading saved act/dsd, differentiates the blend analytically
+ * (Aggregation.py:30-79) and applies the chain rule of ray_trace_voge.cu:324-330 in ONE kernel.  grad_packed is
+ * ONE buffer of per-Gaussian records [d verts(3) | d P] padded to float4 units so that 16-byte vector reductions
+ * can be used: kind 1: (N,4) = [gx,gy,gz,gP]; kind 3: (N,8) = [gx,gy,gz,0,gP0,gP1,gP2,0];
+ * kind 9: (N,12) = [gx,gy,gz,gP00..gP22].  ZEROED by the caller, accumulated into; voge_unpack_gradients
+ * turns it into the caller's tensors.
  * weight: optional (B,H,W,K) = the forward's out_weight (an output the caller holds anyway); when given the
  * kernel skips re-evaluating the blend weights (NULL: recompute them from the hits).
- * Camera gradients (pose optimisation, reference grad_rays of ray_trace_voge.cu:283-332): grad_rays (B,H,W,3),
- * optional, written in full; grad_origins (B,3), optional, ZEROED by the caller (= -sum of d/d(mu') over the
- * view's hits, since mu' = verts - origin, Renderer.py:130).                                        */
+ * Camera gradients (pose optimisation, reference grad_rays of ray_trace_voge.cu:283-332): grad_origins (B,3),
+ * optional, ZEROED by the caller (= -sum of d/d(mu') over the view's hits, since mu' = verts - origin,
+ * Renderer.py:130); with a rays tensor: grad_rays (B,H,W,3), optional, written in full; with generated rays
+ * (rays = NULL): grad_cam (B,16), optional, ZEROED by the caller = d/d(cam record) [dR (9), dfx, dfy, dpx, dpy],
+ * the ray generator's chain rule reduced per view inside the kernel.                                       */
 int voge_render_backward_fused(const float* gauss, int sigma_kind,
                                const float* origins, const float* rays, const int32_t* idx,
                                const int64_t* valid_num, const float* grad_weight, const float* weight,
                                const float* grad_len_out, float absorptivity,
                                int B, int N, int H, int W, int K,
                                float* grad_packed, int need_sigma, float* grad_rays, float* grad_origins,
-                               voge_stream_t stream);
+                               const float* cam, float* grad_cam, voge_stream_t stream);
 
 #ifdef __cplusplus
 }

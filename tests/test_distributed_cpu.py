@@ -48,6 +48,23 @@ def _worker(rank, world, port, out):
     ok = torch.allclose(verts.grad, total * verts.detach()) and torch.allclose(sig.grad, total * sig.detach())
     ok = ok and float(col.grad.abs().sum()) == 0.0
     ok = ok and max_over_ranks(float(rank)) == float(world - 1)
+    # persistent bucket: .grad tensors alias one flat buffer, autograd accumulates in place over several
+    # backward calls (chunks of views), one in-place all-reduce, zero() between steps
+    from voge_b200.distributed import GradientBucket
+    a = torch.nn.Parameter(torch.ones(4, 3))
+    b = torch.nn.Parameter(torch.ones(5))
+    bucket = GradientBucket([a, b])
+    for step in range(2):
+        bucket.zero()
+        for v in range(first, first + count):          # one backward per view of this rank
+            ((v + 1) * (a.sum() + 2 * b.sum())).backward()
+        ok = ok and bucket.attached() and a.grad.data_ptr() == bucket.flat.data_ptr()
+        bucket.allreduce()
+        ok = ok and torch.allclose(a.grad, torch.full((4, 3), float(total))) and torch.allclose(b.grad, torch.full((5,), 2.0 * total))
+    bucket.allreduce(average=True)
+    ok = ok and torch.allclose(a.grad, torch.full((4, 3), float(total)))      # the average of equal buffers
+    a.grad = None
+    ok = ok and not bucket.attached()
     barrier()
     out[rank] = ok
     dist.destroy_process_group()

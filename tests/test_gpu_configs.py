@@ -7,11 +7,13 @@ import numpy as np
 import pytest
 import torch
 
+from scene_utils import ambiguous_bbox_gaussians, check_index_rows
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _render_and_check(oracle, verts, sig, R, T, focal, hw, K, M, frac=0.9995):
+def _render_and_check(oracle, verts, sig, R, T, focal, hw, K, M, max_differing_frac=5e-4):
     from voge_b200.cameras import PerspectiveCameras
     from voge_b200.Meshes import GaussianMeshes
     from voge_b200.Renderer import GaussianRenderer, GaussianRenderSettings
@@ -26,11 +28,19 @@ def _render_and_check(oracle, verts, sig, R, T, focal, hw, K, M, frac=0.9995):
     o = oracle.render_reference_cpu(verts, sig, R, T, focal, (W / 2, H / 2), hw, K=K, max_points_per_bin=M, rays=rays,
                                     origin=origins)
     idx = frag.vert_index.cpu()
-    same = idx == o["idx"]
-    # candidate sets can differ from the oracle's only for a Gaussian whose bbox edge is within an ulp of a
-    # bin edge (bbox maths is fp32 PyTorch in the oracle, closed form in the kernel)
-    assert same.float().mean() > frac
-    rows = same.all(dim=-1)
+    # Exact index parity: the top-K lists equal the oracle's on every pixel, except where a Gaussian's reference
+    # bbox edge is within 2e-3 px of a coarse-bin edge (its bin membership is then not decided in fp32: bbox maths
+    # is a PyTorch transcription in the oracle, a closed form in the kernel) -- counted, printed, and every
+    # differing row must contain such a Gaussian in the symmetric difference of the two lists.
+    from voge_b200.Aggregation import expend_sigma
+    bs = oracle.default_bin_size(hw)
+    if M == -1:
+        amb = torch.zeros((R.shape[0], verts.shape[0]), dtype=torch.bool)
+    else:
+        amb = ambiguous_bbox_gaussians(R, T, focal, (W / 2, H / 2), hw, verts, 2 * expend_sigma(sig), 0.01, bs)
+    rows, stats = check_index_rows(idx, o["idx"], amb, verts.shape[0], label="%dx%d K=%d" % (H, W, K))
+    assert stats["unexplained"] == 0
+    assert stats["differing"] <= max_differing_frac * stats["rows"]
     assert torch.equal(frag.vert_hit_length.cpu()[rows], o["len"][rows])
     assert torch.equal(frag.valid_num.cpu()[rows], o["valid_num"][rows])
     assert torch.allclose(frag.vert_weight.cpu()[rows], o["weight"][rows], rtol=1e-5, atol=1e-7)
@@ -60,7 +70,7 @@ def test_c3_shape_fitting_no_coarse(oracle):
     sig = torch.full((2562,), 400.0)
     R, T = oracle.look_at_view(torch.full((5,), 2.7), torch.tensor([0.0, 20.0, -15.0, 40.0, 5.0]),
                                torch.tensor([0.0, 72.0, 144.0, 216.0, 288.0]))
-    _render_and_check(oracle, verts, sig, R, T, 150.0, (128, 128), K=25, M=-1, frac=0.99999)
+    _render_and_check(oracle, verts, sig, R, T, 150.0, (128, 128), K=25, M=-1, max_differing_frac=0.0)
 
 
 def test_c4_two_cuboids_k60(oracle):
@@ -111,14 +121,9 @@ def test_c5_full_size_band_and_properties(oracle):
     srt = torch.sort(torch.where(ok, idx, -1 - k.expand_as(idx)), dim=-1).values
     assert bool((srt[..., 1:] != srt[..., :-1]).all())                      # a Gaussian hits a pixel at most once
     assert bool((w >= 0).all()) and bool((w <= math.exp(0.5) + 1e-6).all())
-    # the one-launch kernel gives the same fragments
     rays, origins = renderer._rays((HW, HW))
-    Rm, Tm, focal, principal = camera_params(cams, (HW, HW))
     thr_act = -math.log(0.01 + 1e-10)
-    bs = default_bin_size((HW, HW)); tile = choose_tile(bs, K, True)
-    off, tl, rects, _ = _C.bin_views(gm.verts, gm.sigmas, Rm, Tm, origins, focal, principal, (HW, HW), 0.01, thr_act, True, bs, tile)
-    s = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile, need_act=False)
-    assert torch.equal(s[0], idx) and torch.equal(s[2], ln) and torch.equal(s[3], valid)
+    bs = default_bin_size((HW, HW))
     # a band of rows against the CPU oracle: reference coarse bins (bin 32) + fine kernel restatement
     rows, y0 = 64, 480
     mus = (verts[None] - origins.cpu()[:, None])
@@ -132,7 +137,7 @@ def test_c5_full_size_band_and_properties(oracle):
     o_idx, o_len, _, _ = (torch.from_numpy(a) for a in oracle.ray_trace_fine(mus.reshape(-1, 3), isg.reshape(-1, 3, 3), rays_sub,
                                                                              bp_sub, thr_act, bs, K))
     g_idx, g_len = idx[:, y0:y0 + rows].cpu(), ln[:, y0:y0 + rows].cpu()
-    same = (g_idx == o_idx).all(-1)
-    # candidate sets can differ only for a Gaussian whose bbox edge is within an ulp of a bin edge
-    assert same.float().mean() > 0.9995
+    amb = ambiguous_bbox_gaussians(R, T, 900.0, (HW / 2, HW / 2), (HW, HW), verts, 2 * sig, 0.01, bs)
+    same, stats = check_index_rows(g_idx, o_idx, amb, N, label="C5 band 1024 K=20")
+    assert stats["unexplained"] == 0 and stats["differing"] <= 5e-4 * stats["rows"]
     assert torch.equal(g_len[same], o_len[same])

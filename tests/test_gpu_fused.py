@@ -1,5 +1,5 @@
-"""GPU tests of the fused renderer path (voge_bin_count / voge_bin_fill / voge_render_forward /
-voge_render_backward) through the public API: it must reproduce the op-by-op chain
+"""GPU tests of the fused renderer path (voge_pack_gaussians / voge_bin_count / voge_bin_fill / voge_trace_hits /
+voge_select_topk / voge_blend_weights / voge_render_backward_fused / voge_unpack_gradients) through the public API: it must reproduce the op-by-op chain
 (ray_tracing -> aggregation), which test_gpu_parity.py pins to the reference kernels, bit for bit,
 and the CPU oracle run on the same rays."""
 import math
@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from scene_utils import small_scene
+from scene_utils import ambiguous_bbox_gaussians, check_index_rows, small_scene
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -65,11 +65,13 @@ def test_fused_tile_shapes_and_oracle(oracle, hw, K):
     rays, origins = renderer._rays(hw)
     o = oracle.render_reference_cpu(sc["verts"], sc["sigmas"], sc["R"], sc["T"], sc["focal"], sc["principal"], hw, K=K,
                                     max_points_per_bin=500, rays=rays, origin=origins)
-    # candidate sets can differ from the oracle's only for a Gaussian whose bbox edge is within an
-    # ulp of a bin edge (bbox maths is fp32 PyTorch in the oracle, closed form in the kernel)
-    same = frag.vert_index.cpu() == o["idx"]
-    assert same.float().mean() > 0.9995
-    rows = same.all(dim=-1)
+    # candidate sets can differ from the oracle's only for a Gaussian whose bbox edge is within rounding of a
+    # bin edge (bbox maths is fp32 PyTorch in the oracle, closed form in the kernel): exact assertion elsewhere
+    from voge_b200.RayTracing import default_bin_size
+    amb = ambiguous_bbox_gaussians(sc["R"], sc["T"], sc["focal"], sc["principal"], hw, sc["verts"], 2 * sc["sigmas"], 0.01,
+                                   default_bin_size(hw))
+    rows, stats = check_index_rows(frag.vert_index.cpu(), o["idx"], amb, sc["verts"].shape[0], label="%dx%d K=%d" % (hw + (K,)))
+    assert stats["unexplained"] == 0 and stats["differing"] <= 2e-3 * stats["rows"]
     assert torch.equal(frag.vert_hit_length.cpu()[rows], o["len"][rows])
     assert torch.allclose(frag.vert_weight.cpu()[rows], o["weight"][rows], rtol=1e-5, atol=1e-7)
 
@@ -176,7 +178,9 @@ def test_fused_edge_cases(oracle):
     covp = cov.to(DEV).requires_grad_(True)
     gm3 = GaussianMeshesNaive(sc["verts"].to(DEV), covp)
     a3, b3 = _both(r3, gm3)
-    assert torch.equal(a3.vert_index, b3.vert_index) and (a3.vert_index >= 0).sum() > 200
+    # fused: adjugate inverse inside voge_pack_gaussians; op-by-op: torch.inverse (LU) -- last-bit differences of S
+    # may flip a hit that sits within rounding of the threshold
+    assert float((a3.vert_index == b3.vert_index).all(-1).float().mean()) > 0.99 and (a3.vert_index >= 0).sum() > 200
     interpolate_attr(a3, sc["colors"].to(DEV)).sum().backward()
     assert torch.isfinite(covp.grad).all() and covp.grad.abs().sum() > 0
 
@@ -233,7 +237,7 @@ def test_sampler_api_roundtrip(oracle):
 
 @pytest.mark.parametrize("K,hw", [(8, (48, 48)), (20, (64, 64)), (30, (40, 56))])
 def test_forward_pipeline_dense_ties_and_single_kernel(K, hw):
-    """trace_hits -> select_topk -> blend_weights against the one-launch kernel and the op-by-op chain on a
+    """trace_hits -> select_topk -> blend_weights against the op-by-op chain on a
     scene built to leave the sorting-network fast path: > 64 hits per pixel (exact-key selection), duplicated
     Gaussians (identical len: ties broken by index), lens spanning many binades."""
     from voge_b200 import _C
@@ -263,13 +267,14 @@ def test_forward_pipeline_dense_ties_and_single_kernel(K, hw):
     off, tl, rects, ioff = _C.bin_views(gm.verts, gm.sigmas, R, T, origins, focal, principal, hw, 0.01, thr_act, True, bs, tile)
     stats = torch.zeros(4, dtype=torch.int64, device=DEV)
     p = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile, stats=stats, item_offsets=ioff)
-    s = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile)
-    for name, x, y in zip(("idx", "weight", "len", "valid", "act", "dsd"), p, s):
-        if name == "weight":      # same maths, different summation order inside the blend (1-ulp level)
-            assert torch.allclose(x, y, rtol=1e-5, atol=1e-9, equal_nan=True)
-        else:
-            assert torch.equal(x, y), name
-    assert torch.equal(p[0], a.vert_index)
+    assert torch.equal(p[0], a.vert_index) and torch.equal(p[2], a.vert_hit_length) and torch.equal(p[3], a.valid_num)
+    # rays generated inside the kernels (cam records) == the materialised rays of voge_generate_rays
+    cam = _C.make_cam(R, focal, principal)
+    assert torch.equal(_C.generate_rays(cam, hw), rays)
+    q = _C.render_forward(gm.verts, gm.sigmas, origins, None, off, tl, rects, thr_act, 1.0, K, tile, item_offsets=ioff,
+                          cam=cam, image_size=hw)
+    for name, x, y in zip(("idx", "weight", "len", "valid", "act", "dsd"), p, q):
+        assert torch.equal(x, y), name
     # views traced one group at a time (bounded scratch) give the same fragments
     g = _C.render_forward(gm.verts, gm.sigmas, origins, rays, off, tl, rects, thr_act, 1.0, K, tile, item_offsets=ioff,
                           max_group_items=1)

@@ -20,17 +20,12 @@ colors.requires_grad_(True)
 target = torch.rand(V, HW, HW, 3, device=dev)
 
 times = {}
-def wrap(name):
-    fn = getattr(_C, name)
-    def w(*a, **k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); out = fn(*a, **k); e1.record()
+class _KT:
+    enabled = True
+    def add(self, name, e0, e1):
         times.setdefault(name, []).append((e0, e1))
-        return out
-    setattr(_C, name, w)
-for nm in ("bin_views", "render_forward", "merge_final_forward", "merge_final_backward", "render_backward_fused"):
-    if hasattr(_C, nm):
-        wrap(nm)
+from voge_b200 import _lib
+_lib.kernel_timer = _KT()          # every C-ABI call (= one kernel launch) bracketed by CUDA events
 
 for it in range(ITERS + 1):
     if it == 1:
@@ -43,6 +38,7 @@ for it in range(ITERS + 1):
     t1.record()
     gm.zero_grad(); colors.grad = None
 torch.cuda.synchronize()
+_lib.kernel_timer.enabled = False
 # device counters of the forward (one extra call outside the timing)
 with torch.no_grad():
     import math
@@ -61,15 +57,23 @@ with torch.no_grad():
     st = stats.tolist()
     print("per view: tile entries %.3fM  items %.2fM (alloc %.2fM)  exact-select pixels %d  hits %.2fM" % (
         tl.numel() / V / 1e6, st[0] / V / 1e6, ioff.total_items / V / 1e6, st[2] // V, int((out[0] >= 0).sum()) / V / 1e6))
-    if os.environ.get("XCHECK"):
-        ref = _C.render_forward(verts, sig, origins, rays, off, tl, rects, thr_act, 1.0, K, tile, need_act=False)
-        torch.cuda.synchronize()
-        for nm, x, y in zip(("idx", "weight", "len", "valid"), out, ref):
-            print("  xcheck", nm, "equal" if torch.equal(x, y) else "DIFFERENT (%d, max rel %.2e)" % (
-                int((x != y).sum()), float(((x - y).abs() / y.abs().clamp_min(1e-30)).max())))
+    if os.environ.get("TILESTATS"):
+        # hits per (Gaussian, tile): how much a per-tile Gaussian-major gradient reduction could aggregate
+        idx = out[0]
+        ys = torch.arange(HW, device=dev).view(1, HW, 1, 1)
+        xs = torch.arange(HW, device=dev).view(1, 1, HW, 1)
+        bb = torch.arange(V, device=dev).view(V, 1, 1, 1)
+        ok = idx >= 0
+        n_hits = int(ok.sum())
+        for t in (4, 8, 16):
+            tiles = (bb * ((HW + t - 1) // t) + ys // t) * ((HW + t - 1) // t) + xs // t
+            key = (tiles.expand_as(idx)[ok].long() << 32) | idx[ok].long()
+            uniq = torch.unique(key).numel()
+            print("  tile %2d: %.2f hits per (Gaussian, tile) [%d hits, %d groups]" % (t, n_hits / max(uniq, 1), n_hits, uniq))
+        del key, tiles
 tot = 0.0
 for nm, ev in times.items():
-    ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev) / V
+    ms = sum(a.elapsed_time(b) for a, b in ev) / ITERS / V
     tot += ms
     print("%-24s %.4f ms/view" % (nm, ms))
 print("sum %.4f ms/view -> %.1f Mrays/s ; last step wall %.3f ms/view" % (tot, HW * HW / tot / 1e3, t0.elapsed_time(t1) / V))

@@ -100,7 +100,19 @@ class _MergeFinal(torch.autograd.Function):
                                               background, ctx.mask_thr, ctx.idx_mod,
                                               need_attr=ctx.needs_input_grad[0], need_weight=ctx.needs_input_grad[1],
                                               attr4=ctx.attr4, out=out)
-        return g_attr, g_w, None, None, None, None, None
+        g_bg = None
+        if background is not None and ctx.needs_input_grad[4]:
+            # learnable background (rare): d out / d bg_c = (1 - mask) where min(x, 1) passes the gradient; the
+            # un-clamped composite x is rebuilt with one more gather-blend launch
+            with torch.no_grad():
+                rgb = _C.merge_final_forward(vert_attr, weight, vert_assign, valid_num, None, -1.0, ctx.idx_mod,
+                                             attr4=ctx.attr4)
+                sil = weight.sum(-1).clamp(max=1.0)
+                mask = (sil > ctx.mask_thr).to(sil.dtype) if ctx.mask_thr > 0 else sil
+                x = rgb + (1 - mask).unsqueeze(-1) * background
+                passes = (x < 1).to(x.dtype) + 0.5 * (x == 1).to(x.dtype)       # torch.min subgradient at the tie
+                g_bg = (grad_out * passes * (1 - mask).unsqueeze(-1)).reshape(-1, x.shape[-1]).sum(0)
+        return g_attr, g_w, None, None, g_bg, None, None
 
 
 def _attr_rows(vert_attr, vert_assign):

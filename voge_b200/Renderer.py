@@ -6,11 +6,15 @@ from typing import Tuple, Union
 import torch
 import torch.nn as nn
 
+from . import _C
 from .Aggregation import aggregation, expend_sigma, merge_final
-from .RayTracing import ray_tracing
-from .cameras import camera_params, generate_rays
+from .RayTracing import default_bin_size, ray_tracing
+from .cameras import PerspectiveCameras, camera_params, generate_rays
+from .fused import generate_rays as fused_generate_rays
 from .fused import render_fused
-from .RayTracing import default_bin_size
+
+
+MAX_BACKGROUND_CHANNELS = 32     # kMaxBgChannels of csrc/blend.cu
 
 
 class Fragments(object):
@@ -62,11 +66,11 @@ class Fragments(object):
 
 class GaussianRenderSettings:
     __slots__ = ['image_size', 'max_assign', 'thr_activation', 'absorptivity', 'inverse_sigma', 'principal',
-                 'max_point_per_bin']
+                 'max_point_per_bin', 'cholesky_sigma']
 
     def __init__(self, image_size: Union[int, Tuple[int, int]] = 256, max_assign: int = 20,
                  thr_activation: float = 0.01, absorptivity: float = 1, inverse_sigma: bool = False,
-                 principal=None, max_point_per_bin: Union[None, int] = None, **kwargs):
+                 principal=None, max_point_per_bin: Union[None, int] = None, cholesky_sigma: bool = False, **kwargs):
         # unknown keyword arguments are accepted and ignored, as in the reference (demos pass
         # batch_size=, principal_point=, ...)
         self.image_size = (image_size, image_size) if isinstance(image_size, int) else image_size
@@ -76,9 +80,20 @@ class GaussianRenderSettings:
         self.inverse_sigma = inverse_sigma
         self.principal = principal
         self.max_point_per_bin = max_point_per_bin
+        # extension: `sigmas` (N,3,3) are Cholesky factors L, the inverse covariance is tril(L) tril(L)^T -- the
+        # `to_sym` parameterisation of demo/EfficientCuboidViaOptimization.py:17-18, evaluated (and differentiated)
+        # inside the pack / gradient-epilogue kernels instead of by autograd
+        self.cholesky_sigma = cholesky_sigma
 
     def __getitem__(self, item):
         return getattr(self, item)
+
+
+def _setting(st, name, default=None):
+    try:
+        return st[name]
+    except (KeyError, AttributeError):
+        return default
 
 
 class GaussianRenderer(nn.Module):
@@ -97,53 +112,124 @@ class GaussianRenderer(nn.Module):
 
     # The fused CUDA path (voge_b200/fused.py) is used whenever it applies; set False to force the
     # op-by-op chain ray_tracing -> aggregation (same results, reference-shaped intermediates).
+    # Differences under misuse: the fused path has no per-bin candidate cap (max_point_per_bin only selects
+    # "reference coarse bins" vs "no coarse stage"); the op-by-op chain keeps the first M candidates of an
+    # overflowing bin (the reference drops a non-deterministic chunk, rasterize_coarse.cu:150-163).
     use_fused = True
 
-    def _fusable(self, verts, sigmas, rays, origins):
+    def _builtin_camera(self):
+        return isinstance(self.cameras, PerspectiveCameras)
+
+    def _fusable(self, verts, sigmas):
         if not (verts.is_cuda and verts.dim() == 3 and verts.shape[0] == 1 and verts.dtype == torch.float32):
             return False
-        return sigmas.dim() in (1, 2, 3)
+        if sigmas.dtype != torch.float32 or sigmas.dim() not in (1, 2, 3):
+            return False
+        if _setting(self.render_settings, 'cholesky_sigma', False) and sigmas.dim() != 3:
+            return False
+        return True
+
+    def _sigma_mode(self):
+        st = self.render_settings
+        chol, inv = bool(_setting(st, 'cholesky_sigma', False)), bool(st['inverse_sigma'])
+        if chol and inv:
+            raise ValueError("cholesky_sigma and inverse_sigma are mutually exclusive")
+        return 2 if chol else (1 if inv else 0)
+
+    def _camera_tensors(self, image_size):
+        """(R (B,3,3), T (B,3), focal (B,2), principal (B,2), origins (B,3)); origins = camera centres -T R^T,
+        plain torch ops on (B,.) tensors, differentiable."""
+        R, T, focal, principal = camera_params(self.cameras, image_size)
+        n = max(R.shape[0], T.shape[0], focal.shape[0], principal.shape[0])
+        R, T = R.expand(n, -1, -1), T.expand(n, -1)
+        focal, principal = focal.expand(n, -1), principal.expand(n, -1)
+        origins = -torch.matmul(T[:, None, :], R.transpose(1, 2))[:, 0, :]
+        return R, T, focal, principal, origins
 
     def _forward_fused(self, verts, sigmas, rays, origins):
         st = self.render_settings
         map_size = st['image_size']
-        sig = sigmas
-        if st['inverse_sigma']:
-            sig = torch.inverse(expend_sigma(sigmas))
-        R, T, focal, principal = camera_params(self.cameras, map_size)
-        n_views = rays.shape[0]
-        R, T = R.expand(n_views, -1, -1), T.expand(n_views, -1)
-        focal, principal = focal.expand(n_views, -1), principal.expand(n_views, -1)
+        R, T, focal, principal, cam_origins = self._camera_tensors(map_size)
+        if rays is None:
+            # closed-form camera: rays are generated inside the kernels from the (B,16) camera records
+            cam, origins = _C.make_cam(R, focal, principal), cam_origins
+        else:
+            cam = None
         M = st['max_point_per_bin']
-        w, idx, valid, ln = render_fused(verts[0], sig, origins, rays, R, T, focal, principal, map_size,
+        w, idx, valid, ln = render_fused(verts[0], sigmas, origins, rays, cam, R, T, focal, principal, map_size,
                                          st['thr_activation'], st['absorptivity'], st['max_assign'],
-                                         use_ref_bins=(M != -1), bin_size=default_bin_size(map_size))
+                                         use_ref_bins=(M != -1), bin_size=default_bin_size(map_size),
+                                         sigma_mode=self._sigma_mode())
         return Fragments(vert_weight=w, vert_index=idx, valid_num=valid, vert_hit_length=ln,
                          points_per_view=verts.shape[1])
 
+    def _rays_match_model(self, rays, origins, image_size):
+        """Foreign camera objects (pytorch3d): the fused path culls with the closed-form pinhole model of
+        voge_b200.cameras while the rays come from the camera's own ray sampler.  Compare the two
+        at the image corners and centre (and the origins); on any mismatch -- K-matrix cameras, other camera
+        classes, a sampler with different conventions -- the op-by-op chain is used instead.  One host sync per
+        camera state (cached on the camera tensors' identities and versions)."""
+        H, W = int(image_size[0]), int(image_size[1])
+        key = self._camera_key(image_size)
+        cached = getattr(self, '_model_check', None)
+        if cached is not None and cached[0] == key:
+            return cached[2]
+        ok = False
+        try:
+            R, T, focal, principal, cam_origins = self._camera_tensors(image_size)
+            if rays.shape[0] == R.shape[0] and tuple(rays.shape[1:3]) == (H, W):
+                ys = torch.tensor([0, 0, H - 1, H - 1, H // 2], device=rays.device)
+                xs = torch.tensor([0, W - 1, 0, W - 1, W // 2], device=rays.device)
+                a = (principal[:, 0:1] - 0.5 - xs[None].float()) / focal[:, 0:1]
+                b = (principal[:, 1:2] - 0.5 - ys[None].float()) / focal[:, 1:2]
+                dc = torch.nn.functional.normalize(torch.stack([a, b, torch.ones_like(a)], -1), dim=-1)   # (B,5,3)
+                want = torch.matmul(dc, R.transpose(1, 2))
+                got = rays[:, ys, xs]
+                err = max(float((got - want).abs().max()), float((origins - cam_origins).abs().max()))
+                ok = err < 2e-5
+        except Exception:
+            ok = False
+        self._model_check = (key, [t for t in self._camera_key_tensors()], ok)
+        return ok
+
+    def _camera_key_tensors(self):
+        cams = self.cameras
+        names = ('R', 'T', 'focal_length', 'principal_point')
+        return [getattr(cams, n) for n in names if torch.is_tensor(getattr(cams, n, None))]
+
+    def _camera_key(self, image_size):
+        # identity (not address) of the camera tensors + version + layout: the cache below keeps references to the
+        # keyed tensors, so an id can not be recycled while its entry is alive
+        return (tuple(image_size),) + tuple((id(t), t._version, tuple(t.shape), tuple(t.stride()), str(t.device),
+                                             t.data_ptr()) for t in self._camera_key_tensors())
+
     def _rays(self, image_size):
         """(directions (B,H,W,3), origins (B,3)).  Real pytorch3d cameras go through pytorch3d's own
-        ray sampler exactly like the reference (:124-128); the built-in camera uses the closed form."""
+        ray sampler exactly like the reference (:124-128); the built-in camera uses the closed form
+        (voge_generate_rays: the generator the fused kernels evaluate per pixel, materialised)."""
         cams = self.cameras
-        if type(cams).__module__.startswith('pytorch3d'):
+        if not self._builtin_camera():
             from pytorch3d.renderer.implicit.raysampling import NDCMultinomialRaysampler
             sampler = NDCMultinomialRaysampler(image_width=int(image_size[1]), image_height=int(image_size[0]),
                                                unit_directions=True, n_pts_per_ray=1, min_depth=0, max_depth=10)
             bundle = sampler(cams)
             return bundle.directions, bundle.origins[:, 0, 0, :]
-        # The rays depend only on the camera tensors: regenerate them (a dozen elementwise passes over
-        # (B,H,W,3)) only when one of those tensors was replaced or written to, or when gradients must
-        # flow to the camera.  The reference rebuilds them on every forward.
-        tensors = [t for t in (cams.R, cams.T, cams.focal_length, cams.principal_point) if torch.is_tensor(t)]
+        R, T, focal, principal, origins = self._camera_tensors(image_size)
+        if not R.is_cuda:
+            return generate_rays(cams, image_size)      # host-side transcription (CPU tensors: tests of the glue)
+        tensors = self._camera_key_tensors()
         if any(t.requires_grad for t in tensors):
-            return generate_rays(cams, image_size)
-        key = (tuple(image_size),) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+            return fused_generate_rays(_C.make_cam(R, focal, principal), image_size), origins
+        # The rays depend only on the camera tensors: regenerate them only when one of those tensors was
+        # replaced or written to.  The reference rebuilds them on every forward.
+        key = self._camera_key(image_size)
         cache = getattr(self, '_ray_cache', None)
         if cache is None or cache[0] != key:
             with torch.no_grad():
-                cache = (key,) + tuple(generate_rays(cams, image_size))
+                rays = _C.generate_rays(_C.make_cam(R, focal, principal), image_size)
+                cache = (key, list(tensors), rays, origins.detach())
             self._ray_cache = cache
-        return cache[1], cache[2]
+        return cache[2], cache[3]
 
     def forward(self, gmeshes, **kwargs):
         assert not self.cameras.in_ndc(), 'Got NDC camera. Cameras.in_ndc must be set to false.'
@@ -157,9 +243,17 @@ class GaussianRenderer(nn.Module):
         if verts.dim() == 2:
             verts = verts[None]
 
-        rays, ray_origins = self._rays(map_size)
-        if self.use_fused and self._fusable(verts, sigmas, rays, ray_origins):
-            return self._forward_fused(verts, sigmas, rays, ray_origins)
+        if self.use_fused and self._fusable(verts, sigmas):
+            if self._builtin_camera():
+                return self._forward_fused(verts, sigmas, None, None)
+            rays, ray_origins = self._rays(map_size)
+            if self._rays_match_model(rays, ray_origins, map_size):
+                return self._forward_fused(verts, sigmas, rays, ray_origins)
+        else:
+            rays, ray_origins = self._rays(map_size)
+        if _setting(st, 'cholesky_sigma', False):
+            low = torch.tril(sigmas)
+            sigmas = low @ low.transpose(-2, -1)
         sigmas = expend_sigma(sigmas)
         verts_transformed = verts - ray_origins[:, None]
         if sigmas.dim() == 3:
@@ -201,8 +295,16 @@ def to_colored_background(fragments: Fragments, colors: torch.Tensor,
     if not torch.is_tensor(background_color):
         background_color = torch.tensor(list(background_color), dtype=torch.float32)
     background_color = background_color.to(device=colors.device, dtype=torch.float32).reshape(-1)
+    C = int(colors.shape[-1])
     if background_color.numel() == 1:
-        background_color = background_color.expand(colors.shape[-1])
+        background_color = background_color.expand(C)
+    elif background_color.numel() != C:
+        # the reference's `rgb + ones_like(rgb) * (1 - masks) * background` raises the same way (:171)
+        raise RuntimeError("The size of tensor a (%d) must match the size of tensor b (%d) at non-singleton "
+                           "dimension 3: background_color must have 1 or %d entries" % (C, background_color.numel(), C))
+    if C > MAX_BACKGROUND_CHANNELS:
+        raise RuntimeError("to_colored_background supports at most %d colour channels (got %d); composite wider "
+                           "feature maps with interpolate_attr and get_silhouette" % (MAX_BACKGROUND_CHANNELS, C))
     return merge_final(vert_attr=colors, weight=fragments.vert_weight, valid_num=fragments.valid_num,
                        vert_assign=fragments.vert_index, background=background_color.contiguous(), mask_thr=thr,
                        idx_mod=_idx_mod(fragments, colors))

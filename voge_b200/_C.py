@@ -5,6 +5,8 @@ at::full / at::zeros) so PyTorch's caching allocator owns all memory.
 
 CPU tensors raise RuntimeError, as the reference's CUDAGuard does: there is no CPU path.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -19,11 +21,21 @@ class BinOverflowError(RuntimeError):
     pass
 
 
+# Overflow policy of rasterize_points_coarse.  The reference prints a device-side warning, drops the
+# overflowing chunk (non-deterministically) and carries on (rasterize_coarse.cu:150-163).  Here a bin that
+# receives more than max_points_per_bin Gaussians keeps the first M in ascending index order (deterministic),
+# the true counts are returned / kept in `last_bin_counts`, and nothing is read back to the host: no sync on
+# the hot path.  check_overflow=True (or VOGE_CHECK_OVERFLOW=1) opts into a blocking check that raises.
+CHECK_OVERFLOW_DEFAULT = os.environ.get("VOGE_CHECK_OVERFLOW", "0") == "1"
+
+
 def rasterize_points_coarse(points, cloud_to_packed_first_idx, num_points_per_cloud, image_size, radius,
-                            bin_size, max_points_per_bin, return_counts=False, check_overflow=True):
+                            bin_size, max_points_per_bin, return_counts=False, check_overflow=None):
     """Reference: RasterizeEllipseCoarseCuda, rasterize_coarse.cu:254-305.
     points (P,3) f32, first_idx (B,) i64, num_per (B,) i64, image_size (H,W), radius (P,2) f32
     -> bin_points (B,BH,BW,M) int32, -1 padded, packed indices (ascending inside each bin)."""
+    if check_overflow is None:
+        check_overflow = CHECK_OVERFLOW_DEFAULT
     global last_bin_counts
     require_cuda(points, cloud_to_packed_first_idx, num_points_per_cloud, radius)
     if points.dim() != 2 or points.shape[1] != 3:
@@ -313,27 +325,55 @@ def sigma_kind(sigmas):
     raise Exception('Got unexpected sigma, which has shape: ' + str(sigmas.shape))
 
 
+SIGMA_MODES = {"direct": 0, "inverse": 1, "cholesky": 2}
+GAUSS_WIDTH = {1: 4, 3: 8, 9: 12}
+BIN_FLAG_DENSE_MARGIN = 1      # voge_bin_count flags: rounding margin with the dense-S constants (A/B aid)
+
+
+def make_cam(R, focal, principal):
+    """(B,16) f32 per-view camera records [R row-major (9), fx, fy, px, py, 0, 0, 0] read by the kernels that
+    generate their rays (render_core.cuh: gen_ray).  Plain torch ops: differentiable w.r.t. R / focal / principal."""
+    B = int(R.shape[0])
+    return torch.cat([R.reshape(B, 9), focal.reshape(B, 2), principal.reshape(B, 2),
+                      torch.zeros((B, 3), dtype=R.dtype, device=R.device)], dim=1).to(torch.float32).contiguous()
+
+
+def generate_rays(cam, image_size):
+    """Closed-form unit ray directions through the pixel centres (reference Renderer.py:124-128), (B,H,W,3):
+    the materialised form of the generator the fused kernels evaluate in registers -- same bits."""
+    cam = f32c(cam)
+    B, H, W = int(cam.shape[0]), int(image_size[0]), int(image_size[1])
+    with torch.cuda.device(cam.device):
+        rays = torch.empty((B, H, W, 3), dtype=torch.float32, device=cam.device)
+        check(lib().voge_generate_rays(ptr(cam), B, H, W, ptr(rays), stream_of(cam)), "generate_rays")
+    return rays
+
+
 def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act, use_ref_bins, bin_size,
-              tile):
+              tile, gauss=None, sigma_mode=0, flags=None):
     """-> (tile_offsets (B*TY*TX*S+1,) int64, tile_list (total,) int32, rects (B,N,2) int32,
     tile_item_offsets (B*TY*TX*S+1,) int64 with .total_items), S = voge_bin_sub() list segments per tile.
     One host sync (the two totals)."""
-    verts, sigmas = f32c(verts), f32c(sigmas)
     R, T, origins, focal, principal = f32c(R), f32c(T), f32c(origins), f32c(focal), f32c(principal)
-    B, N = int(R.shape[0]), int(verts.shape[0])
+    if gauss is None:
+        gauss = pack_gaussians(verts, sigmas, sigma_mode)
+    B, N = int(R.shape[0]), int(gauss.shape[0])
+    kind = {4: 1, 8: 3, 12: 9}[int(gauss.shape[1])]
     H, W = int(image_size[0]), int(image_size[1])
     TX, TY = (W + tile - 1) // tile, (H + tile - 1) // tile
-    dev = verts.device
+    if flags is None:
+        flags = BIN_FLAG_DENSE_MARGIN if os.environ.get("VOGE_DENSE_MARGIN") == "1" else 0
+    dev = gauss.device
     with torch.cuda.device(dev):
         rects = torch.empty((B, N, 2), dtype=torch.int32, device=dev)
         # row 0: list entries per tile, row 1: items (rectangle pixels) per tile; one leading zero column so
         # that the inclusive scan is the exclusive offset table
         S = int(lib().voge_bin_sub())
         counts = torch.zeros((2, B * TY * TX * S + 1), dtype=torch.int32, device=dev)
-        check(lib().voge_bin_count(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(R), ptr(T), ptr(origins),
+        check(lib().voge_bin_count(ptr(gauss), kind, ptr(R), ptr(T), ptr(origins),
                                    ptr(focal), ptr(principal), B, N, H, W, float(thr), float(thr_act),
-                                   int(bool(use_ref_bins)), int(bin_size), int(tile), ptr(rects), ptr(counts[0, 1:]),
-                                   ptr(counts[1, 1:]), stream_of(verts)), "bin_count")
+                                   int(bool(use_ref_bins)), int(bin_size), int(tile), int(flags), ptr(rects),
+                                   ptr(counts[0, 1:]), ptr(counts[1, 1:]), stream_of(gauss)), "bin_count")
         # two 1-D scans (cub DeviceScan); a (2, n) scan along dim 1 runs one thread block per row
         offsets = (torch.cumsum(counts[0], 0, dtype=torch.int64), torch.cumsum(counts[1], 0, dtype=torch.int64))
         # one host sync: total list entries + the item count at every view boundary (views can then be
@@ -345,33 +385,46 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
         tile_list = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
         cursor = torch.zeros((B * TY * TX * S,), dtype=torch.int32, device=dev)
         check(lib().voge_bin_fill(ptr(rects), ptr(offsets[0]), ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
-                                  stream_of(verts)), "bin_fill")
+                                  stream_of(gauss)), "bin_fill")
     item_offsets = offsets[1]
     item_offsets.total_items = total_items
     item_offsets.view_item_starts = view_item_starts      # B + 1 host ints
     return offsets[0], tile_list, rects, item_offsets
 
 
-def pack_gaussians(verts, sigmas):
-    """-> (N, 4 | 8 | 12) f32 records [x, y, z, S = 2 sigma ...] (16-byte aligned) read by the fused kernels."""
+def pack_gaussians(verts, sigmas, sigma_mode=0):
+    """-> (N, 4 | 8 | 12) f32 records [x, y, z, S = 2 P ...] (16-byte aligned) read by the fused kernels; P = sigmas
+    (mode 0), inverse(sigmas) (mode 1, reference inverse_sigma=True) or tril(sigmas) tril(sigmas)^T (mode 2)."""
     verts, sigmas = f32c(verts), f32c(sigmas)
     N, kind = int(verts.shape[0]), sigma_kind(sigmas)
     with torch.cuda.device(verts.device):
-        out = torch.empty((N, {1: 4, 3: 8, 9: 12}[kind]), dtype=torch.float32, device=verts.device)
-        check(lib().voge_pack_gaussians(ptr(verts), ptr(sigmas), kind, N, ptr(out), stream_of(verts)), "pack_gaussians")
+        out = torch.empty((N, GAUSS_WIDTH[kind]), dtype=torch.float32, device=verts.device)
+        check(lib().voge_pack_gaussians(ptr(verts), ptr(sigmas), kind, int(sigma_mode), N, ptr(out), stream_of(verts)),
+              "pack_gaussians")
     return out
 
 
 def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects, thr_act, absorptivity, K, tile,
-                   need_act=True, stats=None, item_offsets=None, gauss=None, max_group_items=1 << 29, debug=None):
-    """Fragments of the fused renderer.  With item_offsets (bin_views' fourth result): trace_hits ->
-    select_topk -> blend_weights, no per-pixel capacity limit; the views are traced in groups of at most
-    max_group_items items (8 bytes of scratch each).  Without: the one-launch shared-memory top-K kernel
-    (voge_render_forward) -- same results, kept as a cross-check."""
-    verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
-    B, H, W = int(rays.shape[0]), int(rays.shape[1]), int(rays.shape[2])
-    N, K = int(verts.shape[0]), int(K)
-    dev = verts.device
+                   need_act=True, stats=None, item_offsets=None, gauss=None, max_group_items=1 << 29, debug=None,
+                   cam=None, image_size=None, sigma_mode=0):
+    """Fragments of the fused renderer: trace_hits -> select_topk -> blend_weights over the tile lists of
+    bin_views (item_offsets = its fourth result); no per-pixel capacity limit; the views are traced in groups of
+    at most max_group_items items (8 bytes of scratch each).  rays (B,H,W,3), or None with cam (B,16) and
+    image_size: the kernels generate the rays themselves."""
+    origins = f32c(origins)
+    if rays is not None:
+        rays = f32c(rays)
+        B, H, W = int(rays.shape[0]), int(rays.shape[1]), int(rays.shape[2])
+    else:
+        cam = f32c(cam)
+        B, H, W = int(cam.shape[0]), int(image_size[0]), int(image_size[1])
+    if item_offsets is None:
+        raise RuntimeError("voge_b200.render_forward: item_offsets (bin_views' fourth result) is required")
+    if gauss is None:
+        gauss = pack_gaussians(verts, sigmas, sigma_mode)
+    N, K = int(gauss.shape[0]), int(K)
+    skind = {4: 1, 8: 3, 12: 9}[int(gauss.shape[1])]
+    dev = gauss.device
     with torch.cuda.device(dev):
         idx = torch.empty((B, H, W, K), dtype=torch.int32, device=dev)
         weight = torch.empty((B, H, W, K), dtype=torch.float32, device=dev)
@@ -379,16 +432,7 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
         valid = torch.empty((B, H, W), dtype=torch.int64, device=dev)
         act = torch.empty((B, H, W, K), dtype=torch.float32, device=dev) if need_act else None
         dsd = torch.empty((B, H, W, K), dtype=torch.float32, device=dev) if need_act else None
-        skind, st = sigma_kind(sigmas), stream_of(verts)
-        if item_offsets is None:
-            check(lib().voge_render_forward(ptr(verts), ptr(sigmas), skind, ptr(origins), ptr(rays),
-                                            ptr(tile_offsets), ptr(tile_list), ptr(rects), float(thr_act),
-                                            float(absorptivity), B, N, H, W, K, int(tile), ptr(idx), ptr(weight),
-                                            ptr(tlen), ptr(valid), ptr(act), ptr(dsd), ptr(stats), st),
-                  "render_forward")
-            return idx, weight, tlen, valid, act, dsd
-        if gauss is None:
-            gauss = pack_gaussians(verts, sigmas)
+        st = stream_of(gauss)
         nt = int(lib().voge_trace_threads(int(tile)))
         S = int(lib().voge_bin_sub())
         tiles_per_view = (int(tile_offsets.numel()) - 1) // S // max(B, 1)
@@ -417,13 +461,15 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
             t_off = tile_offsets[b0 * tiles_per_view * S:]
             i_off = item_offsets[b0 * tiles_per_view * S:]
             c_g, s_g = sl(counts, b0, b1, tiles_per_view * nt), sl(seg_base, b0, b1, tiles_per_view * nt)
-            check(lib().voge_trace_hits(ptr(gauss), skind, ptr(origins[b0:b1]), ptr(rays[b0:b1]), ptr(t_off),
+            check(lib().voge_trace_hits(ptr(gauss), skind, ptr(origins[b0:b1]),
+                                        ptr(rays[b0:b1]) if rays is not None else None,
+                                        ptr(cam[b0:b1]) if cam is not None else None, ptr(t_off),
                                         ptr(tile_list), ptr(rects[b0:b1]), ptr(i_off), int(starts[b0]), float(thr_act),
                                         nb, N, H, W, int(tile), ptr(c_g), ptr(s_g), ptr(hits), ptr(stats), st),
                   "trace_hits")
             check(lib().voge_select_topk(ptr(c_g), ptr(s_g), ptr(hits), b0, nb, N, H, W, K, int(tile),
                                          ptr(idx[b0:b1]), ptr(valid[b0:b1]), ptr(stats), st), "select_topk")
-        check(lib().voge_blend_weights(ptr(gauss), skind, ptr(origins), ptr(rays), ptr(idx), ptr(valid),
+        check(lib().voge_blend_weights(ptr(gauss), skind, ptr(origins), ptr(rays), ptr(cam), ptr(idx), ptr(valid),
                                        float(absorptivity), 0, B, N, H, W, K, ptr(weight), ptr(tlen), ptr(act), ptr(dsd),
                                        st), "blend_weights")
         if debug is not None:          # development aid (tools/select_hist.py): the per-pixel hit counts of the trace
@@ -431,51 +477,46 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
     return idx, weight, tlen, valid, act, dsd
 
 
-def render_backward(verts, sigmas, origins, rays, idx, valid, g_len, g_act, g_dsd, need_sigma=True):
-    verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
-    idx, g_len, g_act, g_dsd = i32c(idx), f32c(g_len), f32c(g_act), f32c(g_dsd)
-    B, H, W, K = (int(s) for s in idx.shape)
-    N = int(verts.shape[0])
-    dev = verts.device
-    with torch.cuda.device(dev):
-        g_verts = torch.zeros_like(verts)
-        g_sig = torch.zeros_like(sigmas) if need_sigma else None
-        check(lib().voge_render_backward(ptr(verts), ptr(sigmas), sigma_kind(sigmas), ptr(origins), ptr(rays),
-                                         ptr(idx), ptr(valid), ptr(g_len), ptr(g_act), ptr(g_dsd), B, N, H, W, K,
-                                         ptr(g_verts),
-                                         ptr(g_sig), stream_of(verts)), "render_backward")
-    return g_verts, g_sig
-
-
 def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_len_out, absorptivity,
-                          need_sigma=True, need_rays=False, need_origins=False, gauss=None, weight=None):
-    """-> (g_verts, g_sigmas | None, g_rays (B,H,W,3) | None, g_origins (B,3) | None)"""
-    verts, sigmas, origins, rays = f32c(verts), f32c(sigmas), f32c(origins), f32c(rays)
+                          need_sigma=True, need_rays=False, need_origins=False, gauss=None, weight=None,
+                          cam=None, need_cam=False, sigma_mode=0):
+    """-> (g_verts, g_sigmas | None, g_rays (B,H,W,3) | None, g_origins (B,3) | None, g_cam (B,16) | None).
+    rays None: the kernel generates them from cam (B,16); need_cam then returns the gradient of the camera
+    records (d/dR, d/dfocal, d/dprincipal summed over each view's pixels in the kernel)."""
+    verts, sigmas, origins = f32c(verts), f32c(sigmas), f32c(origins)
+    rays = f32c(rays) if rays is not None else None
+    cam = f32c(cam) if cam is not None else None
     idx, g_weight = i32c(idx), f32c(g_weight)
     g_len_out = f32c(g_len_out) if g_len_out is not None else None
     weight = f32c(weight) if weight is not None else None
     B, H, W, K = (int(s) for s in idx.shape)
     N = int(verts.shape[0])
     kind = sigma_kind(sigmas)
-    width = {1: 4, 3: 8, 9: 12}[kind]
     dev = verts.device
     with torch.cuda.device(dev):
         if gauss is None:
-            gauss = pack_gaussians(verts, sigmas)
-        packed = torch.zeros((N, width), dtype=torch.float32, device=dev)
-        g_rays = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev) if need_rays else None
+            gauss = pack_gaussians(verts, sigmas, sigma_mode)
+        packed = torch.zeros((N, GAUSS_WIDTH[kind]), dtype=torch.float32, device=dev)
+        g_rays = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev) if (need_rays and rays is not None) else None
         g_org = torch.zeros((B, 3), dtype=torch.float32, device=dev) if need_origins else None
+        g_cam = torch.zeros((B, 16), dtype=torch.float32, device=dev) if (need_cam and rays is None) else None
         check(lib().voge_render_backward_fused(ptr(gauss), kind, ptr(origins), ptr(rays),
                                                ptr(idx), ptr(valid), ptr(g_weight), ptr(weight), ptr(g_len_out),
                                                float(absorptivity), B, N, H, W, K, ptr(packed), int(bool(need_sigma)),
-                                               ptr(g_rays), ptr(g_org), stream_of(verts)), "render_backward_fused")
-    g_verts = packed[:, :3].contiguous()
-    g_sig = None
-    if need_sigma:
-        if kind == 1:
-            g_sig = packed[:, 3].contiguous()
-        elif kind == 3:
-            g_sig = packed[:, 4:7].contiguous()
-        else:
-            g_sig = packed[:, 3:12].reshape(N, 3, 3)
-    return g_verts, g_sig, g_rays, g_org
+                                               ptr(g_rays), ptr(g_org), ptr(cam), ptr(g_cam), stream_of(verts)),
+              "render_backward_fused")
+        g_verts, g_sig = unpack_gradients(packed, gauss, sigmas, sigma_mode, need_sigma)
+    return g_verts, g_sig, g_rays, g_org, g_cam
+
+
+def unpack_gradients(packed, gauss, sigmas, sigma_mode=0, need_sigma=True):
+    """Packed per-Gaussian gradient records -> (g_verts (N,3), g_sigmas shaped like `sigmas` | None), with the
+    chain rule of the sigma parameterisation (inverse / Cholesky) applied (voge_unpack_gradients)."""
+    sigmas = f32c(sigmas)
+    N, kind = int(packed.shape[0]), sigma_kind(sigmas)
+    with torch.cuda.device(packed.device):
+        g_verts = torch.empty((N, 3), dtype=torch.float32, device=packed.device)
+        g_sig = torch.empty_like(sigmas) if need_sigma else None
+        check(lib().voge_unpack_gradients(ptr(packed), ptr(gauss), ptr(sigmas), kind, int(sigma_mode), N, ptr(g_verts),
+                                          ptr(g_sig), stream_of(packed)), "unpack_gradients")
+    return g_verts, g_sig

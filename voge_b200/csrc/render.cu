@@ -1,7 +1,10 @@
 // render.cu -- the fused renderer path behind GaussianRenderer.forward:
 //   voge_bin_count / voge_bin_fill : per-view screen-space culling into per-tile CSR lists
-//   voge_render_forward            : tile-staged filter -> bit-faithful refine -> top-K -> blend weights
-//   voge_render_backward           : recompute + chain rule straight into (N,.) parameter gradients
+//   voge_pack_gaussians / voge_unpack_gradients : per-Gaussian parameter records (S = 2 sigma, 2 inverse(sigma) or
+//                                    2 L L^T) and the matching gradient epilogue
+//   voge_generate_rays             : closed-form pixel rays (never materialised on the fused path)
+//   voge_render_backward_fused     : recompute + analytic blend backward + chain rule straight into (N,.) gradients
+//   (forward pipeline: trace.cu, select.cu)
 //
 // Replaces, for the renderer's own call pattern, the chain
 //   rasterize_coarse (PyTorch maths RayTracing.py:42-57 + kernels rasterize_coarse.cu:20-188)
@@ -21,8 +24,7 @@ namespace voge {
 
 // ---- binning ---------------------------------------------------------------------------------------
 struct BinArgs {
-    const float* verts;
-    const float* sigmas;
+    const float* gauss;      // packed records (voge_pack_gaussians): [x, y, z, S = 2 P ...]
     int kind;
     const float* Rm;         // (B,3,3) row-vector convention X_view = X_world @ R + T
     const float* Tv;         // (B,3)
@@ -32,6 +34,7 @@ struct BinArgs {
     int B, N, H, W;
     float neg_log_thr, thr_act;
     int use_ref_bins, bin_size, BH, BW, tile, TX, TY;
+    int zero_aware_margin;   // 1: rounding margin counts the non-zero entries of S (default); 0: dense-S constants
     uint2* rects;            // (B,N): x = x0 | x1 << 16, y = y0 | y1 << 16 in PIXELS (inclusive); empty if x0 > x1
     int32_t* tile_counts;    // (B, TY*TX)
     int32_t* tile_items;     // optional (B, TY*TX): sum over the tile's entries of the rectangle area inside the tile
@@ -74,7 +77,11 @@ __device__ __forceinline__ void ref_bin_range(float lo, float hi, int nb, int bi
 // l = lambda_min(sym S); the factor 1.25 covers the second-order terms, which stay below 1 % of the first-order
 // ones as long as g10 Us / l < 1e-2 (otherwise the Gaussian is not culled analytically).  This is about half
 // the margin of the pixel-major filter (fine_core.cuh), which also has to cover its own re-associated sums.
-__device__ __forceinline__ bool gaussian_margin(const float* mu, const float* S, float thr_act, float& margin) {
+// Zero structure: a term whose S_ij is exactly 0 contributes t_ij = 0 and fma(0, c, acc) == acc exactly, i.e. neither a
+// product rounding nor a partial-sum rounding.  With n = number of non-zero entries of S every form passes through at
+// most 1 + n roundings (10 for a dense S, 4 for a diagonal / isotropic one stored as 3x3 or as a compact kind), so the
+// constants 10 / 20 / 10 above become (1 + n) / 2 (1 + n) / (1 + n): the margin of a diagonal Gaussian shrinks to 0.43x.
+__device__ __forceinline__ bool gaussian_margin(const float* mu, const float* S, float thr_act, bool zero_aware, float& margin) {
     const float m0 = mu[0], m1 = mu[1], m2 = mu[2];
     const float q0 = m0 * S[0] + m1 * S[3] + m2 * S[6];
     const float q1 = m0 * S[1] + m1 * S[4] + m2 * S[7];
@@ -117,7 +124,14 @@ __device__ __forceinline__ bool gaussian_margin(const float* mu, const float* S,
     const float Us = fmaxf(fmaxf(fmaxf(r0, r1), r2), fmaxf(fmaxf(k0, k1), k2));
     const float il = 1.f / lmin;
     if (!(Us * il < 1.6e4f)) return false;                       // g10 Us / l < 1e-2: second-order terms negligible
-    const float bound = 10.f * Tmm + 20.f * Qn * Um2 * il + 10.f * Us * (Qn * il) * (Qn * il) + 2.1f * Qn * Qn * il +
+    float g1 = 10.f;
+    if (zero_aware) {
+        int nnz = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) nnz += (S[i] != 0.f) ? 1 : 0;
+        g1 = (float)(1 + nnz);
+    }
+    const float bound = g1 * Tmm + 2.f * g1 * Qn * Um2 * il + g1 * Us * (Qn * il) * (Qn * il) + 2.1f * Qn * Qn * il +
                         2.f * fabsf(thr_act);
     margin = 7.4505806e-8f * 1.003f * bound;                     // 1.25 x 2^-24 (x rays within 1e-3 of unit length)
     return margin >= 0.f && margin < 3.0e38f;
@@ -134,10 +148,13 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
     const float half_y = __fdiv_rn(ndc_range(a.H, a.W) / 2.0f, (float)a.H);
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < a.N; g += gridDim.x * blockDim.x) {
         float mu[3], S[9];
-        mu[0] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
-        mu[1] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
-        mu[2] = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
-        load_S_dyn(a.kind, a.sigmas, g, S);
+        {
+            float v0, v1, v2;
+            if (a.kind == 1) load_gauss<1>(a.gauss, g, v0, v1, v2, S);
+            else if (a.kind == 3) load_gauss<3>(a.gauss, g, v0, v1, v2, S);
+            else load_gauss<9>(a.gauss, g, v0, v1, v2, S);
+            mu[0] = __fsub_rn(v0, c0); mu[1] = __fsub_rn(v1, c1); mu[2] = __fsub_rn(v2, c2);
+        }
         // view space (X_v = mu' @ R since the origin is the camera centre)
         const float xv = mu[0] * R[0] + mu[1] * R[3] + mu[2] * R[6];
         const float yv = mu[0] * R[1] + mu[1] * R[4] + mu[2] * R[7];
@@ -186,7 +203,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
         const bool sym_near = as01 <= 9.5367e-7f * (fabsf(S[1]) + fabsf(S[3])) &&
                               as02 <= 9.5367e-7f * (fabsf(S[2]) + fabsf(S[6])) &&
                               as12 <= 9.5367e-7f * (fabsf(S[5]) + fabsf(S[7]));
-        if (!empty && zv > 0.f && sym_near && gaussian_margin(mu, S, a.thr_act, margin)) {
+        if (!empty && zv > 0.f && sym_near && gaussian_margin(mu, S, a.thr_act, a.zero_aware_margin != 0, margin)) {
             if (!sym_exact) margin *= 2.f;
             const float a00 = S[0], a11 = S[4], a22 = S[8];
             const float a01 = 0.5f * (S[1] + S[3]), a02 = 0.5f * (S[2] + S[6]), a12 = 0.5f * (S[5] + S[7]);
@@ -270,422 +287,6 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__
     }
 }
 
-// ---- fused forward -----------------------------------------------------------------------------------
-struct RenderArgs {
-    const float* verts;
-    const float* sigmas;
-    const float* origins;   // (B,3)
-    const float* rays;      // (B,H,W,3)
-    const int64_t* tile_offsets;  // (B*TY*TX + 1)
-    const int32_t* tile_list;     // local Gaussian indices
-    const uint2* rects;           // (B,N) conservative pixel rectangles from bin_count_kernel
-    float thr_act, omega;
-    int B, N, H, W, K, tile, TX, TY, cap;
-    int32_t* out_idx;       // (B,H,W,K) packed b*N+g, -1 padded
-    float* out_weight;      // (B,H,W,K)
-    float* out_len;         // (B,H,W,K), 1e10 padded
-    int64_t* out_valid;     // (B,H,W)
-    float* out_act;         // optional (B,H,W,K)
-    float* out_dsd;         // optional (B,H,W,K)
-    unsigned long long* stats;  // optional: [0] pairs evaluated, [1] pairs refined (= [0]), [2] pixels that overflowed
-};
-
-// Gaussian-major ("splat") forward.  The Gaussians of the C5-like scenes cover a few dozen pixels
-// each while a 16x16 tile sees several hundred candidates, so iterating pixels x candidates evaluates
-// ~10x more pairs than there are near-hits (profiles/ncu_r1_fwd_bwd_v3.md: 460M filtered vs 44M refined
-// pairs per view).  Here every warp takes candidates of the tile list in turn and visits only the
-// pixels of the candidate's conservative pixel rectangle (reference bin rectangle AND tangent bound of
-// {act < thr + margin}, computed by bin_count_kernel) clipped to the tile, evaluates the pair with the
-// bit-faithful arithmetic (exact_pair) and appends hits to the pixel's unsorted key buffer in shared
-// memory (one shared-memory atomic per hit).  Each pixel thread then sorts its buffer, keeps the K
-// smallest (len, idx) keys and runs the blend epilogue.  Results are independent of the order in
-// which warps append (keys are unique and totally ordered) => bit-identical to the pixel-major path.
-constexpr int kSplatChunk = 128;   // candidates between two per-pixel compactions
-
-template <int NT, int KIND>
-__global__ void __launch_bounds__(NT, (NT == 256 ? 3 : 4)) render_fwd_kernel(const RenderArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);           // [cap][NT]
-    float* s_ray = reinterpret_cast<float*>(s_key + (size_t)a.cap * NT);                   // [3][NT]
-    int* s_cnt = reinterpret_cast<int*>(s_ray + 3 * NT);                                   // [NT]
-    unsigned long long* s_lim = reinterpret_cast<unsigned long long*>(s_cnt + NT);         // [NT] admission limit per pixel
-    float* s_E = reinterpret_cast<float*>(s_key + (size_t)a.K * NT);                       // epilogue alias, [K][NT]
-
-    const int tid = threadIdx.x;
-    int blk = blockIdx.x;
-    const int tx = blk % a.TX; blk /= a.TX;
-    const int ty = blk % a.TY;
-    const int b = blk / a.TY;
-
-    // pixel owned by this thread (inverse of pix_to_col)
-    int lx, ly;
-    bool in_tile;
-    if (a.tile == 16 && NT == 256) {
-        const int w = tid >> 5, l = tid & 31;
-        lx = (w & 1) * 8 + (l & 7);
-        ly = (w >> 1) * 4 + (l >> 3);
-        in_tile = true;
-    } else {
-        lx = tid % a.tile; ly = tid / a.tile;
-        in_tile = tid < a.tile * a.tile;
-    }
-    const int xi = tx * a.tile + lx, yi = ty * a.tile + ly;
-    const bool live = in_tile && xi < a.W && yi < a.H;
-    const int64_t ray = ((int64_t)b * a.H + yi) * a.W + xi;
-    const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
-    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-    if (live) { r0 = a.rays[ray * 3 + 0]; r1 = a.rays[ray * 3 + 1]; r2 = a.rays[ray * 3 + 2]; }
-    s_ray[tid] = r0; s_ray[NT + tid] = r1; s_ray[2 * NT + tid] = r2;
-    s_cnt[tid] = 0;
-    s_lim[tid] = pack_key(kEmptyLen, 0);
-
-    const int64_t tile_id = ((int64_t)b * a.TY + ty) * a.TX + tx;
-    const int64_t beg = a.tile_offsets[tile_id * kBinSub];
-    const int n = (int)(a.tile_offsets[(tile_id + 1) * kBinSub] - beg);
-    const int32_t* list = a.tile_list + beg;
-    __syncthreads();
-
-    // ---- phase A: Gaussian-major exact evaluation over each candidate's pixel rectangle, in chunks of
-    // kSplatChunk candidates; after every chunk each pixel thread compacts its buffer to the K smallest
-    // keys and publishes its K-th key as the admission limit for the following chunks ----
-    const int warp = tid >> 5, lane = tid & 31;
-    const int px0 = tx * a.tile, py0 = ty * a.tile;
-    const int pxe = min(px0 + a.tile, a.W) - 1, pye = min(py0 + a.tile, a.H) - 1;
-    unsigned n_eval = 0;
-    bool overflow = false;
-    // Software pipeline over this warp's candidates (i = warp, warp + NT/32, ...): the index is fetched two
-    // items ahead and the Gaussian's record (rectangle, mean, S) one item ahead, so the two dependent L2
-    // round trips overlap with the evaluation of the current candidate.
-    constexpr int kStep = NT / 32;
-    int g_nn = (warp + kStep < n) ? __ldg(list + warp + kStep) : -1;
-    int g_n = (warp < n) ? __ldg(list + warp) : -1;
-    uint2 rc_n = make_uint2(1u, 0u);
-    float v_n[3] = {0.f, 0.f, 0.f};
-    float S_n[9];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) S_n[q] = 0.f;
-    if (g_n >= 0) {
-        rc_n = a.rects[(int64_t)b * a.N + g_n];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) v_n[q] = __ldg(a.verts + 3 * (int64_t)g_n + q);
-        load_S<KIND>(a.sigmas, g_n, S_n);
-    }
-    for (int base = 0; base < n; base += kSplatChunk) {
-        const int end = min(n, base + kSplatChunk);
-        for (int i = base + warp; i < end; i += kStep) {
-            const int g = g_n;
-            const uint2 rc = rc_n;
-            const float m0 = __fsub_rn(v_n[0], c0), m1 = __fsub_rn(v_n[1], c1), m2 = __fsub_rn(v_n[2], c2);
-            float S[9];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) S[q] = S_n[q];
-            // prefetch the next record / the index after it
-            g_n = g_nn;
-            g_nn = (i + 2 * kStep < n) ? __ldg(list + i + 2 * kStep) : -1;
-            if (g_n >= 0) {
-                rc_n = a.rects[(int64_t)b * a.N + g_n];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) v_n[q] = __ldg(a.verts + 3 * (int64_t)g_n + q);
-                load_S<KIND>(a.sigmas, g_n, S_n);
-            }
-            const int xl = max((int)(rc.x & 0xffffu), px0), xh = min((int)(rc.x >> 16), pxe);
-            const int yl = max((int)(rc.y & 0xffffu), py0), yh = min((int)(rc.y >> 16), pye);
-            const int w = xh - xl + 1, h = yh - yl + 1;
-            if (w <= 0 || h <= 0) continue;
-            // ray-independent part of exact_pair: t_ij = rn(mu_i S_ij) and msm (shared by msk / msm in the reference)
-            Prod9 pm;
-            float msm;
-            if (KIND == 9) {
-                pm = exact_row_products(m0, m1, m2, S);
-                msm = exact_contract(pm, m0, m1, m2);
-            } else {
-                pm.t[0] = __fmul_rn(m0, S[0]); pm.t[4] = __fmul_rn(m1, S[4]); pm.t[8] = __fmul_rn(m2, S[8]);
-                msm = __fmaf_rn(pm.t[8], m2, __fmaf_rn(pm.t[4], m1, __fmul_rn(pm.t[0], m0)));
-            }
-            const int area = w * h;
-            const unsigned inv_w = kInvW[w];
-            for (int p = lane; p < area; p += 32) {
-                const int yy = (int)(((unsigned)p * inv_w) >> 16);
-                const int xx = p - yy * w;
-                const int col = pix_to_col<NT>(xl + xx - px0, yl + yy - py0, a.tile);
-                const float d0 = s_ray[col], d1 = s_ray[NT + col], d2 = s_ray[2 * NT + col];
-                float ksk, msk;
-                if (KIND == 9) {
-                    const Prod9 pd = exact_row_products(d0, d1, d2, S);
-                    ksk = exact_contract(pd, d0, d1, d2);
-                    msk = exact_contract(pm, d0, d1, d2);
-                } else {
-                    const float t0 = __fmul_rn(d0, S[0]), t1 = __fmul_rn(d1, S[4]), t2 = __fmul_rn(d2, S[8]);
-                    ksk = __fmaf_rn(t2, d2, __fmaf_rn(t1, d1, __fmul_rn(t0, d0)));
-                    msk = __fmaf_rn(pm.t[8], d2, __fmaf_rn(pm.t[4], d1, __fmul_rn(pm.t[0], d0)));
-                }
-                const float len = __fdiv_rn(msk, ksk);
-                const float act = __fsub_rn(msm, __fdiv_rn(__fmul_rn(msk, msk), ksk));
-                ++n_eval;
-                if (act < a.thr_act && len == len) {
-                    const unsigned long long key = pack_key(len, g);
-                    if (key < s_lim[col]) {     // initially len < 1e10 (reference :197), later the pixel's K-th key
-                        const int slot = atomicAdd(&s_cnt[col], 1);
-                        if (slot < a.cap) s_key[slot * NT + col] = key;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // compaction: keep the K smallest keys of this pixel, publish the K-th as the new limit
-        int c = s_cnt[tid];
-        if (c > a.cap) { overflow = true; c = a.cap; }
-        if (c > a.K) {
-            while (c > a.K) {           // drop the current maximum
-                unsigned long long mx = s_key[tid];
-                int mp = 0;
-                for (int k = 1; k < c; ++k) {
-                    const unsigned long long v = s_key[k * NT + tid];
-                    if (v > mx) { mx = v; mp = k; }
-                }
-                --c;
-                s_key[mp * NT + tid] = s_key[c * NT + tid];
-            }
-            unsigned long long mx = s_key[tid];
-            for (int k = 1; k < c; ++k) {
-                const unsigned long long v = s_key[k * NT + tid];
-                if (v > mx) mx = v;
-            }
-            s_lim[tid] = mx;
-            s_cnt[tid] = c;
-        }
-        __syncthreads();
-    }
-    if (a.stats != nullptr) {
-        unsigned long long e = n_eval, o = (live && overflow) ? 1ull : 0ull;
-        for (int s = 16; s > 0; s >>= 1) {
-            e += __shfl_down_sync(0xffffffffu, e, s);
-            o += __shfl_down_sync(0xffffffffu, o, s);
-        }
-        if (lane == 0) { atomicAdd(a.stats, e); atomicAdd(a.stats + 1, e); atomicAdd(a.stats + 2, o); }
-    }
-
-    // ---- phase B: per pixel, order the (at most K) survivors ----
-    TopKU<NT> top;
-    top.init(s_key, a.K, tid);
-    if (!live) {
-        top.cnt = 0;
-    } else if (overflow) {
-        // a single chunk delivered more hits than the buffer holds (rare): stream all candidates of the
-        // tile through the replace-the-maximum top-K buffer for this pixel alone
-        for (int i = 0; i < n; ++i) {
-            const int g = __ldg(list + i);
-            const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r0, r1, r2);
-            if (h.act < a.thr_act) top.insert(h.len, g);
-        }
-        top.sort();
-    } else {
-        top.cnt = min(s_cnt[tid], a.K);
-        top.sort();
-    }
-    const int cnt = top.cnt;
-    // the epilogue's E array aliases key rows K..1.5K of ALL columns: every thread must be done with
-    // its unsorted entries before anyone writes there
-    __syncthreads();
-    if (!live) return;
-
-    // ---- epilogue: exact (len, act, dsd) of the survivors, blend weights, fragment write-out ----
-    // Each thread owns a (K,) row of every fragment tensor; rows are written four slots at a time as
-    // 16-byte vectors when K % 4 == 0 (a scalar store at a 4K-byte lane stride costs one L1/L2 sector
-    // operation per lane and slot).
-    int32_t* o_idx = a.out_idx + ray * a.K;
-    float* o_len = a.out_len + ray * a.K;
-    float* o_w = a.out_weight + ray * a.K;
-    const bool vec = (a.K & 3) == 0;
-    float2* s_ls = reinterpret_cast<float2*>(s_key);   // the key slots are re-used for (len, sqrt(dsd + 1e-10))
-    float s_min = 3.0e38f;
-    for (int k0 = 0; k0 < a.K; k0 += 4) {
-        int iv[4];
-        float lv[4], av[4], dv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = k0 + j;
-            iv[j] = -1; lv[j] = kEmptyLen; av[j] = kEmptyLen; dv[j] = 0.f;
-            if (k < cnt) {
-                const int g = (int)(unsigned)(s_key[k * NT + tid] & 0xffffffffull);
-                const Hit h = exact_hit<KIND>(a.verts, a.sigmas, g, c0, c1, c2, r0, r1, r2);
-                iv[j] = b * a.N + g; lv[j] = h.len; av[j] = h.act; dv[j] = h.dsd;
-                const float sk = sqrtf(h.dsd + 1e-10f);                              // Aggregation.py:49
-                s_ls[k * NT + tid] = make_float2(h.len, sk);
-                s_E[k * NT + tid] = expf(-h.act);
-                s_min = fminf(s_min, sk);
-            }
-        }
-        if (vec) {
-            *reinterpret_cast<int4*>(o_idx + k0) = make_int4(iv[0], iv[1], iv[2], iv[3]);
-            *reinterpret_cast<float4*>(o_len + k0) = make_float4(lv[0], lv[1], lv[2], lv[3]);
-            if (a.out_act != nullptr) {
-                *reinterpret_cast<float4*>(a.out_act + ray * a.K + k0) = make_float4(av[0], av[1], av[2], av[3]);
-                *reinterpret_cast<float4*>(a.out_dsd + ray * a.K + k0) = make_float4(dv[0], dv[1], dv[2], dv[3]);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (k0 + j >= a.K) break;
-                o_idx[k0 + j] = iv[j]; o_len[k0 + j] = lv[j];
-                if (a.out_act != nullptr) { a.out_act[ray * a.K + k0 + j] = av[j]; a.out_dsd[ray * a.K + k0 + j] = dv[j]; }
-            }
-        }
-    }
-    // D_m = sum_k E_k Phi((len_m - len_k) s_k).  The list is sorted by len, so outside the window
-    // |len_m - len_k| * min_k(s_k) < 4 the erf is saturated: Phi = 1 for k < lo(m) (their E_k are
-    // carried in a running prefix sum -- lo(m) only moves forward), Phi = 0 behind the window.
-    // The summation order is the plain k = 0..cnt-1 order of the stand-alone aggregation kernel.
-    {
-        int lo = 0;
-        float SE = 0.f;
-        for (int m0 = 0; m0 < a.K; m0 += 4) {
-            float wv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int m = m0 + j;
-                wv[j] = 0.f;
-                if (m < cnt) {
-                    const float lm = s_ls[m * NT + tid].x;
-                    while (lo < m && (lm - s_ls[lo * NT + tid].x) * s_min >= kErfSat) { SE += s_E[lo * NT + tid]; ++lo; }
-                    float D = SE;
-                    for (int k = lo; k < cnt; ++k) {
-                        const float2 lk = s_ls[k * NT + tid];
-                        const float dl = lm - lk.x;
-                        if (dl * s_min <= -kErfSat) break;
-                        D += s_E[k * NT + tid] * phi(dl * lk.y);
-                    }
-                    const float Em = s_E[m * NT + tid];
-                    wv[j] = Em != 0.f ? expf(-(D * a.omega)) * Em * kInvExpMinusHalf : 0.f;
-                }
-            }
-            if (vec) {
-                *reinterpret_cast<float4*>(o_w + m0) = make_float4(wv[0], wv[1], wv[2], wv[3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (m0 + j < a.K) o_w[m0 + j] = wv[j];
-            }
-        }
-    }
-    a.out_valid[ray] = cnt;
-}
-
-// per-pixel hit buffer capacity: 2K when it fits comfortably, never below 1.5K (the epilogue aliases
-// its E array onto slots K..1.5K)
-static int hit_capacity(int K, int nt) {
-    int cap = 2 * K;
-    // prefer three resident CTAs per SM (<= ~72 KB each) when the minimum depth allows it
-    while (cap > (3 * K + 1) / 2 && (size_t)cap * nt * 8 + (size_t)nt * 24 > 73 * 1024) --cap;
-    return cap;
-}
-
-template <int NT, int KIND>
-static int launch_render(const RenderArgs& a0, cudaStream_t stream) {
-    RenderArgs a = a0;
-    a.cap = hit_capacity(a.K, NT);
-    const size_t smem = (size_t)a.cap * NT * 8 + (size_t)NT * 24;
-    if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
-    VOGE_CUDA_TRY(cudaFuncSetAttribute(render_fwd_kernel<NT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long grid = (long long)a.B * a.TX * a.TY;
-    if (grid <= 0 || grid > 2147483647LL) return (int)cudaErrorInvalidValue;
-    render_fwd_kernel<NT, KIND><<<(unsigned)grid, NT, smem, stream>>>(a);
-    VOGE_LAUNCH_CHECK();
-    return 0;
-}
-
-template <int KIND>
-static int dispatch_render(const RenderArgs& a, cudaStream_t s) {
-    const int px = a.tile * a.tile;
-    if (px > 256) return (int)cudaErrorInvalidValue;
-    if (px > 128) return launch_render<256, KIND>(a, s);
-    if (px > 64) return launch_render<128, KIND>(a, s);
-    return launch_render<64, KIND>(a, s);
-}
-
-// ---- backward of the geometry: d(len, act, dsd) -> d(verts), d(sigmas) ----------------------------------
-struct RenderBwdArgs {
-    const float* verts;
-    const float* sigmas;
-    int kind;
-    const float* origins;
-    const float* rays;
-    const int32_t* idx;      // packed
-    const int64_t* valid;    // (B,H,W) number of leading valid slots (idx itself may have been rewritten
-                             // -1 -> 0 by merge_final, reference Aggregation.py:131)
-    const float* g_len;
-    const float* g_act;
-    const float* g_dsd;
-    int B, N, H, W, K;
-    float* grad_verts;       // (N,3) accumulated
-    float* grad_sigmas;      // (N,), (N,3) or (N,3,3) accumulated (gradient w.r.t. sigma, i.e. includes the factor 2)
-};
-
-__global__ void __launch_bounds__(256) render_bwd_kernel(const RenderBwdArgs a) {
-    // 8x4 pixel block per warp so that lanes of a warp touch the same Gaussians
-    const int bw = (a.W + 7) / 8, bh = (a.H + 3) / 4;
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int64_t per_view = (int64_t)bw * bh;
-    if (wid >= per_view * a.B) return;
-    const int b = (int)(wid / per_view);
-    const int wb = (int)(wid % per_view);
-    const int xi = (wb % bw) * 8 + (lane & 7), yi = (wb / bw) * 4 + (lane >> 3);
-    if (xi >= a.W || yi >= a.H) return;
-    const int64_t r = ((int64_t)b * a.H + yi) * a.W + xi;
-    const float d0 = a.rays[r * 3 + 0], d1 = a.rays[r * 3 + 1], d2 = a.rays[r * 3 + 2];
-    const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
-    const int cnt = (int)min((int64_t)a.K, a.valid[r]);
-    for (int k = 0; k < cnt; ++k) {
-        const int gp = a.idx[r * a.K + k];
-        const int g = gp - b * a.N;
-        if (g < 0 || g >= a.N) continue;
-        const float gl = a.g_len[r * a.K + k], ga = a.g_act[r * a.K + k], gd = a.g_dsd[r * a.K + k];
-        float S[9];
-        load_S_dyn(a.kind, a.sigmas, g, S);
-        const float m0 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g), c0);
-        const float m1 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 1), c1);
-        const float m2 = __fsub_rn(__ldg(a.verts + 3 * (int64_t)g + 2), c2);
-        const Prod9 pd = exact_row_products(d0, d1, d2, S);
-        const Prod9 pm = exact_row_products(m0, m1, m2, S);
-        const float ksk = exact_contract(pd, d0, d1, d2);
-        const float msk = exact_contract(pm, d0, d1, d2);
-        const float g_ksk = (ga * msk - gl) * msk / (ksk * ksk) + gd;   // ray_trace_voge.cu:324-326
-        const float g_msk = (gl - 2.f * ga * msk) / ksk;
-        const float g_msm = ga;
-        const float Sd0 = S[0] * d0 + S[1] * d1 + S[2] * d2, Sd1 = S[3] * d0 + S[4] * d1 + S[5] * d2,
-                    Sd2 = S[6] * d0 + S[7] * d1 + S[8] * d2;
-        const float Sm0 = S[0] * m0 + S[1] * m1 + S[2] * m2, Sm1 = S[3] * m0 + S[4] * m1 + S[5] * m2,
-                    Sm2 = S[6] * m0 + S[7] * m1 + S[8] * m2;
-        const float Stm0 = S[0] * m0 + S[3] * m1 + S[6] * m2, Stm1 = S[1] * m0 + S[4] * m1 + S[7] * m2,
-                    Stm2 = S[2] * m0 + S[5] * m1 + S[8] * m2;
-        float* gv = a.grad_verts + 3 * (int64_t)g;
-        atomicAdd(gv + 0, g_msk * Sd0 + g_msm * (Sm0 + Stm0));
-        atomicAdd(gv + 1, g_msk * Sd1 + g_msm * (Sm1 + Stm1));
-        atomicAdd(gv + 2, g_msk * Sd2 + g_msm * (Sm2 + Stm2));
-        if (a.grad_sigmas != nullptr) {
-            const float dv[3] = {d0, d1, d2}, mv[3] = {m0, m1, m2};
-            if (a.kind == 1) {
-                const float tr = g_ksk * (d0 * d0 + d1 * d1 + d2 * d2) + g_msk * (m0 * d0 + m1 * d1 + m2 * d2) +
-                                 g_msm * (m0 * m0 + m1 * m1 + m2 * m2);
-                atomicAdd(a.grad_sigmas + g, 2.f * tr);
-            } else if (a.kind == 3) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-                    atomicAdd(a.grad_sigmas + 3 * (int64_t)g + i,
-                              2.f * (g_ksk * dv[i] * dv[i] + g_msk * mv[i] * dv[i] + g_msm * mv[i] * mv[i]));
-            } else {
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        atomicAdd(a.grad_sigmas + 9 * (int64_t)g + 3 * i + j,
-                                  2.f * (g_ksk * dv[i] * dv[j] + g_msk * mv[i] * dv[j] + g_msm * mv[i] * mv[j]));
-            }
-        }
-    }
-}
-
 // ---- fused backward: d(weight), d(len) -> d(verts), d(sigmas) in ONE kernel ----------------------------
 // Recompute, don't store: per pixel the K hits are re-evaluated with the bit-faithful arithmetic
 // (so neither act nor dsd is ever written to HBM by the forward), the blend is differentiated
@@ -695,7 +296,8 @@ struct FusedBwdArgs {
     const float* gauss;      // packed records (voge_pack_gaussians)
     int kind;
     const float* origins;
-    const float* rays;
+    const float* rays;       // (B,H,W,3), or NULL: generated from `cam` (render_core.cuh: gen_ray)
+    const float* cam;        // (B,16) per-view camera records, read when rays == NULL
     const int32_t* idx;
     const int64_t* valid;
     const float* g_weight;   // (B,H,W,K)
@@ -707,6 +309,8 @@ struct FusedBwdArgs {
     int need_sigma;
     float* grad_rays;        // optional (B,H,W,3), written in full: d/d(ray direction) (pose optimisation)
     float* grad_origins;     // optional (B,3), zeroed by the caller: d/d(ray origin) = -sum over the view's hits of d/d(mu')
+    float* grad_cam;         // optional (B,16), zeroed by the caller, generated rays only: d/d(cam record) = the chain rule of
+                             // the ray generator summed over the view's pixels [dR (9), dfx, dfy, dpx, dpy, -, -, -]
 };
 
 template <bool CAM>
@@ -767,6 +371,25 @@ __device__ __forceinline__ void geom_grad_accumulate(const FusedBwdArgs& a, int 
     }
 }
 
+// d/d(ray direction) of the warp's pixels -> d/d(cam record) of their view (all 32 lanes belong to view b): the chain
+// rule of the ray generator per contributing lane, a warp reduction per component, 13 atomics per warp.
+__device__ __forceinline__ void cam_grad_reduce(const FusedBwdArgs& a, int b, int xi, int yi, bool contributes,
+                                                const float* cam_acc, int lane) {
+    float o13[13];
+#pragma unroll
+    for (int q = 0; q < 13; ++q) o13[q] = 0.f;
+    if (contributes) {
+        const ViewCam v = load_view_cam(a.cam, b);
+        gen_ray_backward(v, xi, yi, cam_acc[0], cam_acc[1], cam_acc[2], o13);
+    }
+#pragma unroll
+    for (int q = 0; q < 13; ++q) {
+        float v = o13[q];
+        for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_down_sync(0xffffffffu, v, sft);
+        if (lane == 0 && v != 0.f) atomicAdd(a.grad_cam + 16 * b + q, v);
+    }
+}
+
 template <int NT, int KIND, bool CAM>
 __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -789,7 +412,8 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
     const int64_t r = live ? ((int64_t)b * a.H + yi) * a.W + xi : 0;
     const int cnt = live ? (int)min((int64_t)a.K, a.valid[r]) : 0;
     if (!CAM && cnt == 0) return;
-    const float d0 = a.rays[r * 3 + 0], d1 = a.rays[r * 3 + 1], d2 = a.rays[r * 3 + 2];
+    float d0 = 0.f, d1 = 0.f, d2 = 1.f;
+    if (live) pixel_ray(a.rays, a.cam, b, xi, yi, a.H, a.W, d0, d1, d2);
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
     const float omega = a.omega;
     float cam_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d/d(ray) of this pixel, d/d(origin) partial sum
@@ -958,8 +582,9 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
         if (a.grad_rays != nullptr && live) {
             a.grad_rays[r * 3 + 0] = cam_acc[0]; a.grad_rays[r * 3 + 1] = cam_acc[1]; a.grad_rays[r * 3 + 2] = cam_acc[2];
         }
+        __syncwarp();
+        if (a.grad_cam != nullptr) cam_grad_reduce(a, b, xi, yi, live, cam_acc, lane);
         if (a.grad_origins != nullptr) {
-            __syncwarp();
 #pragma unroll
             for (int q = 3; q < 6; ++q) {
                 float v = cam_acc[q];          // the 32 lanes of a warp belong to one view
@@ -974,7 +599,7 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
 // memory bound the resident pixels per SM, and with one thread per pixel that left 20 warps of serial,
 // latency-bound work.  The pair shares the arrays; thread `sub` owns the slots k = sub, sub + 2, ... in every pass.
 template <int NT, int KIND, bool CAM>
-__global__ void __launch_bounds__(NT) render_bwd_pair_kernel(const FusedBwdArgs a) {
+__global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(const FusedBwdArgs a) {
     constexpr int NP = NT / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const size_t A = (size_t)a.K * NP;
@@ -997,7 +622,8 @@ __global__ void __launch_bounds__(NT) render_bwd_pair_kernel(const FusedBwdArgs 
     const int64_t r = live ? ((int64_t)b * a.H + yi) * a.W + xi : 0;
     const int cnt = live ? (int)min((int64_t)a.K, a.valid[r]) : 0;
     if (!CAM && cnt == 0) return;
-    const float d0 = a.rays[r * 3 + 0], d1 = a.rays[r * 3 + 1], d2 = a.rays[r * 3 + 2];
+    float d0 = 0.f, d1 = 0.f, d2 = 1.f;
+    if (live) pixel_ray(a.rays, a.cam, b, xi, yi, a.H, a.W, d0, d1, d2);
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
     const float omega = a.omega;
     float cam_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d/d(ray), d/d(origin) partial sums of this thread's slots
@@ -1154,12 +780,13 @@ __global__ void __launch_bounds__(NT) render_bwd_pair_kernel(const FusedBwdArgs 
     }
     if (CAM) {
         __syncwarp();
-        if (a.grad_rays != nullptr) {
+        if (a.grad_rays != nullptr || a.grad_cam != nullptr) {
 #pragma unroll
             for (int q = 0; q < 3; ++q) cam_acc[q] += __shfl_xor_sync(0xffffffffu, cam_acc[q], 1);
-            if (live && sub == 0) {
+            if (a.grad_rays != nullptr && live && sub == 0) {
                 a.grad_rays[r * 3 + 0] = cam_acc[0]; a.grad_rays[r * 3 + 1] = cam_acc[1]; a.grad_rays[r * 3 + 2] = cam_acc[2];
             }
+            if (a.grad_cam != nullptr) cam_grad_reduce(a, b, xi, yi, live && sub == 0, cam_acc, lane);
         }
         if (a.grad_origins != nullptr) {
 #pragma unroll
@@ -1179,14 +806,17 @@ extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
                                           const int64_t* valid, const float* grad_weight, const float* weight,
                                           const float* grad_len_out, float absorptivity, int B, int N, int H,
                                           int W, int K, float* grad_packed, int need_sigma, float* grad_rays,
-                                          float* grad_origins, voge_stream_t stream) {
+                                          float* grad_origins, const float* cam, float* grad_cam,
+                                          voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
-    FusedBwdArgs a{gauss, sigma_kind, origins, rays, idx, valid, grad_weight, weight, grad_len_out, absorptivity,
-                   B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins};
+    if (rays == nullptr && cam == nullptr) return (int)cudaErrorInvalidValue;
+    if (grad_cam != nullptr && (rays != nullptr || cam == nullptr)) return (int)cudaErrorInvalidValue;
+    FusedBwdArgs a{gauss, sigma_kind, origins, rays, cam, idx, valid, grad_weight, weight, grad_len_out, absorptivity,
+                   B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins, grad_cam};
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool cam = grad_rays != nullptr || grad_origins != nullptr;
+    const bool cam_grads = grad_rays != nullptr || grad_origins != nullptr || grad_cam != nullptr;
     auto launch = [&](auto kernel, int nt, int per_pixel) -> int {
         // per_pixel = 2: two threads per pixel, 4x4 pixel blocks per warp; 1: 8x4 blocks
         const int64_t warps = per_pixel == 2 ? (int64_t)B * cdiv(W, 4) * cdiv(H, 4) : (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
@@ -1211,17 +841,61 @@ extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
         if (sigma_kind == 3) return by_threads(std::integral_constant<int, 3>{}, cam_tag);
         return by_threads(std::integral_constant<int, 9>{}, cam_tag);
     };
-    return cam ? by_kind(std::true_type{}) : by_kind(std::false_type{});
+    return cam_grads ? by_kind(std::true_type{}) : by_kind(std::false_type{});
 }
 
 namespace voge {
+// ---- parameter records ---------------------------------------------------------------------------------------
+// sigma_mode: how the renderer's `sigmas` argument maps to the matrix P of S = 2 P (reference Renderer.py:134-137):
+//   0  P = sigmas                     (inverse covariances given, inverse_sigma = False)
+//   1  P = inverse(sigmas)            (covariances given, inverse_sigma = True: `2 * torch.inverse(sigmas)`)
+//   2  P = tril(L) tril(L)^T          (Cholesky factor given: `to_sym`, demo/EfficientCuboidViaOptimization.py:17-18)
+// The 3x3 inverse is the adjugate over the determinant (the reference calls torch.inverse = batched LU; both are
+// backward-stable, the results differ in the last bits like two LU implementations do).
+__device__ __forceinline__ void sigma_to_S(int kind, int mode, const float* __restrict__ sig, int g, float* S) {
+    if (mode == 0) {
+        load_S_dyn(kind, sig, g, S);
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) S[i] = 0.f;
+    if (kind == 1) {
+        const float v = 2.f / __ldg(sig + g);
+        S[0] = v; S[4] = v; S[8] = v;
+    } else if (kind == 3) {
+        S[0] = 2.f / __ldg(sig + 3 * (int64_t)g);
+        S[4] = 2.f / __ldg(sig + 3 * (int64_t)g + 1);
+        S[8] = 2.f / __ldg(sig + 3 * (int64_t)g + 2);
+    } else {
+        float m[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) m[i] = __ldg(sig + 9 * (int64_t)g + i);
+        if (mode == 1) {
+            const float c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+            const float det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+            const float t = 2.f / det;
+            S[0] = c00 * t; S[1] = (m[2] * m[7] - m[1] * m[8]) * t; S[2] = (m[1] * m[5] - m[2] * m[4]) * t;
+            S[3] = c01 * t; S[4] = (m[0] * m[8] - m[2] * m[6]) * t; S[5] = (m[2] * m[3] - m[0] * m[5]) * t;
+            S[6] = c02 * t; S[7] = (m[1] * m[6] - m[0] * m[7]) * t; S[8] = (m[0] * m[4] - m[1] * m[3]) * t;
+        } else {
+            const float l00 = m[0], l10 = m[3], l11 = m[4], l20 = m[6], l21 = m[7], l22 = m[8];
+            S[0] = 2.f * (l00 * l00);
+            S[1] = S[3] = 2.f * (l00 * l10);
+            S[2] = S[6] = 2.f * (l00 * l20);
+            S[4] = 2.f * (l10 * l10 + l11 * l11);
+            S[5] = S[7] = 2.f * (l10 * l20 + l11 * l21);
+            S[8] = 2.f * (l20 * l20 + l21 * l21 + l22 * l22);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) pack_gaussians_kernel(const float* __restrict__ verts, const float* __restrict__ sigmas,
-                                                             int kind, int N, float* __restrict__ out) {
+                                                             int kind, int mode, int N, float* __restrict__ out) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
     const float x = verts[3 * (int64_t)g], y = verts[3 * (int64_t)g + 1], z = verts[3 * (int64_t)g + 2];
     float S[9];
-    load_S_dyn(kind, sigmas, g, S);                     // S = 2 sigma (Renderer.py:137), exact in fp32
+    sigma_to_S(kind, mode, sigmas, g, S);               // mode 0: S = 2 sigma (Renderer.py:137), exact in fp32
     float4* o = reinterpret_cast<float4*>(out);
     if (kind == 1) {
         o[g] = make_float4(x, y, z, S[0]);
@@ -1234,34 +908,138 @@ __global__ void __launch_bounds__(256) pack_gaussians_kernel(const float* __rest
         o[3 * (int64_t)g + 2] = make_float4(S[5], S[6], S[7], S[8]);
     }
 }
+
+// Gradient epilogue: the fused backward accumulates one packed record per Gaussian, [d verts (3) | d P] with
+// d P = dL/dP (P as above; the factor 2 of S = 2 P is already applied).  This kernel splits the records into the
+// caller's tensors and applies the chain rule of the sigma parameterisation:
+//   mode 1:  dL/dSigma = -P^T (dL/dP) P^T   (P = S / 2 read back from the Gaussian's record)
+//   mode 2:  dL/dL     = tril((G + G^T) tril(L))
+__global__ void __launch_bounds__(256) unpack_gradients_kernel(const float* __restrict__ packed, const float* __restrict__ gauss,
+                                                               const float* __restrict__ sigmas, int kind, int mode, int N,
+                                                               float* __restrict__ g_verts, float* __restrict__ g_sigmas) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const int width = kind == 9 ? 12 : (kind == 3 ? 8 : 4);
+    const float4* pk = reinterpret_cast<const float4*>(packed) + (int64_t)g * (width / 4);
+    const float4 q0 = pk[0];
+    g_verts[3 * (int64_t)g] = q0.x; g_verts[3 * (int64_t)g + 1] = q0.y; g_verts[3 * (int64_t)g + 2] = q0.z;
+    if (g_sigmas == nullptr) return;
+    if (kind == 1) {
+        float v = q0.w;
+        if (mode == 1) { const float p = 1.f / __ldg(sigmas + g); v = -v * p * p; }
+        g_sigmas[g] = v;
+    } else if (kind == 3) {
+        const float4 q1 = pk[1];
+        float v[3] = {q1.x, q1.y, q1.z};
+        if (mode == 1) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { const float p = 1.f / __ldg(sigmas + 3 * (int64_t)g + i); v[i] = -v[i] * p * p; }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) g_sigmas[3 * (int64_t)g + i] = v[i];
+    } else {
+        const float4 q1 = pk[1], q2 = pk[2];
+        const float G[9] = {q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+        float o[9];
+        if (mode == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) o[i] = G[i];
+        } else if (mode == 1) {
+            float v0, v1, v2, S[9], P[9];
+            load_gauss<9>(gauss, g, v0, v1, v2, S);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) P[i] = 0.5f * S[i];
+            float T[9];   // T = P^T G
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) T[3 * i + j] = P[i] * G[j] + P[3 + i] * G[3 + j] + P[6 + i] * G[6 + j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) o[3 * i + j] = -(T[3 * i] * P[3 * j] + T[3 * i + 1] * P[3 * j + 1] + T[3 * i + 2] * P[3 * j + 2]);
+        } else {
+            float L[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) L[i] = __ldg(sigmas + 9 * (int64_t)g + i);
+            L[1] = L[2] = L[5] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) acc += (G[3 * i + k] + G[3 * k + i]) * L[3 * k + j];
+                    o[3 * i + j] = j <= i ? acc : 0.f;
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) g_sigmas[9 * (int64_t)g + i] = o[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) generate_rays_kernel(const float* __restrict__ cam, int B, int H, int W,
+                                                            float* __restrict__ rays) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)B * H * W) return;
+    const int x = (int)(t % W), y = (int)((t / W) % H), b = (int)(t / ((int64_t)W * H));
+    const ViewCam v = load_view_cam(cam, b);
+    float d0, d1, d2;
+    gen_ray(v, x, y, d0, d1, d2);
+    rays[3 * t] = d0; rays[3 * t + 1] = d1; rays[3 * t + 2] = d2;
+}
 }  // namespace voge
 
-extern "C" int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int N, float* out,
-                                   voge_stream_t stream) {
+extern "C" int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int sigma_mode, int N,
+                                   float* out, voge_stream_t stream) {
     using namespace voge;
     if (N <= 0) return 0;
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
-    pack_gaussians_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(verts, sigmas, sigma_kind, N, out);
+    if (sigma_mode < 0 || sigma_mode > 2 || (sigma_mode == 2 && sigma_kind != 9)) return (int)cudaErrorInvalidValue;
+    pack_gaussians_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(verts, sigmas, sigma_kind, sigma_mode, N, out);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int voge_unpack_gradients(const float* grad_packed, const float* gauss, const float* sigmas, int sigma_kind,
+                                     int sigma_mode, int N, float* grad_verts, float* grad_sigmas, voge_stream_t stream) {
+    using namespace voge;
+    if (N <= 0) return 0;
+    if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
+    if (sigma_mode < 0 || sigma_mode > 2 || (sigma_mode == 2 && sigma_kind != 9)) return (int)cudaErrorInvalidValue;
+    unpack_gradients_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(grad_packed, gauss, sigmas, sigma_kind, sigma_mode,
+                                                                           N, grad_verts, grad_sigmas);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int voge_generate_rays(const float* cam, int B, int H, int W, float* rays, voge_stream_t stream) {
+    using namespace voge;
+    const int64_t total = (int64_t)B * H * W;
+    if (total <= 0) return 0;
+    generate_rays_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cam, B, H, W, rays);
     VOGE_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int voge_bin_sub(void) { return voge::kBinSub; }
 
-extern "C" int voge_bin_count(const float* verts, const float* sigmas, int sigma_kind, const float* Rm,
+extern "C" int voge_bin_count(const float* gauss, int sigma_kind, const float* Rm,
                               const float* Tv, const float* origins, const float* focal, const float* principal,
                               int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins, int bin_size,
-                              int tile, uint32_t* rects, int32_t* tile_counts, int32_t* tile_items, voge_stream_t stream) {
+                              int tile, int flags, uint32_t* rects, int32_t* tile_counts, int32_t* tile_items,
+                              voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || N <= 0) return 0;
     if (tile <= 0 || tile > 16 || (use_ref_bins && (bin_size <= 0 || bin_size % tile != 0))) return (int)cudaErrorInvalidValue;
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     BinArgs a;
-    a.verts = verts; a.sigmas = sigmas; a.kind = sigma_kind; a.Rm = Rm; a.Tv = Tv; a.origins = origins;
+    a.gauss = gauss; a.kind = sigma_kind; a.Rm = Rm; a.Tv = Tv; a.origins = origins;
     a.focal = focal; a.principal = principal; a.B = B; a.N = N; a.H = H; a.W = W;
     a.neg_log_thr = -logf(thr); a.thr_act = thr_act; a.use_ref_bins = use_ref_bins; a.bin_size = bin_size;
     a.BH = use_ref_bins ? cdiv(H, bin_size) : 1; a.BW = use_ref_bins ? cdiv(W, bin_size) : 1;
     a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
+    a.zero_aware_margin = (flags & 1) ? 0 : 1;
     if (a.TX > 65535 || a.TY > 65535) return (int)cudaErrorInvalidValue;
     a.rects = reinterpret_cast<uint2*>(rects); a.tile_counts = tile_counts; a.tile_items = tile_items;
     dim3 grid(cdiv(N, 256), B);   // one Gaussian per thread: the dependent load -> atomic -> store chain is pure latency
@@ -1277,43 +1055,6 @@ extern "C" int voge_bin_fill(const uint32_t* rects, const int64_t* tile_offsets,
     dim3 grid(cdiv(N, 256), B);   // one Gaussian per thread: the dependent load -> atomic -> store chain is pure latency
     bin_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(rects), tile_offsets, cursor,
                                                              B, N, cdiv(W, tile), cdiv(H, tile), tile, tile_list);
-    VOGE_LAUNCH_CHECK();
-    return 0;
-}
-
-extern "C" int voge_render_forward(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
-                                   const float* rays, const int64_t* tile_offsets, const int32_t* tile_list,
-                                   const uint32_t* rects, float thr_act, float absorptivity, int B, int N, int H,
-                                   int W, int K, int tile,
-                                   int32_t* out_idx, float* out_weight, float* out_len, int64_t* out_valid,
-                                   float* out_act, float* out_dsd, uint64_t* stats, voge_stream_t stream) {
-    using namespace voge;
-    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
-    RenderArgs a;
-    a.verts = verts; a.sigmas = sigmas; a.origins = origins; a.rays = rays; a.tile_offsets = tile_offsets;
-    a.tile_list = tile_list; a.rects = reinterpret_cast<const uint2*>(rects); a.cap = 0; a.thr_act = thr_act; a.omega = absorptivity; a.B = B; a.N = N; a.H = H; a.W = W; a.K = K;
-    a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
-    a.out_idx = out_idx; a.out_weight = out_weight; a.out_len = out_len; a.out_valid = out_valid;
-    a.out_act = out_act; a.out_dsd = out_dsd; a.stats = reinterpret_cast<unsigned long long*>(stats);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (sigma_kind == 1) return dispatch_render<1>(a, s);
-    if (sigma_kind == 3) return dispatch_render<3>(a, s);
-    if (sigma_kind == 9) return dispatch_render<9>(a, s);
-    return (int)cudaErrorInvalidValue;
-}
-
-extern "C" int voge_render_backward(const float* verts, const float* sigmas, int sigma_kind, const float* origins,
-                                    const float* rays, const int32_t* idx, const int64_t* valid,
-                                    const float* grad_len, const float* grad_act, const float* grad_dsd, int B,
-                                    int N, int H, int W, int K,
-                                    float* grad_verts, float* grad_sigmas, voge_stream_t stream) {
-    using namespace voge;
-    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
-    RenderBwdArgs a{verts, sigmas, sigma_kind, origins, rays, idx, valid, grad_len, grad_act, grad_dsd, B, N, H, W, K,
-                    grad_verts, grad_sigmas};
-    const int64_t warps = (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
-    const int64_t grid = (warps * 32 + 255) / 256;
-    render_bwd_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a);
     VOGE_LAUNCH_CHECK();
     return 0;
 }

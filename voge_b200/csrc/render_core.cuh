@@ -134,6 +134,89 @@ __device__ __forceinline__ Hit exact_hit_packed(const float* __restrict__ gp, in
     return exact_pair_diag(m0, m1, m2, S[0], S[4], S[8], d0, d1, d2);
 }
 
+// ---- closed-form ray generator (reference Renderer.py:124-128: NDCMultinomialRaysampler with unit directions on a
+// screen-space PerspectiveCameras; semantics SURVEY.md 8c) -------------------------------------------------
+// d = R . normalize(a, b, 1),  a = -(x + .5 - px) / fx,  b = -(y + .5 - py) / fy   (pytorch3d view frame: +X left,
+// +Y up, +Z forward; row-vector convention X_view = X_world R + T, so d_world = R d_cam).
+// ONE definition, written with explicit roundings, shared by voge_generate_rays (materialised (B,H,W,3) rays for
+// the op-by-op ops and the oracle) and by the fused kernels (rays never materialised): every kernel sees the same
+// bits for the same pixel.  Per-view camera record `cam` (B,16) f32 = [R row-major (9), fx, fy, px, py, 0, 0, 0].
+struct ViewCam {
+    float R[9];
+    float ifx, ify, cx, cy;   // 1/fx, 1/fy, px - .5, py - .5
+};
+
+__device__ __forceinline__ ViewCam load_view_cam(const float* __restrict__ cam, int b) {
+    const float* c = cam + 16 * (int64_t)b;
+    ViewCam v;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) v.R[i] = c[i];
+    v.ifx = __fdiv_rn(1.f, c[9]);
+    v.ify = __fdiv_rn(1.f, c[10]);
+    v.cx = __fsub_rn(c[11], 0.5f);
+    v.cy = __fsub_rn(c[12], 0.5f);
+    return v;
+}
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// camera-frame unit direction (dc) of pixel (x, y)
+__device__ __forceinline__ void gen_ray_cam(const ViewCam& v, int x, int y, float& a, float& b, float& inv) {
+    a = __fmul_rn(__fsub_rn(v.cx, (float)x), v.ifx);
+    b = __fmul_rn(__fsub_rn(v.cy, (float)y), v.ify);
+    inv = rsqrt_approx(__fmaf_rn(a, a, __fmaf_rn(b, b, 1.f)));
+}
+
+__device__ __forceinline__ void gen_ray(const ViewCam& v, int x, int y, float& d0, float& d1, float& d2) {
+    float a, b, inv;
+    gen_ray_cam(v, x, y, a, b, inv);
+    const float c0 = __fmul_rn(a, inv), c1 = __fmul_rn(b, inv);
+    d0 = __fmaf_rn(v.R[2], inv, __fmaf_rn(v.R[1], c1, __fmul_rn(v.R[0], c0)));
+    d1 = __fmaf_rn(v.R[5], inv, __fmaf_rn(v.R[4], c1, __fmul_rn(v.R[3], c0)));
+    d2 = __fmaf_rn(v.R[8], inv, __fmaf_rn(v.R[7], c1, __fmul_rn(v.R[6], c0)));
+}
+
+// ray of pixel (x, y) of view b: read from the (B,H,W,3) tensor when one is given (user-supplied rays, pytorch3d
+// cameras), generated otherwise
+__device__ __forceinline__ void pixel_ray(const float* __restrict__ rays, const float* __restrict__ cam, int b, int x,
+                                          int y, int H, int W, float& d0, float& d1, float& d2) {
+    if (rays != nullptr) {
+        const int64_t r = ((int64_t)b * H + y) * W + x;
+        d0 = rays[r * 3 + 0]; d1 = rays[r * 3 + 1]; d2 = rays[r * 3 + 2];
+    } else {
+        const ViewCam v = load_view_cam(cam, b);
+        gen_ray(v, x, y, d0, d1, d2);
+    }
+}
+
+// Chain rule of the generator: d/d(ray direction) of one pixel -> its contribution to d/d(cam record)
+// [dR (9), dfx, dfy, dpx, dpy] (the fused backward sums these per view: the reference's grad_rays,
+// RayTracing.py:179-206, carried on to R / focal by autograd through pytorch3d's ray sampler).
+__device__ __forceinline__ void gen_ray_backward(const ViewCam& v, int x, int y, float g0, float g1, float g2,
+                                                 float* out13) {
+    float a, b, inv;
+    gen_ray_cam(v, x, y, a, b, inv);
+    const float c0 = a * inv, c1 = b * inv, c2 = inv;
+    out13[0] = g0 * c0; out13[1] = g0 * c1; out13[2] = g0 * c2;
+    out13[3] = g1 * c0; out13[4] = g1 * c1; out13[5] = g1 * c2;
+    out13[6] = g2 * c0; out13[7] = g2 * c1; out13[8] = g2 * c2;
+    // g_dc = R^T g ; through the normalisation dc = v / |v|, v = (a, b, 1): g_v = (g_dc - dc (dc . g_dc)) / |v|
+    const float h0 = v.R[0] * g0 + v.R[3] * g1 + v.R[6] * g2;
+    const float h1 = v.R[1] * g0 + v.R[4] * g1 + v.R[7] * g2;
+    const float h2 = v.R[2] * g0 + v.R[5] * g1 + v.R[8] * g2;
+    const float dot = c0 * h0 + c1 * h1 + c2 * h2;
+    const float ga = (h0 - c0 * dot) * inv, gb = (h1 - c1 * dot) * inv;
+    // a = (px - .5 - x) / fx:  da/dpx = 1/fx, da/dfx = -a/fx
+    out13[9] = -ga * a * v.ifx;
+    out13[10] = -gb * b * v.ify;
+    out13[11] = ga * v.ifx;
+    out13[12] = gb * v.ify;
+}
+
 // Every tile owns kBinSub counters / list segments (entry g goes to segment g % kBinSub): L2 serialises atomics
 // on one address, and a C5 tile receives several hundred entries per view.  The segments of a tile are
 // adjacent, so a tile's list is tile_offsets[tile * kBinSub] .. tile_offsets[(tile + 1) * kBinSub].

@@ -271,7 +271,8 @@ static int launch_select(const SelectArgs& a, cudaStream_t stream) {
 struct BlendArgs {
     const float* gauss;           // packed records (voge_pack_gaussians)
     const float* origins;
-    const float* rays;
+    const float* rays;            // (B,H,W,3), or NULL: generated from `cam`
+    const float* cam;             // (B,16) per-view camera records (render_core.cuh), read when rays == NULL
     const int32_t* idx;           // (B,H,W,K) packed, first valid[r] slots
     const int64_t* valid;         // (B,H,W)
     float omega;
@@ -330,7 +331,8 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const BlendArgs a) {
         return;
     }
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
-    const float r0 = a.rays[ray * 3 + 0], r1 = a.rays[ray * 3 + 1], r2 = a.rays[ray * 3 + 2];
+    float r0, r1, r2;
+    pixel_ray(a.rays, a.cam, b, xi, yi, a.H, a.W, r0, r1, r2);
     const int pack_off = (a.view_base + b) * a.N;
     float s_min = 3.0e38f;
     for (int k0 = 0; k0 < a.K; k0 += 4) {
@@ -454,7 +456,8 @@ __global__ void __launch_bounds__(NT) blend_pair_kernel(const BlendArgs a) {
         return;
     }
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
-    const float r0 = a.rays[ray * 3 + 0], r1 = a.rays[ray * 3 + 1], r2 = a.rays[ray * 3 + 2];
+    float r0, r1, r2;
+    pixel_ray(a.rays, a.cam, b, xi, yi, a.H, a.W, r0, r1, r2);
     const int pack_off = (a.view_base + b) * a.N;
     float s_min = 3.0e38f;
     // ---- exact (len, act, dsd) of this thread's slots ----
@@ -574,13 +577,14 @@ extern "C" int voge_select_topk(const int32_t* counts, const int64_t* seg_base, 
 }
 
 extern "C" int voge_blend_weights(const float* gauss, int sigma_kind, const float* origins,
-                                  const float* rays, const int32_t* idx, const int64_t* valid, float absorptivity,
+                                  const float* rays, const float* cam, const int32_t* idx, const int64_t* valid, float absorptivity,
                                   int view_base, int B, int N, int H, int W, int K, float* out_weight, float* out_len,
                                   float* out_act, float* out_dsd, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
     BlendArgs a;
-    a.gauss = gauss; a.origins = origins; a.rays = rays; a.idx = idx; a.valid = valid;
+    if (rays == nullptr && cam == nullptr) return (int)cudaErrorInvalidValue;
+    a.gauss = gauss; a.origins = origins; a.rays = rays; a.cam = cam; a.idx = idx; a.valid = valid;
     a.omega = absorptivity; a.B = B; a.N = N; a.H = H; a.W = W; a.K = K; a.view_base = view_base;
     a.out_weight = out_weight; a.out_len = out_len; a.out_act = out_act; a.out_dsd = out_dsd;
     cudaStream_t s = (cudaStream_t)stream;

@@ -28,7 +28,8 @@ namespace voge {
 struct TraceArgs {
     const float* gauss;                // packed records (voge_pack_gaussians)
     const float* origins;              // (B,3)
-    const float* rays;                 // (B,H,W,3)
+    const float* rays;                 // (B,H,W,3), or NULL: generated from `cam` (render_core.cuh: gen_ray)
+    const float* cam;                  // (B,16) per-view camera records, read when rays == NULL
     const int64_t* tile_offsets;       // (B*TY*TX*kBinSub + 1) into tile_list
     const int32_t* tile_list;          // local Gaussian indices
     const uint2* rects;                // (B,N) conservative pixel rectangles from bin_count_kernel
@@ -109,10 +110,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
     {
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-        if (live) {
-            const int64_t ray = ((int64_t)b * a.H + yi) * a.W + xi;
-            r0 = a.rays[ray * 3 + 0]; r1 = a.rays[ray * 3 + 1]; r2 = a.rays[ray * 3 + 2];
-        }
+        if (live) pixel_ray(a.rays, a.cam, b, xi, yi, a.H, a.W, r0, r1, r2);
         s_ray[tid] = r0; s_ray[NT + tid] = r1; s_ray[2 * NT + tid] = r2;
     }
     for (int i = tid; i < 17 * 17; i += NT) s_diff[i] = 0;
@@ -327,14 +325,15 @@ static int dispatch_trace(const TraceArgs& a, cudaStream_t s) {
 extern "C" int voge_trace_threads(int tile) { return voge::tile_threads(tile); }
 
 extern "C" int voge_trace_hits(const float* gauss, int sigma_kind, const float* origins,
-                               const float* rays, const int64_t* tile_offsets, const int32_t* tile_list,
+                               const float* rays, const float* cam, const int64_t* tile_offsets, const int32_t* tile_list,
                                const uint32_t* rects, const int64_t* tile_item_offsets, int64_t item_base, float thr_act, int B, int N,
                                int H, int W, int tile, int32_t* counts, int64_t* seg_base, uint32_t* hits,
                                uint64_t* stats, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     TraceArgs a;
-    a.gauss = gauss; a.origins = origins; a.rays = rays; a.tile_offsets = tile_offsets;
+    if (rays == nullptr && cam == nullptr) return (int)cudaErrorInvalidValue;
+    a.gauss = gauss; a.origins = origins; a.rays = rays; a.cam = cam; a.tile_offsets = tile_offsets;
     a.tile_list = tile_list; a.rects = reinterpret_cast<const uint2*>(rects); a.tile_item_offsets = tile_item_offsets;
     a.item_base = item_base;
     a.thr_act = thr_act; a.B = B; a.N = N; a.H = H; a.W = W; a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);

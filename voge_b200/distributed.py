@@ -39,26 +39,73 @@ def shard_views(n_views: int, rank: int, world: int) -> Tuple[int, int]:
     return first, count
 
 
+class GradientBucket:
+    """ONE persistent flat fp32 buffer [d verts ; d sigmas ; d colours ...] whose slices ARE the `.grad` tensors
+    of the parameters: autograd accumulates every view's gradient straight into it (AccumulateGrad adds in place
+    into an existing `.grad`), and the fitting step's only collective is one in-place all-reduce of the buffer --
+    no concatenation before, no copy back after.  Use `zero()` instead of `p.grad = None` between steps."""
+
+    def __init__(self, params: Sequence[torch.Tensor]):
+        self.params = list(params)
+        if not self.params:
+            raise ValueError("GradientBucket needs at least one parameter")
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(self.params, sizes):
+                if p.dtype != torch.float32 or p.device != dev:
+                    raise ValueError("GradientBucket: parameters must be float32 on one device")
+                view = self.flat[off:off + n].view(p.shape)
+                if p.grad is not None:
+                    view.copy_(p.grad)
+                p.grad = view
+                off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+    def attached(self) -> bool:
+        """False if somebody replaced a `.grad` (e.g. optimizer.zero_grad(set_to_none=True)); re-create then."""
+        base = self.flat.data_ptr()
+        off = 0
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != base + 4 * off:
+                return False
+            off += p.numel()
+        return True
+
+    def allreduce(self, average: bool = False, async_op: bool = False):
+        """Sum (or average) over all ranks, in place.  async_op=True returns the work handle (the collective
+        runs on the process group's own stream behind the work already queued on the current stream)."""
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+            return None
+        if not self.attached():
+            raise RuntimeError("GradientBucket: a parameter's .grad no longer aliases the bucket")
+        op = dist.ReduceOp.AVG if (average and dist.get_backend() == "nccl") else dist.ReduceOp.SUM
+        work = dist.all_reduce(self.flat, op=op, async_op=async_op)
+        if average and op == dist.ReduceOp.SUM:
+            if work is not None:
+                work.wait()
+                work = None
+            self.flat /= dist.get_world_size()
+        return work
+
+
 def allreduce_gradients(params: Sequence[torch.Tensor], average: bool = False):
     """Sum (or average) the .grad of `params` over all ranks with ONE all-reduce on a flat fp32
     bucket [d verts ; d sigmas ; d colours ...].  Parameters without a gradient contribute zeros so
-    that every rank issues the same collective."""
+    that every rank issues the same collective.  One-shot form of GradientBucket (which keeps the bucket
+    between steps and avoids the gather / scatter copies): afterwards the .grad tensors alias the bucket."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
-        return
-    grads = []
+        return None
     for p in params:
         if p.grad is None:
             p.grad = torch.zeros_like(p)
-        grads.append(p.grad)
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    if average:
-        flat /= dist.get_world_size()
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
+    bucket = GradientBucket(params)
+    bucket.allreduce(average=average)
+    return bucket
 
 
 def max_over_ranks(value: float, device=None) -> float:

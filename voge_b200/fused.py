@@ -1,11 +1,16 @@
 """Fused renderer path: one autograd Function for GaussianRenderer.forward's whole chain
-(reference Renderer.py:130-150: camera-centred copies -> ray_tracing -> aggregation).
+(reference Renderer.py:124-150: ray generation -> camera-centred copies -> ray_tracing -> aggregation).
 
-Forward : per-view tile culling (voge_bin_count / voge_bin_fill) -> voge_render_forward
+Forward : voge_pack_gaussians (S = 2 sigma | 2 inverse(sigma) | 2 L L^T) -> per-view tile culling
+          (voge_bin_count / voge_bin_fill) -> voge_trace_hits -> voge_select_topk -> voge_blend_weights
 Backward: voge_render_backward_fused -- recompute the hits, analytic blend backward, chain rule straight
-          into (N,3) / compact-sigma gradients for all views of the batch, plus d/d(rays), d/d(origins) when
-          the camera requires grad (the reference materialises
-          (B*N,3) and (B*N,3,3) gradient tensors and differentiates ~15 PyTorch ops over (R,K,K)).
+          into packed per-Gaussian gradients for all views of the batch -> voge_unpack_gradients (chain rule of
+          the sigma parameterisation), plus d/d(origins) and d/d(camera record) = d/dR, d/dfocal, d/dprincipal
+          reduced per view inside the kernel when the camera requires grad (the reference materialises
+          (B*N,3), (B*N,3,3) and (B,H,W,3) gradient tensors and differentiates ~15 PyTorch ops over (R,K,K)).
+
+For the built-in closed-form camera the (B,H,W,3) rays are never materialised: every kernel generates the ray
+of its pixel from the (B,16) camera records (csrc/render_core.cuh: gen_ray).
 """
 import math
 
@@ -28,47 +33,94 @@ def choose_tile(bin_size, K, use_ref_bins):
 
 class _RenderFused(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, verts, sigmas, origins, rays, R, T, focal, principal, image_size, thr, absorptivity, K,
-                use_ref_bins, bin_size):
+    def forward(ctx, verts, sigmas, origins, rays, cam, R, T, focal, principal, image_size, thr, absorptivity, K,
+                use_ref_bins, bin_size, sigma_mode):
         thr_act = -math.log(thr + 1e-10)                       # RayTracing.py:85
         tile = choose_tile(bin_size, K, use_ref_bins)
-        offsets, tile_list, rects, item_offsets = _C.bin_views(verts, sigmas, R, T, origins, focal, principal,
-                                                               image_size, thr, thr_act, use_ref_bins, bin_size, tile)
-        gauss = _C.pack_gaussians(verts, sigmas)     # (N, 4|8|12) aligned records shared by forward and backward
-        idx, weight, tlen, valid, _, _ = _C.render_forward(verts, sigmas, origins, rays, offsets, tile_list, rects,
+        # (N, 4|8|12) aligned records shared by binning, forward and backward
+        gauss = _C.pack_gaussians(verts, sigmas, sigma_mode)
+        offsets, tile_list, rects, item_offsets = _C.bin_views(None, None, R, T, origins, focal, principal, image_size,
+                                                               thr, thr_act, use_ref_bins, bin_size, tile, gauss=gauss)
+        idx, weight, tlen, valid, _, _ = _C.render_forward(None, None, origins, rays, offsets, tile_list, rects,
                                                            thr_act, absorptivity, K, tile, need_act=False,
-                                                           item_offsets=item_offsets, gauss=gauss)
-        if verts.requires_grad or sigmas.requires_grad or origins.requires_grad or rays.requires_grad:
+                                                           item_offsets=item_offsets, gauss=gauss, cam=cam,
+                                                           image_size=image_size)
+        if any(ctx.needs_input_grad[:5]):
             # recompute-not-store: only the inputs and the returned weights (which the caller's Fragments keep
             # alive anyway) are saved; the backward re-evaluates the K hits per pixel from idx (the reference
             # saves mus, isigmas (B*N copies), rays, sel_idx and the PyTorch aggregation ~10 (R,K,K) tensors)
-            ctx.save_for_backward(verts, sigmas, origins, rays, weight)
+            ctx.save_for_backward(verts, sigmas, origins, rays, cam, weight)
             # idx / valid are handed out as Fragments.vert_index / valid_num and merge_final rewrites
             # vert_index in place (-1 -> 0, reference Aggregation.py:131; the reference clones the
             # tensor for that reason, Renderer.py:145).  They are kept outside autograd's version
             # tracking instead of cloned: the backward only reads the first valid_num slots.
             ctx.idx, ctx.valid, ctx.gauss = idx, valid, gauss
         ctx.absorptivity = float(absorptivity)
+        ctx.sigma_mode = int(sigma_mode)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(idx, valid)
         return weight, idx, valid, tlen
 
     @staticmethod
     def backward(ctx, g_weight, _g_idx, _g_valid, g_len_out):
-        verts, sigmas, origins, rays, weight = ctx.saved_tensors
+        verts, sigmas, origins, rays, cam, weight = ctx.saved_tensors
         if g_weight is None:
             g_weight = torch.zeros(ctx.idx.shape, dtype=torch.float32, device=ctx.idx.device)
-        # camera gradients (pose optimisation): d/d(origins), d/d(rays) come out of the same kernel and flow
-        # on to R, T, focal through the ray generator's autograd graph (voge_b200/cameras.py)
-        g_verts, g_sig, g_rays, g_org = _C.render_backward_fused(
+        # camera gradients (pose optimisation): d/d(origins) and d/d(rays) or d/d(cam record) come out of the same
+        # kernel; the tiny (B,.) tensors flow on to R, T, focal through plain autograd
+        g_verts, g_sig, g_rays, g_org, g_cam = _C.render_backward_fused(
             verts, sigmas, origins, rays, ctx.idx, ctx.valid, g_weight.contiguous(), g_len_out, ctx.absorptivity,
             need_sigma=ctx.needs_input_grad[1], need_rays=ctx.needs_input_grad[3], need_origins=ctx.needs_input_grad[2],
-            gauss=ctx.gauss, weight=weight)
-        return (g_verts, g_sig, g_org, g_rays) + (None,) * 10
+            gauss=ctx.gauss, weight=weight, cam=cam, need_cam=ctx.needs_input_grad[4], sigma_mode=ctx.sigma_mode)
+        return (g_verts, g_sig, g_org, g_rays, g_cam) + (None,) * 11
 
 
-def render_fused(verts, sigmas, origins, rays, R, T, focal, principal, image_size, thr, absorptivity, K,
-                 use_ref_bins, bin_size):
-    """-> (vert_weight, vert_index (packed, -1 padded), valid_num i64, vert_hit_length)."""
-    return _RenderFused.apply(verts, sigmas, origins, rays, R, T, focal, principal, tuple(image_size), float(thr),
-                              float(absorptivity), int(K), bool(use_ref_bins), int(bin_size))
+def render_fused(verts, sigmas, origins, rays, cam, R, T, focal, principal, image_size, thr, absorptivity, K,
+                 use_ref_bins, bin_size, sigma_mode=0):
+    """-> (vert_weight, vert_index (packed, -1 padded), valid_num i64, vert_hit_length).
+    rays (B,H,W,3) or None (generated in the kernels from cam (B,16) = _C.make_cam(R, focal, principal))."""
+    return _RenderFused.apply(verts, sigmas, origins, rays, cam, R, T, focal, principal, tuple(image_size),
+                              float(thr), float(absorptivity), int(K), bool(use_ref_bins), int(bin_size),
+                              int(sigma_mode))
+
+
+class _GenerateRays(torch.autograd.Function):
+    """Materialised rays of the closed-form camera for the op-by-op entry points: forward = voge_generate_rays
+    (the same device function the fused kernels evaluate per pixel, so both paths trace identical rays);
+    backward = the generator's chain rule (d = R normalize(a, b, 1), a = (px - .5 - x) / fx) in plain torch."""
+
+    @staticmethod
+    def forward(ctx, cam, image_size):
+        ctx.save_for_backward(cam)
+        ctx.image_size = image_size
+        return _C.generate_rays(cam, image_size)
+
+    @staticmethod
+    def backward(ctx, g):
+        (cam,) = ctx.saved_tensors
+        H, W = ctx.image_size
+        B = cam.shape[0]
+        Rm = cam[:, :9].reshape(B, 3, 3)
+        fx, fy, px, py = (cam[:, i].view(B, 1, 1) for i in (9, 10, 11, 12))
+        xs = torch.arange(W, dtype=torch.float32, device=cam.device).view(1, 1, W)
+        ys = torch.arange(H, dtype=torch.float32, device=cam.device).view(1, H, 1)
+        a = ((px - 0.5 - xs) / fx).expand(B, H, W)
+        b = ((py - 0.5 - ys) / fy).expand(B, H, W)
+        inv = torch.rsqrt(a * a + b * b + 1)
+        dc = torch.stack([a * inv, b * inv, inv], dim=-1)                       # (B,H,W,3)
+        g_R = torch.einsum('bhwi,bhwj->bij', g, dc)
+        h = torch.einsum('bij,bhwi->bhwj', Rm, g)                               # R^T g
+        gv = (h - dc * (dc * h).sum(-1, keepdim=True)) * inv.unsqueeze(-1)
+        ga, gb = gv[..., 0], gv[..., 1]
+        g_cam = torch.zeros_like(cam)
+        g_cam[:, :9] = g_R.reshape(B, 9)
+        g_cam[:, 9] = -(ga * a).sum((1, 2)) / fx.view(B)
+        g_cam[:, 10] = -(gb * b).sum((1, 2)) / fy.view(B)
+        g_cam[:, 11] = ga.sum((1, 2)) / fx.view(B)
+        g_cam[:, 12] = gb.sum((1, 2)) / fy.view(B)
+        return g_cam, None
+
+
+def generate_rays(cam, image_size):
+    """(B,H,W,3) unit ray directions of the closed-form camera records cam (B,16); differentiable."""
+    return _GenerateRays.apply(cam, (int(image_size[0]), int(image_size[1])))
