@@ -82,11 +82,14 @@ def test_coarse_matches_oracle(oracle, C):
     assert np.array_equal(bp.cpu().numpy(), bp_o)          # deterministic ascending order
     assert bc_o.max() > 20
     # overflow: first M kept, error raised
+    # overflow: the first M (ascending) are kept and the call carries on like the reference (which warns and drops a
+    # chunk, rasterize_coarse.cu:150-163); the blocking check that raises is opt-in
     with pytest.raises(RuntimeError):
         C.rasterize_points_coarse(ndc.reshape(-1, 3).to(DEV), first.to(DEV), nper.to(DEV), sc["image_size"],
-                                  radii.reshape(-1, 2).to(DEV), 10, 5)
+                                  radii.reshape(-1, 2).to(DEV), 10, 5, check_overflow=True)
     bp5 = C.rasterize_points_coarse(ndc.reshape(-1, 3).to(DEV), first.to(DEV), nper.to(DEV), sc["image_size"],
-                                    radii.reshape(-1, 2).to(DEV), 10, 5, check_overflow=False)
+                                    radii.reshape(-1, 2).to(DEV), 10, 5)
+    assert int(C.last_bin_counts.max()) > 5
     assert np.array_equal(bp5.cpu().numpy(), bp_o[..., :5])
 
 

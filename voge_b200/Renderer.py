@@ -293,7 +293,7 @@ def to_colored_background(fragments: Fragments, colors: torch.Tensor,
     """min(sum_k w_k colour[idx_k] + (1 - silhouette) * background, 1) -- one fused gather-blend kernel
     (the reference chains get_silhouette, interpolate_attr and four elementwise ops, :162-171)."""
     if not torch.is_tensor(background_color):
-        background_color = torch.tensor(list(background_color), dtype=torch.float32)
+        background_color = torch.as_tensor(background_color, dtype=torch.float32)
     background_color = background_color.to(device=colors.device, dtype=torch.float32).reshape(-1)
     C = int(colors.shape[-1])
     if background_color.numel() == 1:
