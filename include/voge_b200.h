@@ -109,11 +109,13 @@ int voge_aggregation_backward(const float* act, const float* len, const float* d
  * idx_mod > 0 maps packed indices (b*N+n) onto attr rows with idx % idx_mod; attr has n_attr
  * rows and indices >= n_attr are ignored (the reference asserts on the host, :120).
  * attr_padded4 != 0 (C <= 4 only): attr is an (n_attr,4) zero-padded table, fetched with one 16-byte
- * load per hit (every lane of a warp gathers a different row).                              */
+ * load per hit (every lane of a warp gathers a different row).
+ * sat_code (optional, (R,) uint8, C <= 4 with a background): per channel c two bits at 2c telling where the
+ * final min(x, 1) clamped -- 2: x < 1, 1: x == 1, 0: x > 1 -- i.e. twice the factor the backward applies.       */
 int voge_merge_final(const float* attr, const float* weight, const int32_t* idx,
                      const int64_t* valid_num, const float* background, float mask_thr,
                      int64_t R, int K, int C, int idx_mod, int n_attr, int attr_padded4,
-                     float* out, voge_stream_t stream);
+                     float* out, uint8_t* sat_code, voge_stream_t stream);
 
 /* Backward of voge_merge_final: grad_attr must be ZEROED by the caller and is accumulated into;
  * its layout is (n_attr,C), or -- packed4 != 0 and C <= 4 -- (n_attr,4) zero-padded rows so that one
@@ -265,6 +267,22 @@ int voge_render_backward_fused(const float* gauss, int sigma_kind,
                                int B, int N, int H, int W, int K,
                                float* grad_packed, int need_sigma, float* grad_rays, float* grad_origins,
                                const float* cam, float* grad_cam, voge_stream_t stream);
+
+/* The same backward with merge_final's backward folded in ("image mode", K <= 112): the upstream gradient arrives on
+ * out = min(sum_k w_k attr[idx_k] + (1 - mask) background, 1) (Aggregation.py:111-141 + Renderer.py:153-176) instead
+ * of on the weights.  grad_out / fwd_out (B,H,W,C), C <= 4; attr4 (N,4) = attribute rows padded to 16 bytes;
+ * background (C) or NULL (plain interpolate_attr); mask_thr as voge_merge_final; weight = the forward's out_weight
+ * (required); sat_code (B,H,W) optional = voge_merge_final's clamp code of the same forward (else the kernel rebuilds the
+ * un-clamped composite of saturated pixels).  dL/dw_k is formed in registers (no (B,H,W,K) weight-gradient round trip through HBM) and dL/d(attr) is
+ * reduced by the same kernel into grad_attr4 (N,4), optional, ZEROED by the caller.  Everything else as
+ * voge_render_backward_fused.                                                                               */
+int voge_render_backward_image(const float* gauss, int sigma_kind, const float* origins, const float* rays,
+                               const float* cam, const int32_t* idx, const int64_t* valid_num,
+                               const float* weight, const float* grad_out, const float* fwd_out,
+                               const uint8_t* sat_code, const float* attr4, const float* background, float mask_thr, int C,
+                               float absorptivity, int B, int N, int H, int W, int K, float* grad_packed,
+                               int need_sigma, float* grad_attr4, float* grad_rays, float* grad_origins,
+                               float* grad_cam, voge_stream_t stream);
 
 #ifdef __cplusplus
 }

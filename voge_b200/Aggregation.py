@@ -122,13 +122,14 @@ def _attr_rows(vert_attr, vert_assign):
 
 
 def merge_final(vert_attr: torch.Tensor, weight: torch.Tensor, vert_assign: torch.Tensor, valid_num: torch.Tensor,
-                background=None, mask_thr: float = -1.0, idx_mod: int = 0):
+                background=None, mask_thr: float = -1.0, idx_mod: int = 0, fused_src=None):
     """out[..., :] = sum_{k < valid_num} weight[..., k] * vert_attr[vert_assign[..., k], :].
 
     Reference :111-141.  Like the reference this permanently rewrites `vert_assign` -1 -> 0 in place
     (:131).  `background` / `mask_thr` optionally fuse the composite of Renderer.to_colored_background;
     `idx_mod=N` folds packed multi-view indices b*N+n onto an (N, d) attribute table (extension: the
-    reference asserts out for B > 1)."""
+    reference asserts out for B > 1).  `fused_src`: provenance of fragments produced by the fused renderer path
+    (Fragments._fused_src); when given and applicable the backward is folded into the renderer's."""
     vert_attr = _attr_rows(vert_attr, vert_assign)
     if STRICT_INDEX_ASSERT:
         limit = vert_attr.shape[0] if idx_mod <= 0 else None
@@ -136,6 +137,11 @@ def merge_final(vert_attr: torch.Tensor, weight: torch.Tensor, vert_assign: torc
             assert limit > vert_assign.max()
     with torch.no_grad():
         vert_assign.clamp_(min=0)   # reference :131, done before the tensor is saved for backward
+    # fragments straight from the fused renderer (`fused_src`, set by GaussianRenderer): one autograd node whose
+    # backward is the renderer's fused backward with this gather-blend's backward folded in (voge_b200/fused.py)
+    from . import fused as _fused
+    if _fused.image_fusion_applies(fused_src, vert_attr, weight, vert_assign, valid_num, background, idx_mod):
+        return _fused.render_image(fused_src, vert_attr, background, mask_thr, idx_mod)
     return _MergeFinal.apply(vert_attr, weight, vert_assign, valid_num, background, float(mask_thr), int(idx_mod))
 
 

@@ -32,9 +32,13 @@ class Fragments(object):
         self.points_per_view = points_per_view
 
     def _map(self, fn):
-        return Fragments(vert_weight=fn(self.vert_weight), vert_index=fn(self.vert_index),
-                         valid_num=fn(self.valid_num), vert_hit_length=fn(self.vert_hit_length),
-                         points_per_view=self.points_per_view)
+        out = Fragments(vert_weight=fn(self.vert_weight), vert_index=fn(self.vert_index),
+                        valid_num=fn(self.valid_num), vert_hit_length=fn(self.vert_hit_length),
+                        points_per_view=self.points_per_view)
+        src = getattr(self, '_fused_src', None)
+        if src is not None:      # honoured only if the mapped tensors are still the renderer's own objects (copy())
+            out._fused_src = src
+        return out
 
     def __getitem__(self, item):
         assert len(self.valid_num.shape) == 3, 'Index access is only available when batched.'
@@ -156,12 +160,14 @@ class GaussianRenderer(nn.Module):
         else:
             cam = None
         M = st['max_point_per_bin']
-        w, idx, valid, ln = render_fused(verts[0], sigmas, origins, rays, cam, R, T, focal, principal, map_size,
-                                         st['thr_activation'], st['absorptivity'], st['max_assign'],
-                                         use_ref_bins=(M != -1), bin_size=default_bin_size(map_size),
-                                         sigma_mode=self._sigma_mode())
-        return Fragments(vert_weight=w, vert_index=idx, valid_num=valid, vert_hit_length=ln,
+        w, idx, valid, ln, src = render_fused(verts[0], sigmas, origins, rays, cam, R, T, focal, principal, map_size,
+                                              st['thr_activation'], st['absorptivity'], st['max_assign'],
+                                              use_ref_bins=(M != -1), bin_size=default_bin_size(map_size),
+                                              sigma_mode=self._sigma_mode(), with_source=True)
+        frag = Fragments(vert_weight=w, vert_index=idx, valid_num=valid, vert_hit_length=ln,
                          points_per_view=verts.shape[1])
+        frag._fused_src = src          # lets interpolate_attr / to_*_background fold their backward into the renderer's
+        return frag
 
     def _rays_match_model(self, rays, origins, image_size):
         """Foreign camera objects (pytorch3d): the fused path culls with the closed-form pinhole model of
@@ -280,7 +286,8 @@ def _idx_mod(fragments, vert_attr):
 
 def interpolate_attr(fragments: Fragments, vert_attr: torch.Tensor):
     return merge_final(vert_attr=vert_attr, weight=fragments.vert_weight, valid_num=fragments.valid_num,
-                       vert_assign=fragments.vert_index, idx_mod=_idx_mod(fragments, vert_attr))
+                       vert_assign=fragments.vert_index, idx_mod=_idx_mod(fragments, vert_attr),
+                       fused_src=getattr(fragments, '_fused_src', None))
 
 
 def get_silhouette(fragments: Fragments):
@@ -307,7 +314,7 @@ def to_colored_background(fragments: Fragments, colors: torch.Tensor,
                            "feature maps with interpolate_attr and get_silhouette" % (MAX_BACKGROUND_CHANNELS, C))
     return merge_final(vert_attr=colors, weight=fragments.vert_weight, valid_num=fragments.valid_num,
                        vert_assign=fragments.vert_index, background=background_color.contiguous(), mask_thr=thr,
-                       idx_mod=_idx_mod(fragments, colors))
+                       idx_mod=_idx_mod(fragments, colors), fused_src=getattr(fragments, '_fused_src', None))
 
 
 def to_white_background(fragments: Fragments, colors: torch.Tensor, thr: float = -1):

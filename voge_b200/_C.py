@@ -269,8 +269,10 @@ def pad_attr4(attr):
     return out
 
 
-def merge_final_forward(attr, weight, idx, valid_num, background=None, mask_thr=-1.0, idx_mod=0, attr4=None):
-    """attr4: optional pad_attr4(attr) (used instead of attr when C <= 4)."""
+def merge_final_forward(attr, weight, idx, valid_num, background=None, mask_thr=-1.0, idx_mod=0, attr4=None,
+                        want_sat_code=False):
+    """attr4: optional pad_attr4(attr) (used instead of attr when C <= 4).  want_sat_code: also return the (R,) uint8
+    clamp code of the background composite (None when there is no background or C > 4)."""
     require_cuda(attr, weight, idx, valid_num)
     attr, weight, idx = f32c(attr), f32c(weight), i32c(idx)
     valid_num = valid_num.to(torch.int64).contiguous()
@@ -281,10 +283,13 @@ def merge_final_forward(attr, weight, idx, valid_num, background=None, mask_thr=
         out = torch.empty(tuple(idx.shape[:-1]) + (C,), dtype=torch.float32, device=dev)
         bg = f32c(background) if background is not None else None
         p4 = attr4 is not None and C <= 4
+        code = None
+        if want_sat_code and bg is not None and C <= 4:
+            code = torch.empty(tuple(idx.shape[:-1]), dtype=torch.uint8, device=dev)
         check(lib().voge_merge_final(ptr(attr4 if p4 else attr), ptr(weight), ptr(idx), ptr(valid_num), ptr(bg),
                                      float(mask_thr), R, K, C, int(idx_mod), int(attr.shape[0]), int(p4), ptr(out),
-                                     stream_of(attr)), "merge_final")
-    return out
+                                     ptr(code), stream_of(attr)), "merge_final")
+    return (out, code) if want_sat_code else out
 
 
 def merge_final_backward(attr, weight, idx, valid_num, grad_out, background=None, mask_thr=-1.0, idx_mod=0,
@@ -477,6 +482,13 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
     return idx, weight, tlen, valid, act, dsd
 
 
+def _bwd_flags(need_sigma):
+    """bit 0: sigma gradients wanted; bit 1: per-hit backward kernels.  The tile-aggregated backward
+    (csrc/render_bwd_agg.cuh) is opt-in (VOGE_AGG=1): it issues 8x fewer L2 reductions but runs at half the
+    occupancy, and measures 0.81 against 0.50 ms per C5 view (profiles/ncu_r2_backward.md)."""
+    return int(bool(need_sigma)) | (0 if os.environ.get("VOGE_AGG") == "1" else 2)
+
+
 def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_len_out, absorptivity,
                           need_sigma=True, need_rays=False, need_origins=False, gauss=None, weight=None,
                           cam=None, need_cam=False, sigma_mode=0):
@@ -502,11 +514,45 @@ def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_
         g_cam = torch.zeros((B, 16), dtype=torch.float32, device=dev) if (need_cam and rays is None) else None
         check(lib().voge_render_backward_fused(ptr(gauss), kind, ptr(origins), ptr(rays),
                                                ptr(idx), ptr(valid), ptr(g_weight), ptr(weight), ptr(g_len_out),
-                                               float(absorptivity), B, N, H, W, K, ptr(packed), int(bool(need_sigma)),
+                                               float(absorptivity), B, N, H, W, K, ptr(packed), _bwd_flags(need_sigma),
                                                ptr(g_rays), ptr(g_org), ptr(cam), ptr(g_cam), stream_of(verts)),
               "render_backward_fused")
         g_verts, g_sig = unpack_gradients(packed, gauss, sigmas, sigma_mode, need_sigma)
     return g_verts, g_sig, g_rays, g_org, g_cam
+
+
+def render_backward_image(verts, sigmas, origins, rays, idx, valid, weight, grad_out, fwd_out, attr4, background,
+                          mask_thr, absorptivity, sat_code=None, need_sigma=True, need_attr=True, need_rays=False, need_origins=False,
+                          gauss=None, cam=None, need_cam=False, sigma_mode=0, n_channels=3, need_geometry=True):
+    """Fused backward with merge_final's backward folded in (voge_render_backward_image): the gradient of the
+    composited image -> (g_verts, g_sigmas | None, g_attr (N,C) | None, g_rays | None, g_origins | None, g_cam | None)."""
+    verts, sigmas, origins = f32c(verts), f32c(sigmas), f32c(origins)
+    rays = f32c(rays) if rays is not None else None
+    cam = f32c(cam) if cam is not None else None
+    idx, weight, grad_out, attr4 = i32c(idx), f32c(weight), f32c(grad_out), f32c(attr4)
+    fwd_out = f32c(fwd_out) if fwd_out is not None else None
+    background = f32c(background) if background is not None else None
+    B, H, W, K = (int(s) for s in idx.shape)
+    N, C = int(verts.shape[0]), int(n_channels)
+    kind = sigma_kind(sigmas)
+    dev = verts.device
+    with torch.cuda.device(dev):
+        if gauss is None:
+            gauss = pack_gaussians(verts, sigmas, sigma_mode)
+        packed = torch.zeros((N, GAUSS_WIDTH[kind]), dtype=torch.float32, device=dev)
+        g_attr4 = torch.zeros((N, 4), dtype=torch.float32, device=dev) if need_attr else None
+        g_rays = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev) if (need_rays and rays is not None) else None
+        g_org = torch.zeros((B, 3), dtype=torch.float32, device=dev) if need_origins else None
+        g_cam = torch.zeros((B, 16), dtype=torch.float32, device=dev) if (need_cam and rays is None) else None
+        check(lib().voge_render_backward_image(ptr(gauss), kind, ptr(origins), ptr(rays), ptr(cam), ptr(idx), ptr(valid),
+                                               ptr(weight), ptr(grad_out), ptr(fwd_out), ptr(sat_code), ptr(attr4),
+                                               ptr(background),
+                                               float(mask_thr), C, float(absorptivity), B, N, H, W, K, ptr(packed),
+                                               _bwd_flags(need_sigma), ptr(g_attr4), ptr(g_rays), ptr(g_org), ptr(g_cam),
+                                               stream_of(verts)), "render_backward_image")
+        g_verts, g_sig = unpack_gradients(packed, gauss, sigmas, sigma_mode, need_sigma) if need_geometry else (None, None)
+    g_attr = g_attr4[:, :C].contiguous() if need_attr else None
+    return g_verts, g_sig, g_attr, g_rays, g_org, g_cam
 
 
 def unpack_gradients(packed, gauss, sigmas, sigma_mode=0, need_sigma=True):

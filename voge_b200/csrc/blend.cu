@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) merge_fwd_small_kernel(const float* __res
                                                               const int64_t* __restrict__ valid_num,
                                                               const float* __restrict__ background, float mask_thr,
                                                               int64_t R, int K, FastMod idx_mod, int n_attr,
-                                                              float* __restrict__ out) {
+                                                              float* __restrict__ out, uint8_t* __restrict__ sat_code) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const int nv = valid_num != nullptr ? (int)min((int64_t)K, valid_num[r]) : K;
@@ -325,8 +325,16 @@ __global__ void __launch_bounds__(256) merge_fwd_small_kernel(const float* __res
     if (background != nullptr) {
         const float sil = fminf(wsum, 1.f);                                      // Renderer.py:157-159
         const float mask = mask_thr > 0.f ? (sil > mask_thr ? 1.f : 0.f) : sil;  // :167-168
+        // where min(x, 1) clamps, per channel (2 bits: 2 = x < 1, 1 = x == 1, 0 = x > 1): the backward's factor
+        // min1_grad(x) = code / 2 without rebuilding x
+        unsigned code = 0u;
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = fminf(acc[c] + (1.f - mask) * background[c], 1.f);   // :171
+        for (int c = 0; c < C; ++c) {
+            const float x = acc[c] + (1.f - mask) * background[c];
+            code |= (x < 1.f ? 2u : (x == 1.f ? 1u : 0u)) << (2 * c);
+            acc[c] = fminf(x, 1.f);   // :171
+        }
+        if (sat_code != nullptr) sat_code[r] = (uint8_t)code;
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) out[r * C + c] = acc[c];
@@ -519,7 +527,7 @@ extern "C" int voge_aggregation_backward(const float* act, const float* len, con
 extern "C" int voge_merge_final(const float* attr, const float* weight, const int32_t* idx,
                                 const int64_t* valid_num, const float* background, float mask_thr,
                                 int64_t R, int K, int C, int idx_mod, int n_attr, int attr_padded4, float* out,
-                                voge_stream_t stream) {
+                                uint8_t* sat_code, voge_stream_t stream) {
     using namespace voge;
     if (R <= 0 || C <= 0) return 0;
     if (C <= 4) {
@@ -530,16 +538,16 @@ extern "C" int voge_merge_final(const float* attr, const float* weight, const in
     do {                                                                                                            \
         if (K % 4 == 0 && attr_padded4)                                                                             \
             merge_fwd_small_kernel<CC, true, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,  \
-                                                                        mask_thr, R, K, fm, n_attr, out);           \
+                                                                        mask_thr, R, K, fm, n_attr, out, sat_code); \
         else if (K % 4 == 0)                                                                                        \
             merge_fwd_small_kernel<CC, true, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
-                                                                         mask_thr, R, K, fm, n_attr, out);          \
+                                                                         mask_thr, R, K, fm, n_attr, out, sat_code);\
         else if (attr_padded4)                                                                                      \
             merge_fwd_small_kernel<CC, false, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
-                                                                         mask_thr, R, K, fm, n_attr, out);          \
+                                                                         mask_thr, R, K, fm, n_attr, out, sat_code);\
         else                                                                                                        \
             merge_fwd_small_kernel<CC, false, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,\
-                                                                          mask_thr, R, K, fm, n_attr, out);         \
+                                                                          mask_thr, R, K, fm, n_attr, out, sat_code);\
     } while (0)
         if (C == 1) VOGE_MF(1); else if (C == 2) VOGE_MF(2); else if (C == 3) VOGE_MF(3); else VOGE_MF(4);
 #undef VOGE_MF

@@ -292,6 +292,8 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__
 // (so neither act nor dsd is ever written to HBM by the forward), the blend is differentiated
 // analytically inside the depth window where the erf is not saturated, and the chain rule of
 // ray_trace_voge.cu:324-330 is applied straight into the (N,.) parameter gradients.
+constexpr int kMaxPairK = 112;   // two-threads-per-pixel backward up to this K (16 K bytes of shared memory per pixel)
+
 struct FusedBwdArgs {
     const float* gauss;      // packed records (voge_pack_gaussians)
     int kind;
@@ -310,11 +312,28 @@ struct FusedBwdArgs {
     float* grad_rays;        // optional (B,H,W,3), written in full: d/d(ray direction) (pose optimisation)
     float* grad_origins;     // optional (B,3), zeroed by the caller: d/d(ray origin) = -sum over the view's hits of d/d(mu')
     float* grad_cam;         // optional (B,16), zeroed by the caller, generated rays only: d/d(cam record) = the chain rule of
-                             // the ray generator summed over the view's pixels [dR (9), dfx, dfy, dpx, dpy, -, -, -]
+                             // the ray generator summed over the view's pixels [dR (9), dfx, dfy, dpx, dpy, -, -, -]    // "image mode" (render_bwd_pair_kernel<.., IMG = true>): the upstream gradient arrives on the composited image
+    // out = min(sum_k w_k attr[idx_k] + (1 - mask) background, 1) (Renderer.py:153-176, Aggregation.py:111-141)
+    // instead of on the weights: dL/dw_k is formed in registers and the attribute gradient is reduced from the same
+    // kernel, i.e. merge_final's backward is folded in (no (B,H,W,K) weight-gradient round trip through HBM)
+    const float* g_out;      // (B,H,W,C) dL/d(out), C <= 4
+    const float* fwd_out;    // (B,H,W,C) the forward's out (tells where min(., 1) saturated), or NULL
+    const uint8_t* sat_code; // (B,H,W) optional: voge_merge_final's per-channel clamp code (2 bits each); spares the rebuild
+    const float* attr4;      // (N,4) attribute rows padded to 16 bytes
+    const float* background; // (C) or NULL (plain interpolate_attr: no silhouette / clamp)
+    float mask_thr;          // > 0: hard silhouette mask (Renderer.py:167-168)
+    int C;
+    float* grad_attr4;       // optional (N,4), zeroed by the caller: dL/d(attr)
 };
 
-template <bool CAM>
-__device__ __forceinline__ void geom_grad_accumulate(const FusedBwdArgs& a, int g, float m0, float m1, float m2,
+// what geom_grad_accumulate needs of the kernel arguments (passed by value to out-of-line callers)
+struct GradSink {
+    float* grad_packed;
+    int kind, need_sigma;
+};
+
+template <bool CAM, typename ArgsT>
+__device__ __forceinline__ void geom_grad_accumulate(const ArgsT& a, int g, float m0, float m1, float m2,
                                                      const float* S, float d0, float d1, float d2, float ksk,
                                                      float msk, float gl, float ga, float gd, float* cam_acc) {
     const float g_ksk = (ga * msk - gl) * msk / (ksk * ksk) + gd;   // ray_trace_voge.cu:324-326
@@ -598,7 +617,10 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
 // Two threads per pixel (adjacent lanes; a warp covers a 4x4 pixel block): the per-pixel arrays in shared
 // memory bound the resident pixels per SM, and with one thread per pixel that left 20 warps of serial,
 // latency-bound work.  The pair shares the arrays; thread `sub` owns the slots k = sub, sub + 2, ... in every pass.
-template <int NT, int KIND, bool CAM>
+// torch.minimum-style subgradient of min(x, 1): 1 below, 1/2 at the tie, 0 above (as in blend.cu)
+__device__ __forceinline__ float min1_grad_r(float x) { return x < 1.f ? 1.f : (x == 1.f ? 0.5f : 0.f); }
+
+template <int NT, int KIND, bool CAM, bool IMG>
 __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(const FusedBwdArgs a) {
     constexpr int NP = NT / 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -628,9 +650,61 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
     const float omega = a.omega;
     float cam_acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d/d(ray), d/d(origin) partial sums of this thread's slots
     const int32_t* i_idx = a.idx + r * a.K;
-    const float* i_gw = a.g_weight + r * a.K;
+    const float* i_gw = IMG ? nullptr : a.g_weight + r * a.K;
     const int pack_off = b * a.N;
     const bool vec = (a.K & 3) == 0;
+
+    // ---- image mode: per-pixel upstream gradient of the gather-blend / background composite ----
+    // dL/dw_k = sum_c go_c attr[idx_k][c] - gB, with go_c = dL/dout_c through min(., 1) and gB the silhouette term
+    // (merge_bwd_small_kernel, blend.cu); both threads of the pair evaluate the same per-pixel values
+    float go[4] = {0.f, 0.f, 0.f, 0.f};
+    float gB = 0.f;
+    if (IMG && live) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < a.C) go[c] = a.g_out[r * a.C + c];
+        if (a.background != nullptr) {
+            const float* i_w = a.weight + r * a.K;
+            float wsum = 0.f;
+            for (int k = 0; k < cnt; ++k) wsum += i_w[k];       // slots behind valid_num hold zero weights
+            const float sil = fminf(wsum, 1.f);
+            const float mask = a.mask_thr > 0.f ? (sil > a.mask_thr ? 1.f : 0.f) : sil;
+            bool sat = a.fwd_out == nullptr;
+            if (a.sat_code != nullptr) {
+                // the forward recorded where min(., 1) clamped (voge_merge_final: sat_code): factor = code / 2 per channel
+                const unsigned code = a.sat_code[r];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < a.C) go[c] *= 0.5f * (float)((code >> (2 * c)) & 3u);
+                sat = false;
+            } else if (!sat) {
+                for (int c = 0; c < a.C; ++c) sat = sat || !(a.fwd_out[r * a.C + c] < 1.f);
+            }
+            if (sat) {
+                // min(x, 1) saturated in some channel: the factor needs the un-clamped composite x, rebuilt here
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int k = 0; k < cnt; ++k) {
+                    const int g = i_idx[k] - pack_off;
+                    if (g >= 0 && g < a.N) {
+                        const float4 av = __ldg(reinterpret_cast<const float4*>(a.attr4) + g);
+                        const float w = i_w[k];
+                        acc[0] = fmaf(w, av.x, acc[0]); acc[1] = fmaf(w, av.y, acc[1]);
+                        acc[2] = fmaf(w, av.z, acc[2]); acc[3] = fmaf(w, av.w, acc[3]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < a.C) go[c] *= min1_grad_r(acc[c] + (1.f - mask) * a.background[c]);
+            }
+            if (!(a.mask_thr > 0.f)) {
+                float gs = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < a.C) gs += go[c] * a.background[c];
+                gB = gs * min1_grad_r(wsum);
+            }
+        }
+    }
 
     // ---- pass 0: recompute this thread's hits (bit-faithful); w_m dL/dw_m from the forward's weights ----
     float s_min = 3.0e38f, total_gD = 0.f;
@@ -639,9 +713,11 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
         float wv[2] = {0.f, 0.f}, gwv[2] = {0.f, 0.f};
         if (vec) {
             const int4 q = *reinterpret_cast<const int4*>(i_idx + k0);
-            const float4 g4 = *reinterpret_cast<const float4*>(i_gw + k0);
             gv[0] = sub ? q.y : q.x; gv[1] = sub ? q.w : q.z;
-            gwv[0] = sub ? g4.y : g4.x; gwv[1] = sub ? g4.w : g4.z;
+            if (!IMG) {
+                const float4 g4 = *reinterpret_cast<const float4*>(i_gw + k0);
+                gwv[0] = sub ? g4.y : g4.x; gwv[1] = sub ? g4.w : g4.z;
+            }
             if (a.weight != nullptr) {
                 const float4 w4 = *reinterpret_cast<const float4*>(a.weight + r * a.K + k0);
                 wv[0] = sub ? w4.y : w4.x; wv[1] = sub ? w4.w : w4.z;
@@ -651,8 +727,26 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
             for (int jj = 0; jj < 2; ++jj) {
                 const int k = k0 + sub + 2 * jj;
                 if (k < cnt) {
-                    gv[jj] = i_idx[k]; gwv[jj] = i_gw[k];
+                    gv[jj] = i_idx[k];
+                    if (!IMG) gwv[jj] = i_gw[k];
                     if (a.weight != nullptr) wv[jj] = a.weight[r * a.K + k];
+                }
+            }
+        }
+        if (IMG) {
+            // the attribute rows of this thread's two slots: dL/dw from the image gradient, dL/d(attr) reduced here
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int k = k0 + sub + 2 * jj;
+                const int g = gv[jj] - pack_off;
+                if (k < cnt && g >= 0 && g < a.N) {
+                    const float4 av = __ldg(reinterpret_cast<const float4*>(a.attr4) + g);
+                    gwv[jj] = fmaf(go[3], av.w, fmaf(go[2], av.z, fmaf(go[1], av.y, go[0] * av.x))) - gB;
+                    if (a.grad_attr4 != nullptr && wv[jj] != 0.f)
+                        atomicAdd(reinterpret_cast<float4*>(a.grad_attr4) + g,
+                                  make_float4(wv[jj] * go[0], wv[jj] * go[1], wv[jj] * go[2], wv[jj] * go[3]));
+                } else {
+                    gwv[jj] = -gB;
                 }
             }
         }
@@ -801,6 +895,12 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
 
 }  // namespace voge
 
+#include "render_bwd_agg.cuh"
+
+namespace voge {
+static int launch_fused_backward(const FusedBwdArgs& a, bool image_mode, int flags, cudaStream_t s);
+}
+
 extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
                                           const float* origins, const float* rays, const int32_t* idx,
                                           const int64_t* valid, const float* grad_weight, const float* weight,
@@ -813,10 +913,59 @@ extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
     if (rays == nullptr && cam == nullptr) return (int)cudaErrorInvalidValue;
     if (grad_cam != nullptr && (rays != nullptr || cam == nullptr)) return (int)cudaErrorInvalidValue;
     FusedBwdArgs a{gauss, sigma_kind, origins, rays, cam, idx, valid, grad_weight, weight, grad_len_out, absorptivity,
-                   B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins, grad_cam};
+                   B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins, grad_cam,
+                   nullptr, nullptr, nullptr, nullptr, nullptr, -1.f, 0, nullptr};
+    a.need_sigma = need_sigma & 1;
+    return launch_fused_backward(a, false, need_sigma, (cudaStream_t)stream);
+}
+
+extern "C" int voge_render_backward_image(const float* gauss, int sigma_kind, const float* origins, const float* rays,
+                                          const float* cam, const int32_t* idx, const int64_t* valid,
+                                          const float* weight, const float* grad_out, const float* fwd_out,
+                                          const uint8_t* sat_code, const float* attr4, const float* background, float mask_thr, int C,
+                                          float absorptivity, int B, int N, int H, int W, int K, float* grad_packed,
+                                          int need_sigma, float* grad_attr4, float* grad_rays, float* grad_origins,
+                                          float* grad_cam, voge_stream_t stream) {
+    using namespace voge;
+    if (B <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+    if (rays == nullptr && cam == nullptr) return (int)cudaErrorInvalidValue;
+    if (grad_cam != nullptr && (rays != nullptr || cam == nullptr)) return (int)cudaErrorInvalidValue;
+    if (weight == nullptr || grad_out == nullptr || attr4 == nullptr || C < 1 || C > 4 || K > kMaxPairK)
+        return (int)cudaErrorInvalidValue;
+    FusedBwdArgs a{gauss, sigma_kind, origins, rays, cam, idx, valid, nullptr, weight, nullptr, absorptivity,
+                   B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins, grad_cam,
+                   grad_out, fwd_out, sat_code, attr4, background, mask_thr, C, grad_attr4};
+    a.need_sigma = need_sigma & 1;
+    return launch_fused_backward(a, true, need_sigma, (cudaStream_t)stream);
+}
+
+namespace voge {
+// flags: bit 0 = sigma gradients wanted, bit 1 = do not use the tile-aggregated kernel (A/B aid)
+static int launch_fused_backward(const FusedBwdArgs& a, bool image_mode, int flags, cudaStream_t s) {
+    const int sigma_kind = a.kind, B = a.B, H = a.H, W = a.W, K = a.K;
+    float* grad_rays = a.grad_rays; float* grad_origins = a.grad_origins; float* grad_cam = a.grad_cam;
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
-    cudaStream_t s = (cudaStream_t)stream;
     const bool cam_grads = grad_rays != nullptr || grad_origins != nullptr || grad_cam != nullptr;
+    if (!cam_grads && a.weight != nullptr && K <= kAggMaxK && !(flags & 2)) {
+        // per-tile Gaussian-major gradient reduction (render_bwd_agg.cuh): 8x8 pixel tiles, 128 threads
+        const int64_t grid = (int64_t)B * cdiv(W, 8) * cdiv(H, 8);
+        if (grid > 2147483647LL) return (int)cudaErrorInvalidValue;
+        const size_t smem = agg_smem_bytes(K);
+        auto go = [&](auto kernel) -> int {
+            VOGE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kernel<<<(unsigned)grid, kAggNT, smem, s>>>(a);
+            VOGE_LAUNCH_CHECK();
+            return 0;
+        };
+        if (image_mode) {
+            if (sigma_kind == 1) return go(render_bwd_agg_kernel<1, true>);
+            if (sigma_kind == 3) return go(render_bwd_agg_kernel<3, true>);
+            return go(render_bwd_agg_kernel<9, true>);
+        }
+        if (sigma_kind == 1) return go(render_bwd_agg_kernel<1, false>);
+        if (sigma_kind == 3) return go(render_bwd_agg_kernel<3, false>);
+        return go(render_bwd_agg_kernel<9, false>);
+    }
     auto launch = [&](auto kernel, int nt, int per_pixel) -> int {
         // per_pixel = 2: two threads per pixel, 4x4 pixel blocks per warp; 1: 8x4 blocks
         const int64_t warps = per_pixel == 2 ? (int64_t)B * cdiv(W, 4) * cdiv(H, 4) : (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
@@ -832,7 +981,8 @@ extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
     auto by_threads = [&](auto kind_tag, auto cam_tag) -> int {
         constexpr int KIND = decltype(kind_tag)::value;
         constexpr bool CAM = decltype(cam_tag)::value;
-        if (K <= 112) return launch(render_bwd_pair_kernel<128, KIND, CAM>, 128, 2);
+        if (image_mode) return launch(render_bwd_pair_kernel<128, KIND, CAM, true>, 128, 2);
+        if (K <= kMaxPairK) return launch(render_bwd_pair_kernel<128, KIND, CAM, false>, 128, 2);
         if (K <= 200) return launch(render_bwd_fused_kernel<64, KIND, CAM>, 64, 1);
         return launch(render_bwd_fused_kernel<32, KIND, CAM>, 32, 1);
     };
@@ -843,6 +993,7 @@ extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
     };
     return cam_grads ? by_kind(std::true_type{}) : by_kind(std::false_type{});
 }
+}  // namespace voge
 
 namespace voge {
 // ---- parameter records ---------------------------------------------------------------------------------------

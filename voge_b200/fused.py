@@ -34,11 +34,13 @@ def choose_tile(bin_size, K, use_ref_bins):
 class _RenderFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, verts, sigmas, origins, rays, cam, R, T, focal, principal, image_size, thr, absorptivity, K,
-                use_ref_bins, bin_size, sigma_mode):
+                use_ref_bins, bin_size, sigma_mode, holder=None):
         thr_act = -math.log(thr + 1e-10)                       # RayTracing.py:85
         tile = choose_tile(bin_size, K, use_ref_bins)
         # (N, 4|8|12) aligned records shared by binning, forward and backward
         gauss = _C.pack_gaussians(verts, sigmas, sigma_mode)
+        if holder is not None:
+            holder["gauss"] = gauss
         offsets, tile_list, rects, item_offsets = _C.bin_views(None, None, R, T, origins, focal, principal, image_size,
                                                                thr, thr_act, use_ref_bins, bin_size, tile, gauss=gauss)
         idx, weight, tlen, valid, _, _ = _C.render_forward(None, None, origins, rays, offsets, tile_list, rects,
@@ -72,16 +74,84 @@ class _RenderFused(torch.autograd.Function):
             verts, sigmas, origins, rays, ctx.idx, ctx.valid, g_weight.contiguous(), g_len_out, ctx.absorptivity,
             need_sigma=ctx.needs_input_grad[1], need_rays=ctx.needs_input_grad[3], need_origins=ctx.needs_input_grad[2],
             gauss=ctx.gauss, weight=weight, cam=cam, need_cam=ctx.needs_input_grad[4], sigma_mode=ctx.sigma_mode)
-        return (g_verts, g_sig, g_org, g_rays, g_cam) + (None,) * 11
+        return (g_verts, g_sig, g_org, g_rays, g_cam) + (None,) * 12
+
+
+class FusedSource(object):
+    """Provenance of fragments produced by the fused path: what voge_render_backward_image needs to differentiate
+    an image composited from them straight down to the Gaussian parameters (merge_final's backward folded into
+    the renderer's backward).  Attached to Fragments as `_fused_src`; it is honoured only while the fragment
+    tensors are the very objects the renderer returned."""
+    __slots__ = ("verts", "sigmas", "origins", "rays", "cam", "gauss", "sigma_mode", "absorptivity", "weight", "idx",
+                 "valid", "n_points", "K")
+
+    def matches(self, weight, idx, valid):
+        return weight is self.weight and idx is self.idx and valid is self.valid
 
 
 def render_fused(verts, sigmas, origins, rays, cam, R, T, focal, principal, image_size, thr, absorptivity, K,
-                 use_ref_bins, bin_size, sigma_mode=0):
-    """-> (vert_weight, vert_index (packed, -1 padded), valid_num i64, vert_hit_length).
+                 use_ref_bins, bin_size, sigma_mode=0, with_source=False):
+    """-> (vert_weight, vert_index (packed, -1 padded), valid_num i64, vert_hit_length) [, FusedSource].
     rays (B,H,W,3) or None (generated in the kernels from cam (B,16) = _C.make_cam(R, focal, principal))."""
-    return _RenderFused.apply(verts, sigmas, origins, rays, cam, R, T, focal, principal, tuple(image_size),
-                              float(thr), float(absorptivity), int(K), bool(use_ref_bins), int(bin_size),
-                              int(sigma_mode))
+    holder = {}
+    weight, idx, valid, tlen = _RenderFused.apply(verts, sigmas, origins, rays, cam, R, T, focal, principal,
+                                                  tuple(image_size), float(thr), float(absorptivity), int(K),
+                                                  bool(use_ref_bins), int(bin_size), int(sigma_mode), holder)
+    if not with_source:
+        return weight, idx, valid, tlen
+    src = FusedSource()
+    src.verts, src.sigmas, src.origins, src.rays, src.cam = verts, sigmas, origins, rays, cam
+    src.gauss, src.sigma_mode, src.absorptivity = holder.get("gauss"), int(sigma_mode), float(absorptivity)
+    src.weight, src.idx, src.valid, src.n_points, src.K = weight, idx, valid, int(verts.shape[0]), int(K)
+    return weight, idx, valid, tlen, src
+
+
+class _RenderImage(torch.autograd.Function):
+    """out = merge_final(attr, fragments) (+ background composite) for fragments of the fused path, differentiated
+    down to the Gaussian parameters in ONE kernel: voge_render_backward_image forms dL/dw in registers from the
+    image gradient, reduces dL/d(attr), and continues with the blend / geometry backward -- the (B,H,W,K)
+    weight gradient never exists in HBM and merge_final's own backward launch disappears."""
+
+    @staticmethod
+    def forward(ctx, attr, verts, sigmas, origins, rays, cam, background, src, mask_thr, idx_mod):
+        attr4 = _C.pad_attr4(attr)
+        out, code = _C.merge_final_forward(attr, src.weight.detach(), src.idx, src.valid, background, mask_thr, idx_mod,
+                                           attr4=attr4, want_sat_code=True)
+        ctx.save_for_backward(verts, sigmas, origins, rays, cam, attr4, out, background, code)
+        ctx.src, ctx.mask_thr, ctx.C = src, float(mask_thr), int(attr.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        verts, sigmas, origins, rays, cam, attr4, out, background, code = ctx.saved_tensors
+        src = ctx.src
+        need = ctx.needs_input_grad
+        g_verts, g_sig, g_attr, g_rays, g_org, g_cam = _C.render_backward_image(
+            verts, sigmas, origins, rays, src.idx, src.valid, src.weight.detach(), grad_out.contiguous(), out, attr4,
+            background, ctx.mask_thr, src.absorptivity, sat_code=code, need_sigma=need[2], need_attr=need[0], need_rays=need[4],
+            need_origins=need[3], gauss=src.gauss, cam=cam, need_cam=need[5], sigma_mode=src.sigma_mode,
+            n_channels=ctx.C)
+        return g_attr, g_verts, g_sig, g_org, g_rays, g_cam, None, None, None, None
+
+
+def image_fusion_applies(src, vert_attr, weight, vert_assign, valid_num, background, idx_mod):
+    import os
+    if src is None or os.environ.get("VOGE_NO_IMAGE_FUSION") == "1" or not torch.is_grad_enabled():
+        return False
+    if not (src.matches(weight, vert_assign, valid_num) and weight.requires_grad and src.gauss is not None):
+        return False
+    if not (vert_attr.is_cuda and vert_attr.dtype == torch.float32 and vert_attr.dim() == 2 and
+            vert_attr.shape[0] == src.n_points and 1 <= vert_attr.shape[1] <= 4 and src.K <= 112):
+        return False
+    if background is not None and background.requires_grad:
+        return False
+    n_views = weight.shape[0] if weight.dim() == 4 else 1
+    return idx_mod == src.n_points or (n_views == 1 and idx_mod == 0)
+
+
+def render_image(src, vert_attr, background, mask_thr, idx_mod):
+    return _RenderImage.apply(vert_attr, src.verts, src.sigmas, src.origins, src.rays, src.cam, background, src,
+                              float(mask_thr), int(idx_mod))
 
 
 class _GenerateRays(torch.autograd.Function):
