@@ -405,59 +405,6 @@ def test_image_backward_folded_into_renderer(case, monkeypatch):
         assert err < 2e-5, (case, name, err)
 
 
-@pytest.mark.parametrize("case", ["shared", "overflow"])
-def test_tile_aggregated_backward_equals_per_hit(case, monkeypatch):
-    """render_bwd_agg_kernel (per-tile Gaussian-major gradient reduction, K <= 24) against the per-hit kernels
-    (default; the aggregated kernel is opt-in, VOGE_AGG=1), weight-gradient and image modes.  "shared": wide Gaussians, ~10 hits per (Gaussian, tile);
-    "overflow": thousands of pixel-sized Gaussians so that an 8x8 tile meets more distinct Gaussians than the hash
-    table holds and the per-hit fallback inside the kernel runs too."""
-    from voge_b200.Meshes import GaussianMeshesNaive
-    from voge_b200.Renderer import get_silhouette, to_white_background
-    g = torch.Generator().manual_seed(61)
-    if case == "shared":
-        sc = small_scene(seed=59, aniso=True, n=400, views=2, image_size=(40, 56))
-        verts, sig, K, n = sc["verts"], sc["sigmas"], 20, 400
-        R, T, focal, principal, hw = sc["R"], sc["T"], sc["focal"], sc["principal"], sc["image_size"]
-    else:
-        n, K, hw = 30000, 24, (24, 24)
-        verts = torch.cat([(torch.rand(n, 2, generator=g) - 0.5) * 0.9, (torch.rand(n, 1, generator=g) - 0.5) * 1.5], 1)
-        sig = torch.full((n,), 2500.0)
-        import voge_oracle as vo
-        R, T = vo.look_at_view(4.0, 0.0, 0.0)
-        focal, principal = 90.0, (12.0, 12.0)
-    H, W = hw
-    colors0 = torch.rand(n, 3, generator=g)
-    target = torch.rand(R.shape[0], H, W, 3, generator=g).to(DEV)
-    res = {}
-    for agg in (True, False):
-        monkeypatch.setenv("VOGE_AGG", "1" if agg else "0")
-        for image_mode in (True, False):
-            monkeypatch.setenv("VOGE_NO_IMAGE_FUSION", "0" if image_mode else "1")
-            r = _renderer(R, T, focal, principal, hw, K, M=n)
-            v = verts.clone().to(DEV).requires_grad_(True)
-            sg = sig.clone().to(DEV).requires_grad_(True)
-            col = colors0.clone().to(DEV).requires_grad_(True)
-            frag = r(GaussianMeshesNaive(v, sg))
-            if case == "overflow" and agg and image_mode:
-                tiles = frag.vert_index[0].reshape(H // 8, 8, W // 8, 8, K).permute(0, 2, 1, 3, 4).reshape(-1, 64 * K)
-                most = max(int(torch.unique(t[t >= 0]).numel()) for t in tiles)
-                print("[agg overflow] most distinct Gaussians in one 8x8 tile: %d" % most)
-                assert most > 700
-            loss = ((to_white_background(frag, col) - target) ** 2).mean() + 1e-2 * get_silhouette(frag).mean() \
-                + 1e-3 * frag.vert_hit_length.clamp(max=50).mean()
-            loss.backward()
-            res[(agg, image_mode)] = (v.grad.clone(), sg.grad.clone(), col.grad.clone())
-    base = res[(False, False)]
-    for key in ((True, True), (True, False), (False, True)):
-        for name, a, b in zip(("verts", "sigma", "colors"), res[key], base):
-            assert torch.isfinite(a).all() and float(b.abs().max()) > 0
-            err = float((a - b).abs().max() / b.abs().max())
-            print("[agg %s agg=%s image=%s] d%s: max|d| / max %.2e" % ((case,) + key + (name, err)))
-            # the aggregated kernel sums the moments (C, A, b) of a group before combining them: the cancellation
-            # between g_ksk d d^T, g_msk mu d^T and g_msm mu mu^T then acts on the sums (pixel-sized Gaussians: 1e-4)
-            assert err < (2e-4 if key[0] else 2e-5), (case, key, name, err)
-
-
 def test_foreign_camera_rays_are_checked():
     """a camera object that is not the built-in PerspectiveCameras uses the fused path only if its rays
     match the closed-form model the culling uses; otherwise the op-by-op chain runs."""

@@ -483,10 +483,7 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
 
 
 def _bwd_flags(need_sigma):
-    """bit 0: sigma gradients wanted; bit 1: per-hit backward kernels.  The tile-aggregated backward
-    (csrc/render_bwd_agg.cuh) is opt-in (VOGE_AGG=1): it issues 8x fewer L2 reductions but runs at half the
-    occupancy, and measures 0.81 against 0.50 ms per C5 view (profiles/ncu_r2_backward.md)."""
-    return int(bool(need_sigma)) | (0 if os.environ.get("VOGE_AGG") == "1" else 2)
+    return int(bool(need_sigma))
 
 
 def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_len_out, absorptivity,

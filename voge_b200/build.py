@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libvoge_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 SOURCES = ["api.cu", "coarse.cu", "fine_fwd.cu", "fine_bwd.cu", "blend.cu", "sample.cu", "render.cu", "trace.cu", "select.cu", "dense.cu"]
-HEADERS = ["common.cuh", "fine_core.cuh", "render_core.cuh", "render_bwd_agg.cuh", "blend_core.cuh", "sort_net.h", os.path.join("..", "..", "include", "voge_b200.h")]
+HEADERS = ["common.cuh", "fine_core.cuh", "render_core.cuh", "blend_core.cuh", "sort_net.h", os.path.join("..", "..", "include", "voge_b200.h")]
 
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -895,8 +895,6 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
 
 }  // namespace voge
 
-#include "render_bwd_agg.cuh"
-
 namespace voge {
 static int launch_fused_backward(const FusedBwdArgs& a, bool image_mode, int flags, cudaStream_t s);
 }
@@ -940,32 +938,12 @@ extern "C" int voge_render_backward_image(const float* gauss, int sigma_kind, co
 }
 
 namespace voge {
-// flags: bit 0 = sigma gradients wanted, bit 1 = do not use the tile-aggregated kernel (A/B aid)
+// flags: bit 0 = sigma gradients wanted
 static int launch_fused_backward(const FusedBwdArgs& a, bool image_mode, int flags, cudaStream_t s) {
     const int sigma_kind = a.kind, B = a.B, H = a.H, W = a.W, K = a.K;
     float* grad_rays = a.grad_rays; float* grad_origins = a.grad_origins; float* grad_cam = a.grad_cam;
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     const bool cam_grads = grad_rays != nullptr || grad_origins != nullptr || grad_cam != nullptr;
-    if (!cam_grads && a.weight != nullptr && K <= kAggMaxK && !(flags & 2)) {
-        // per-tile Gaussian-major gradient reduction (render_bwd_agg.cuh): 8x8 pixel tiles, 128 threads
-        const int64_t grid = (int64_t)B * cdiv(W, 8) * cdiv(H, 8);
-        if (grid > 2147483647LL) return (int)cudaErrorInvalidValue;
-        const size_t smem = agg_smem_bytes(K);
-        auto go = [&](auto kernel) -> int {
-            VOGE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kernel<<<(unsigned)grid, kAggNT, smem, s>>>(a);
-            VOGE_LAUNCH_CHECK();
-            return 0;
-        };
-        if (image_mode) {
-            if (sigma_kind == 1) return go(render_bwd_agg_kernel<1, true>);
-            if (sigma_kind == 3) return go(render_bwd_agg_kernel<3, true>);
-            return go(render_bwd_agg_kernel<9, true>);
-        }
-        if (sigma_kind == 1) return go(render_bwd_agg_kernel<1, false>);
-        if (sigma_kind == 3) return go(render_bwd_agg_kernel<3, false>);
-        return go(render_bwd_agg_kernel<9, false>);
-    }
     auto launch = [&](auto kernel, int nt, int per_pixel) -> int {
         // per_pixel = 2: two threads per pixel, 4x4 pixel blocks per warp; 1: 8x4 blocks
         const int64_t warps = per_pixel == 2 ? (int64_t)B * cdiv(W, 4) * cdiv(H, 4) : (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
