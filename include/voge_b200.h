@@ -163,6 +163,13 @@ int voge_find_nearest_k(const float* len_in, const float* act_in, const float* d
                         int M, int K, int N, int32_t* out_idx, float* out_len, float* out_act,
                         float* out_dsd, voge_stream_t stream);
 
+/* ---- converters (next-tier row f-4) ------------------------------------------------------------------------
+ * Neighbour statistic of `naive_point_cloud_converter` (VoGE/Converter/Converters.py:106-111): avg_len[i] = mean over
+ * the n_nearest (<= 16) smallest distances from point i to the cloud (its own zero distance included), each clipped at
+ * thr_max x their mean.  points (N,3), avg_len (N,) out.                                                      */
+int voge_knn_mean_dist(const float* points, int N, int n_nearest, float thr_max, float* avg_len,
+                       voge_stream_t stream);
+
 /* ---- fused renderer path (GaussianRenderer.forward, reference VoGE/Renderer.py:102-150) ------
  * Same results as rasterize_coarse -> ray_trace_voge_fine -> aggregation on the renderer's own
  * call pattern, without the per-view (B,N,.) copies, the (B,BH,BW,M) bin table, the (R,K,K)

@@ -79,10 +79,24 @@ def test_off_goff_io_roundtrip_matches_reference(golden_dir, tmp_path):
     assert IO.pre_process_pascal(np.array([[1.0, 2.0, 3.0]]))[0].tolist() == [[1.0, 3.0, -2.0]]
 
 
-def test_cuboid_and_alias_package():
-    from VoGE.Converter.Cuboid import cuboid_gauss
+def test_cuboid_and_alias_package(golden_dir):
+    """Cuboid.py:8-159 against the reference's own outputs: vertex order, sigma, faces, per-face colours, return types."""
+    from VoGE.Converter.Cuboid import cuboid_gauss, cuboid_mesh
     from VoGE.Converter import Converters, IO  # noqa: F401
+    from voge_b200.Meshes import GaussianMeshes
+    g = _g(golden_dir)
+    face_cols = np.eye(6, dtype=np.float32)
+    for tag, a in (("a", ((-1, 1), (-1, 1), (-1, 1), 1000)), ("b", ((0, 2), (-1, 0.5), (3, 3.7), 400))):
+        v, s, c = cuboid_gauss(*a, percentage=0.6, colors=face_cols)
+        assert isinstance(v, np.ndarray) and v.dtype == np.float64 and isinstance(s, np.ndarray)     # ndarrays, as the reference
+        assert np.array_equal(v, g["cub_%s_verts" % tag]) and np.array_equal(s, g["cub_%s_isigma" % tag])
+        assert np.array_equal(c, g["cub_%s_colors" % tag])
+        mv, mf, mc = cuboid_mesh(*a, colors=face_cols)
+        assert np.array_equal(mv, g["mesh_%s_verts" % tag]) and np.array_equal(mf, g["mesh_%s_faces" % tag])
+        assert np.array_equal(mc, g["mesh_%s_colors" % tag]) and mf.dtype == np.int64
     v, s = cuboid_gauss((-1, 1), (-1, 1), (-1, 1), 1000, percentage=0.6)
-    assert v.shape == (866, 3) and s.shape == (866,) and v.dtype == torch.float32
-    v, s, c = cuboid_gauss((-1, 1), (-1, 1), (-1, 1), 1000, colors=(0.2, 0.4, 0.6))
-    assert c.shape == (866, 3)
+    assert v.shape == (866, 3) and s.shape == (866,)
+    obj = cuboid_gauss((-1, 1), (-1, 1), (-1, 1), 1000, as_obj=True)
+    assert isinstance(obj, GaussianMeshes) and obj.verts.dtype == torch.float32 and obj.verts.shape == (866, 3)
+    mesh, cols = cuboid_mesh((-1, 1), (-1, 1), (-1, 1), 1000, colors=face_cols, as_obj=True)
+    assert mesh.verts_list()[0].shape == (1014, 3) and mesh.faces_list()[0].dtype == torch.long and cols.shape == (1014, 6)

@@ -405,6 +405,21 @@ def test_image_backward_folded_into_renderer(case, monkeypatch):
         assert err < 2e-5, (case, name, err)
 
 
+def test_point_cloud_converter_on_gpu(golden_dir):
+    """f-4: naive_point_cloud_converter on CUDA points runs voge_knn_mean_dist (csrc/knn.cu) -- against the
+    reference's own values (tests/golden/converters.npz) and the host path on a larger cloud."""
+    from voge_b200.Converter import Converters as C
+    g = np.load(os.path.join(golden_dir, "converters.npz"))
+    p, s, r = C.naive_point_cloud_converter(torch.from_numpy(g["pts"]).to(DEV), percentage=0.5, n_nearest=4, thr_max=2)
+    assert r is None and p.is_cuda and s.is_cuda and np.allclose(s.cpu().numpy(), g["pc_isigma"], rtol=2e-5)
+    pts = torch.randn(5000, 3, generator=torch.Generator().manual_seed(9))
+    pts[100:110] = pts[0:10]                                  # duplicates: zero distances beyond the point itself
+    for k, thr in ((1, 2.0), (4, 2.0), (7, 1.1), (16, 3.0)):
+        want = C.naive_point_cloud_converter(pts, n_nearest=k, thr_max=thr)[1]
+        got = C.naive_point_cloud_converter(pts.to(DEV), n_nearest=k, thr_max=thr)[1].cpu()
+        assert torch.allclose(got, want, rtol=2e-5), (k, float(((got - want).abs() / want).max()))
+
+
 def test_foreign_camera_rays_are_checked():
     """a camera object that is not the built-in PerspectiveCameras uses the fused path only if its rays
     match the closed-form model the culling uses; otherwise the op-by-op chain runs."""

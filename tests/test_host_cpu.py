@@ -118,3 +118,24 @@ def test_camera_shim_consistent_with_closed_form(oracle):
     n2, _ = coarse_inputs(cam, axis[:, None], isg[:, :1], 0.01)
     assert torch.allclose(n2[0, 0, :2], torch.tensor([(30.0 - W / 2) / 24.0, (25.0 - H / 2) / 24.0]), atol=1e-5)
     assert abs(n2[0, 0, 2].item() - 3.0) < 1e-5
+
+
+def test_batchifier_helpers():
+    """VoGE.Utils.Batchifier / Reshaper (reference Utils.py:59-176): chunked execution over flattened dims gives
+    the unchunked result; scalars are summed; the converters' call pattern (target_dims=0, tbar=True) works."""
+    from VoGE.Utils import Batchifier, DataParallelBatchifier, Reshaper  # noqa: F401
+    x = torch.randn(2, 5, 7, 3, generator=torch.Generator().manual_seed(0))
+
+    def fn(a, b):
+        return a * 2, (a * b).sum()
+    for kw in (dict(target_dims=(1, 2)), dict(remain_dims=(0, -1)), dict(target_dims=0), dict(target_dims=-1)):
+        y, s = Batchifier(4, batch_args=("a",), **kw)(fn)(a=x, b=3.0)
+        assert y.shape == x.shape and torch.equal(y, x * 2) and torch.allclose(s, (x * 3).sum())
+    pts = torch.randn(37, 3, generator=torch.Generator().manual_seed(1))
+
+    def nn(point_v, point_t):
+        return (point_v - point_t).pow(2).sum(-1).pow(.5).topk(4, dim=1, largest=False)[0].mean(1)
+    want = nn(point_v=pts.unsqueeze(1), point_t=pts.unsqueeze(0))
+    got = Batchifier(8, batch_args="point_v", target_dims=0, tbar=True)(nn)(point_v=pts.unsqueeze(1), point_t=pts.unsqueeze(0))
+    assert torch.allclose(want, got)
+    assert Reshaper((2, 3), 0)([torch.ones(4, 5), torch.ones(2, 5)]).shape == (2, 3, 5)

@@ -57,5 +57,14 @@ with tempfile.TemporaryDirectory() as d:
     out["goff_text"] = np.frombuffer(open(q, "rb").read(), dtype=np.uint8)
     gp, gs, gr = io.load_goff(q)
     out["goff_points"], out["goff_sigma"] = gp, gs
+# cuboids (Cuboid.py:8-159): vertices, sigmas, faces, per-face colour expansion
+sys.modules["VoGE.Meshes"] = __import__("voge_b200.Meshes", fromlist=["x"])
+cub = _load("Cuboid.py", "VoGE.Converter.Cuboid")
+face_cols = np.eye(6, dtype=np.float32)
+for tag, a in (("a", ((-1, 1), (-1, 1), (-1, 1), 1000)), ("b", ((0, 2), (-1, 0.5), (3, 3.7), 400))):
+    cv, cs, cc = cub.cuboid_gauss(*a, percentage=0.6, colors=face_cols)
+    mv, mf, mc = cub.cuboid_mesh(*a, colors=face_cols)
+    out.update({"cub_%s_verts" % tag: cv, "cub_%s_isigma" % tag: cs, "cub_%s_colors" % tag: cc,
+                "mesh_%s_verts" % tag: mv, "mesh_%s_faces" % tag: mf, "mesh_%s_colors" % tag: mc})
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "converters.npz"), **out)
 print({k: getattr(v, "shape", None) for k, v in out.items()})

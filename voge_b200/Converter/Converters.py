@@ -100,6 +100,13 @@ def naive_point_cloud_converter(points, percentage=0.5, n_nearest=4, thr_max=2, 
     included, each clipped at thr_max x their mean); reference :100-122."""
     to_np = not torch.is_tensor(points)
     pts = (torch.from_numpy(points) if to_np else points).type(torch.float32)
+    if pts.is_cuda and 1 <= n_nearest <= 16 and n_nearest <= pts.shape[0]:
+        # CUDA points: one hand-written kernel (csrc/knn.cu), no (chunk, N) distance matrices
+        from .. import _C
+        with torch.no_grad():
+            avg = _C.knn_mean_dist(pts, n_nearest, thr_max)
+            isigma = 1 / ((avg ** 2) / (4 * math.log(1 / percentage)) + 1e-8)
+        return pts, isigma, None
     sigma = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
     with torch.no_grad():
         for s in range(0, pts.shape[0], chunk):

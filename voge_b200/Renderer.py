@@ -15,6 +15,7 @@ from .fused import render_fused
 
 
 MAX_BACKGROUND_CHANNELS = 32     # kMaxBgChannels of csrc/blend.cu
+_BACKGROUND_CACHE = {}
 
 
 class Fragments(object):
@@ -299,10 +300,19 @@ def to_colored_background(fragments: Fragments, colors: torch.Tensor,
                           background_color: Union[torch.Tensor, tuple, list] = (1, 1, 1), thr: float = -1):
     """min(sum_k w_k colour[idx_k] + (1 - silhouette) * background, 1) -- one fused gather-blend kernel
     (the reference chains get_silhouette, interpolate_attr and four elementwise ops, :162-171)."""
-    if not torch.is_tensor(background_color):
-        background_color = torch.as_tensor(background_color, dtype=torch.float32)
-    background_color = background_color.to(device=colors.device, dtype=torch.float32).reshape(-1)
     C = int(colors.shape[-1])
+    if not torch.is_tensor(background_color):
+        # constant backgrounds (tuples / lists / scalars) are uploaded once per (value, device): a fresh host -> device
+        # copy per call is a blocking cudaMemcpy on the fitting loop's critical path
+        key = (tuple(float(v) for v in (background_color if hasattr(background_color, '__len__') else (background_color,))),
+               str(colors.device))
+        cached = _BACKGROUND_CACHE.get(key)
+        if cached is None:
+            cached = torch.tensor(key[0], dtype=torch.float32).to(colors.device)
+            if len(_BACKGROUND_CACHE) < 64:
+                _BACKGROUND_CACHE[key] = cached
+        background_color = cached
+    background_color = background_color.to(device=colors.device, dtype=torch.float32).reshape(-1)
     if background_color.numel() == 1:
         background_color = background_color.expand(C)
     elif background_color.numel() != C:

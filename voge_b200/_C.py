@@ -229,6 +229,17 @@ def find_nearest_k(hit_len_in, hit_act_in, hit_dsd_in, thr_act, K):
     return idx, out[0], out[1], out[2]
 
 
+def knn_mean_dist(points, n_nearest, thr_max):
+    """(N,3) CUDA points -> (N,) mean clipped distance to the n_nearest closest points (voge_knn_mean_dist)."""
+    points = f32c(points)
+    N = int(points.shape[0])
+    with torch.cuda.device(points.device):
+        out = torch.empty((N,), dtype=torch.float32, device=points.device)
+        check(lib().voge_knn_mean_dist(ptr(points), N, int(n_nearest), float(thr_max), ptr(out), stream_of(points)),
+              "knn_mean_dist")
+    return out
+
+
 # ---- fused blend ops (PyTorch-only in the reference, Aggregation.py) ---------------------------
 def aggregation_forward(sel_idx, sel_act, sel_len, sel_dsd, absorptivity):
     require_cuda(sel_idx, sel_act, sel_len, sel_dsd)

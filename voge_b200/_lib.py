@@ -37,6 +37,7 @@ SIGNATURES = {
     "voge_ray_trace_ray": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "voge_ray_trace_ray_backward": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "voge_find_nearest_k": (_I, [_P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "voge_knn_mean_dist": (_I, [_P, _I, _I, _F, _P, _P]),
     "voge_bin_sub": (_I, []),
     "voge_bin_count": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P]),
     "voge_bin_fill": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),

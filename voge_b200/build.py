@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvoge_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["api.cu", "coarse.cu", "fine_fwd.cu", "fine_bwd.cu", "blend.cu", "sample.cu", "render.cu", "trace.cu", "select.cu", "dense.cu"]
+SOURCES = ["api.cu", "coarse.cu", "fine_fwd.cu", "fine_bwd.cu", "blend.cu", "sample.cu", "render.cu", "trace.cu", "select.cu", "dense.cu", "knn.cu"]
 HEADERS = ["common.cuh", "fine_core.cuh", "render_core.cuh", "blend_core.cuh", "sort_net.h", os.path.join("..", "..", "include", "voge_b200.h")]
 
 FLAGS = [
