@@ -111,11 +111,14 @@ int voge_aggregation_backward(const float* act, const float* len, const float* d
  * attr_padded4 != 0 (C <= 4 only): attr is an (n_attr,4) zero-padded table, fetched with one 16-byte
  * load per hit (every lane of a warp gathers a different row).
  * sat_code (optional, (R,) uint8, C <= 4 with a background): per channel c two bits at 2c telling where the
- * final min(x, 1) clamped -- 2: x < 1, 1: x == 1, 0: x > 1 -- i.e. twice the factor the backward applies.       */
+ * final min(x, 1) clamped -- 2: x < 1, 1: x == 1, 0: x > 1 -- i.e. twice the factor the backward applies.
+ * idx_pad (optional, C <= 4; normally == idx): the slots k >= valid_num[r] of every row are overwritten with 0 --
+ * the reference's in-place `vert_assign += (vert_assign < 0)` (:131) for fragments whose slots behind valid_num are
+ * known to hold the -1 padding, without a read-modify-write pass over the (R,K) tensor.                          */
 int voge_merge_final(const float* attr, const float* weight, const int32_t* idx,
                      const int64_t* valid_num, const float* background, float mask_thr,
                      int64_t R, int K, int C, int idx_mod, int n_attr, int attr_padded4,
-                     float* out, uint8_t* sat_code, voge_stream_t stream);
+                     float* out, uint8_t* sat_code, int32_t* idx_pad, voge_stream_t stream);
 
 /* Backward of voge_merge_final: grad_attr must be ZEROED by the caller and is accumulated into;
  * its layout is (n_attr,C), or -- packed4 != 0 and C <= 4 -- (n_attr,4) zero-padded rows so that one

@@ -420,6 +420,33 @@ def test_point_cloud_converter_on_gpu(golden_dir):
         assert torch.allclose(got, want, rtol=2e-5), (k, float(((got - want).abs() / want).max()))
 
 
+@pytest.mark.parametrize("K", [8, 6, 5])
+def test_merge_final_rewrites_padding_in_place(K):
+    """Reference Aggregation.py:131: merge_final turns the -1 padding of vert_assign into 0 IN PLACE.  For fragments of
+    the fused renderer the gather-blend kernel stores the zeros itself (K % 4 == 0 and != 0 paths); a cloned index
+    tensor takes the generic clamp.  Valid slots are never touched and the image is the same either way."""
+    from voge_b200.Meshes import GaussianMeshesNaive
+    from voge_b200.Renderer import Fragments, interpolate_attr, to_white_background
+    sc = small_scene(seed=67, n=150, views=2)
+    H, W = sc["image_size"]
+    r = _renderer(sc["R"], sc["T"], sc["focal"], sc["principal"], (H, W), K, M=150)
+    gm = GaussianMeshesNaive(sc["verts"].to(DEV), sc["sigmas"].to(DEV))
+    col = sc["colors"].to(DEV)
+    frag = r(gm)
+    before = frag.vert_index.clone()
+    assert int((before < 0).sum()) > 0
+    img = to_white_background(frag, col)
+    want = torch.where(before < 0, torch.zeros_like(before), before)
+    assert torch.equal(frag.vert_index, want)
+    # generic route: fragments rebuilt from clones (no provenance)
+    f2 = r(gm)
+    g = Fragments(f2.vert_weight.clone(), f2.vert_index.clone(), f2.valid_num.clone(), f2.vert_hit_length.clone(),
+                  points_per_view=f2.points_per_view)
+    img2 = to_white_background(g, col)
+    assert torch.equal(g.vert_index, want) and torch.equal(img, img2)
+    assert torch.equal(interpolate_attr(frag, col), interpolate_attr(g, col))
+
+
 def test_foreign_camera_rays_are_checked():
     """a camera object that is not the built-in PerspectiveCameras uses the fused path only if its rays
     match the closed-form model the culling uses; otherwise the op-by-op chain runs."""

@@ -83,12 +83,12 @@ def aggregation(sel_idx: torch.Tensor, sel_act: torch.Tensor, sel_len: torch.Ten
 
 class _MergeFinal(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, vert_attr, weight, vert_assign, valid_num, background, mask_thr, idx_mod):
+    def forward(ctx, vert_attr, weight, vert_assign, valid_num, background, mask_thr, idx_mod, zero_padding=False):
         # attribute rows padded to 16 bytes once per call: the kernels gather one row per (pixel, k)
         attr4 = _C.pad_attr4(vert_attr) if (vert_attr.is_cuda and vert_attr.dim() == 2 and vert_attr.shape[1] <= 4
                                             and vert_attr.dtype == torch.float32) else None
         out = _C.merge_final_forward(vert_attr, weight, vert_assign, valid_num, background, mask_thr, idx_mod,
-                                     attr4=attr4)
+                                     attr4=attr4, zero_padding=zero_padding)
         ctx.save_for_backward(vert_attr, weight, vert_assign, valid_num, background, out)
         ctx.mask_thr, ctx.idx_mod, ctx.attr4 = mask_thr, idx_mod, attr4
         return out
@@ -112,7 +112,7 @@ class _MergeFinal(torch.autograd.Function):
                 x = rgb + (1 - mask).unsqueeze(-1) * background
                 passes = (x < 1).to(x.dtype) + 0.5 * (x == 1).to(x.dtype)       # torch.min subgradient at the tie
                 g_bg = (grad_out * passes * (1 - mask).unsqueeze(-1)).reshape(-1, x.shape[-1]).sum(0)
-        return g_attr, g_w, None, None, g_bg, None, None
+        return g_attr, g_w, None, None, g_bg, None, None, None
 
 
 def _attr_rows(vert_attr, vert_assign):
@@ -135,14 +135,21 @@ def merge_final(vert_attr: torch.Tensor, weight: torch.Tensor, vert_assign: torc
         limit = vert_attr.shape[0] if idx_mod <= 0 else None
         if limit is not None:
             assert limit > vert_assign.max()
-    with torch.no_grad():
-        vert_assign.clamp_(min=0)   # reference :131, done before the tensor is saved for backward
+    # reference :131 rewrites vert_assign -1 -> 0 in place.  Fragments straight from the fused renderer are known to
+    # hold exactly the -1 padding behind valid_num: the gather-blend kernel then stores the zeros itself (no
+    # read-modify-write pass over the (R,K) tensor); everything else takes the generic in-place clamp.
+    pad_in_kernel = (fused_src is not None and fused_src.matches(weight, vert_assign, valid_num) and vert_attr.is_cuda
+                     and vert_attr.dtype == torch.float32 and vert_attr.shape[1] <= 4 and vert_assign.is_contiguous())
+    if not pad_in_kernel:
+        with torch.no_grad():
+            vert_assign.clamp_(min=0)   # done before the tensor is saved for backward
     # fragments straight from the fused renderer (`fused_src`, set by GaussianRenderer): one autograd node whose
     # backward is the renderer's fused backward with this gather-blend's backward folded in (voge_b200/fused.py)
     from . import fused as _fused
     if _fused.image_fusion_applies(fused_src, vert_attr, weight, vert_assign, valid_num, background, idx_mod):
-        return _fused.render_image(fused_src, vert_attr, background, mask_thr, idx_mod)
-    return _MergeFinal.apply(vert_attr, weight, vert_assign, valid_num, background, float(mask_thr), int(idx_mod))
+        return _fused.render_image(fused_src, vert_attr, background, mask_thr, idx_mod, zero_padding=pad_in_kernel)
+    return _MergeFinal.apply(vert_attr, weight, vert_assign, valid_num, background, float(mask_thr), int(idx_mod),
+                             bool(pad_in_kernel))
 
 
 def expend_sigma(sigma, rotation_matrix=None):

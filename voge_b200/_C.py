@@ -281,9 +281,11 @@ def pad_attr4(attr):
 
 
 def merge_final_forward(attr, weight, idx, valid_num, background=None, mask_thr=-1.0, idx_mod=0, attr4=None,
-                        want_sat_code=False):
+                        want_sat_code=False, zero_padding=False):
     """attr4: optional pad_attr4(attr) (used instead of attr when C <= 4).  want_sat_code: also return the (R,) uint8
-    clamp code of the background composite (None when there is no background or C > 4)."""
+    clamp code of the background composite (None when there is no background or C > 4).  zero_padding (C <= 4): the
+    kernel also writes 0 into idx[..., valid_num:] (the reference's in-place -1 -> 0, for fragments whose padding is
+    known to be -1); idx must then be the caller's own contiguous tensor."""
     require_cuda(attr, weight, idx, valid_num)
     attr, weight, idx = f32c(attr), f32c(weight), i32c(idx)
     valid_num = valid_num.to(torch.int64).contiguous()
@@ -299,7 +301,8 @@ def merge_final_forward(attr, weight, idx, valid_num, background=None, mask_thr=
             code = torch.empty(tuple(idx.shape[:-1]), dtype=torch.uint8, device=dev)
         check(lib().voge_merge_final(ptr(attr4 if p4 else attr), ptr(weight), ptr(idx), ptr(valid_num), ptr(bg),
                                      float(mask_thr), R, K, C, int(idx_mod), int(attr.shape[0]), int(p4), ptr(out),
-                                     ptr(code), stream_of(attr)), "merge_final")
+                                     ptr(code), ptr(idx) if (zero_padding and C <= 4) else None, stream_of(attr)),
+              "merge_final")
     return (out, code) if want_sat_code else out
 
 

@@ -29,7 +29,7 @@ SIGNATURES = {
     "voge_ray_trace_fine_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "voge_aggregation": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _P, _P]),
     "voge_aggregation_backward": (_I, [_P, _P, _P, _P, _F, _L, _I, _P, _P, _P, _P]),
-    "voge_merge_final": (_I, [_P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "voge_merge_final": (_I, [_P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "voge_merge_final_backward": (_I, [_P, _P, _P, _P, _P, _F, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "voge_sample": (_I, [_P, _P, _P, _L, _I, _I, _I, _P, _P, _P]),
     "voge_sample_backward": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P]),

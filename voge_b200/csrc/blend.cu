@@ -289,12 +289,23 @@ __global__ void __launch_bounds__(256) merge_fwd_small_kernel(const float* __res
                                                               const int64_t* __restrict__ valid_num,
                                                               const float* __restrict__ background, float mask_thr,
                                                               int64_t R, int K, FastMod idx_mod, int n_attr,
-                                                              float* __restrict__ out, uint8_t* __restrict__ sat_code) {
+                                                              float* __restrict__ out, uint8_t* __restrict__ sat_code,
+                                                              int32_t* __restrict__ idx_pad) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const int nv = valid_num != nullptr ? (int)min((int64_t)K, valid_num[r]) : K;
     const float* wrow = weight + r * K;
     const int32_t* irow = idx + r * K;
+    if (idx_pad != nullptr) {
+        // the reference rewrites vert_assign -1 -> 0 in place (Aggregation.py:131).  For fragments whose slots behind
+        // valid_num are known to be the -1 padding (the caller's promise) that is a store of zeros -- no read, no
+        // separate pass over the (R,K) tensor
+        int32_t* prow = idx_pad + r * K;
+        int k = nv;
+        for (; k < K && (!VEC || (k & 3)); ++k) prow[k] = 0;
+        for (; k + 4 <= K; k += 4) *reinterpret_cast<int4*>(prow + k) = make_int4(0, 0, 0, 0);
+        for (; k < K; ++k) prow[k] = 0;
+    }
     float acc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
@@ -527,7 +538,7 @@ extern "C" int voge_aggregation_backward(const float* act, const float* len, con
 extern "C" int voge_merge_final(const float* attr, const float* weight, const int32_t* idx,
                                 const int64_t* valid_num, const float* background, float mask_thr,
                                 int64_t R, int K, int C, int idx_mod, int n_attr, int attr_padded4, float* out,
-                                uint8_t* sat_code, voge_stream_t stream) {
+                                uint8_t* sat_code, int32_t* idx_pad, voge_stream_t stream) {
     using namespace voge;
     if (R <= 0 || C <= 0) return 0;
     if (C <= 4) {
@@ -538,23 +549,23 @@ extern "C" int voge_merge_final(const float* attr, const float* weight, const in
     do {                                                                                                            \
         if (K % 4 == 0 && attr_padded4)                                                                             \
             merge_fwd_small_kernel<CC, true, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,  \
-                                                                        mask_thr, R, K, fm, n_attr, out, sat_code); \
+                                                                        mask_thr, R, K, fm, n_attr, out, sat_code, idx_pad); \
         else if (K % 4 == 0)                                                                                        \
             merge_fwd_small_kernel<CC, true, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
-                                                                         mask_thr, R, K, fm, n_attr, out, sat_code);\
+                                                                         mask_thr, R, K, fm, n_attr, out, sat_code, idx_pad);\
         else if (attr_padded4)                                                                                      \
             merge_fwd_small_kernel<CC, false, true><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background, \
-                                                                         mask_thr, R, K, fm, n_attr, out, sat_code);\
+                                                                         mask_thr, R, K, fm, n_attr, out, sat_code, idx_pad);\
         else                                                                                                        \
             merge_fwd_small_kernel<CC, false, false><<<grid, 256, 0, s>>>(attr, weight, idx, valid_num, background,\
-                                                                          mask_thr, R, K, fm, n_attr, out, sat_code);\
+                                                                          mask_thr, R, K, fm, n_attr, out, sat_code, idx_pad);\
     } while (0)
         if (C == 1) VOGE_MF(1); else if (C == 2) VOGE_MF(2); else if (C == 3) VOGE_MF(3); else VOGE_MF(4);
 #undef VOGE_MF
         VOGE_LAUNCH_CHECK();
         return 0;
     }
-    if (attr_padded4) return (int)cudaErrorInvalidValue;     // padded tables only for C <= 4
+    if (attr_padded4 || idx_pad != nullptr) return (int)cudaErrorInvalidValue;     // C <= 4 only
     const int64_t total = R * C;
     merge_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         attr, weight, idx, valid_num, background, mask_thr, R, K, C, idx_mod, n_attr, out);

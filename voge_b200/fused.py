@@ -113,10 +113,10 @@ class _RenderImage(torch.autograd.Function):
     weight gradient never exists in HBM and merge_final's own backward launch disappears."""
 
     @staticmethod
-    def forward(ctx, attr, verts, sigmas, origins, rays, cam, background, src, mask_thr, idx_mod):
+    def forward(ctx, attr, verts, sigmas, origins, rays, cam, background, src, mask_thr, idx_mod, zero_padding=False):
         attr4 = _C.pad_attr4(attr)
         out, code = _C.merge_final_forward(attr, src.weight.detach(), src.idx, src.valid, background, mask_thr, idx_mod,
-                                           attr4=attr4, want_sat_code=True)
+                                           attr4=attr4, want_sat_code=True, zero_padding=zero_padding)
         ctx.save_for_backward(verts, sigmas, origins, rays, cam, attr4, out, background, code)
         ctx.src, ctx.mask_thr, ctx.C = src, float(mask_thr), int(attr.shape[1])
         return out
@@ -131,7 +131,7 @@ class _RenderImage(torch.autograd.Function):
             background, ctx.mask_thr, src.absorptivity, sat_code=code, need_sigma=need[2], need_attr=need[0], need_rays=need[4],
             need_origins=need[3], gauss=src.gauss, cam=cam, need_cam=need[5], sigma_mode=src.sigma_mode,
             n_channels=ctx.C)
-        return g_attr, g_verts, g_sig, g_org, g_rays, g_cam, None, None, None, None
+        return g_attr, g_verts, g_sig, g_org, g_rays, g_cam, None, None, None, None, None
 
 
 def image_fusion_applies(src, vert_attr, weight, vert_assign, valid_num, background, idx_mod):
@@ -149,9 +149,9 @@ def image_fusion_applies(src, vert_attr, weight, vert_assign, valid_num, backgro
     return idx_mod == src.n_points or (n_views == 1 and idx_mod == 0)
 
 
-def render_image(src, vert_attr, background, mask_thr, idx_mod):
+def render_image(src, vert_attr, background, mask_thr, idx_mod, zero_padding=False):
     return _RenderImage.apply(vert_attr, src.verts, src.sigmas, src.origins, src.rays, src.cam, background, src,
-                              float(mask_thr), int(idx_mod))
+                              float(mask_thr), int(idx_mod), bool(zero_padding))
 
 
 class _GenerateRays(torch.autograd.Function):
