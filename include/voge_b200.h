@@ -190,6 +190,13 @@ int voge_knn_mean_dist(const float* points, int N, int n_nearest, float thr_max,
  * splits the packed gradient records of voge_render_backward_fused into grad_verts (N,3) and grad_sigmas
  * (shaped like sigmas, NULL to skip) and applies the chain rule of sigma_mode (mode 1: -P^T G P^T; mode 2:
  * tril((G + G^T) tril(L))) -- replaces autograd through torch.inverse / to_sym.
+ * Isotropic encoding (sigma_kind 9 only).  With iso_flag != NULL (one int32, ZEROED by the caller) voge_pack_gaussians
+ * writes every record whose S is exactly s I, s > 0 (off-diagonal entries +0) with -s in the S00 slot: such a
+ * Gaussian is then fully described by the first 16 bytes of its record and a hit gathers one sector instead of 48
+ * bytes.  The kernels that read `gauss` decode it when their sigma_kind argument is 9 | VOGE_KIND_ISO_ENCODED and
+ * rebuild the same nine floats, so results are bit-identical to plain records.  If any OTHER record has the sign
+ * bit set in S00 (not positive definite) the sign would be ambiguous: the kernel sets *iso_flag = 1 and the caller
+ * must pack again with iso_flag = NULL (plain records, sigma_kind 9).
  *
  * Cameras.  R (B,3,3) row-vector convention X_view = X_world R + T, T (B,3), focal (B,2), principal (B,2) in
  * pixels; origins (B,3) = ray origins.  Rays: either a (B,H,W,3) tensor of unit directions (user-supplied
@@ -210,9 +217,10 @@ int voge_knn_mean_dist(const float* points, int N, int n_nearest, float thr_max,
  * voge_bin_fill: scatters Gaussian indices into tile_list using tile_offsets (B*TY*TX*S+1, int64,
  *   exclusive scan of tile_counts; the S segments of a tile are adjacent); cursor (B*TY*TX*S) int32 must be
  *   ZEROED by the caller.                                                                                  */
+#define VOGE_KIND_ISO_ENCODED 0x100
 int voge_bin_sub(void);   /* counters / list segments per tile (S below) */
 int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int sigma_mode, int N,
-                        float* out, voge_stream_t stream);
+                        float* out, int32_t* iso_flag, voge_stream_t stream);
 int voge_unpack_gradients(const float* grad_packed, const float* gauss, const float* sigmas, int sigma_kind,
                           int sigma_mode, int N, float* grad_verts, float* grad_sigmas, voge_stream_t stream);
 int voge_generate_rays(const float* cam, int B, int H, int W, float* rays, voge_stream_t stream);

@@ -447,6 +447,55 @@ def test_merge_final_rewrites_padding_in_place(K):
     assert torch.equal(interpolate_attr(frag, col), interpolate_attr(g, col))
 
 
+@pytest.mark.parametrize("case", ["mixed", "negative_s00"])
+def test_isotropic_record_encoding(case, monkeypatch):
+    """(N,3,3) sigmas whose S is exactly s I are stored in the first 16 bytes of their record (pack_gaussians:
+    iso_encode, csrc/render_core.cuh: kKindIsoEncoded).  Fragments must be bit-identical to plain records and the
+    gradients equal up to the order of the atomics.  A record with a negative S00 that is not of that form makes the
+    sign ambiguous: the renderer must fall back to plain records (same results again)."""
+    from voge_b200 import _C
+    from voge_b200.Meshes import GaussianMeshes
+    from voge_b200.Renderer import to_white_background
+    sc = small_scene(seed=91, n=400, views=2, K=12)
+    H, W = sc["image_size"]
+    sig = sc["sigmas"].clone()
+    n = sig.shape[0]
+    s = sig.diagonal(dim1=1, dim2=2).mean(-1)
+    iso = torch.arange(n) % 10 != 0                      # 90 % isotropic, as in the C5 scene
+    sig[iso] = torch.eye(3)[None] * s[iso].view(-1, 1, 1)
+    if case == "negative_s00":
+        sig[5] = torch.diag(torch.tensor([-30.0, 40.0, 50.0]))   # not positive definite, S00 < 0
+    calls = []
+    orig_pack = _C.pack_gaussians
+    monkeypatch.setattr(_C, "pack_gaussians", lambda *a, **k: (calls.append(k.get("iso_encode", False)), orig_pack(*a, **k))[1])
+    tgt = torch.rand(2, H, W, 3, generator=torch.Generator().manual_seed(3)).to(DEV)
+    res = {}
+    for mode in ("encoded", "plain"):
+        if mode == "plain":
+            monkeypatch.setenv("VOGE_NO_ISO_ENCODING", "1")
+        del calls[:]
+        r = _renderer(sc["R"], sc["T"], sc["focal"], sc["principal"], (H, W), 12, M=400)
+        gm = GaussianMeshes(sc["verts"].clone(), sig.clone()).to(DEV)
+        col = sc["colors"].clone().to(DEV).requires_grad_(True)
+        frag = r(gm)
+        idx = frag.vert_index.clone()
+        img = to_white_background(frag, col)
+        ((img - tgt) ** 2).mean().backward()
+        res[mode] = (idx, frag.vert_weight.detach().clone(), frag.vert_hit_length.clone(), frag.valid_num.clone(),
+                     gm.verts.grad.clone(), gm.sigmas.grad.clone(), col.grad.clone())
+        if mode == "encoded":
+            # one encoded pack; the ambiguous scene packs a second time (plain)
+            assert calls == ([True, False] if case == "negative_s00" else [True]), calls
+    a, b = res["encoded"], res["plain"]
+    assert int(a[3].sum()) > 1000
+    for i in range(4):
+        assert torch.equal(a[i], b[i]), i
+    for i, name in ((4, "verts"), (5, "sigma"), (6, "colors")):
+        err = float((a[i] - b[i]).abs().max() / b[i].abs().max())
+        print("[iso encoding %s] d%s: max|encoded - plain| / max %.2e" % (case, name, err))
+        assert err < 5e-6, (name, err)
+
+
 def test_foreign_camera_rays_are_checked():
     """a camera object that is not the built-in PerspectiveCameras uses the fused path only if its rays
     match the closed-form model the culling uses; otherwise the op-by-op chain runs."""

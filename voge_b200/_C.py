@@ -346,6 +346,13 @@ def sigma_kind(sigmas):
 
 SIGMA_MODES = {"direct": 0, "inverse": 1, "cholesky": 2}
 GAUSS_WIDTH = {1: 4, 3: 8, 9: 12}
+KIND_ISO_ENCODED = 0x100       # sigma_kind flag: kind-9 records with the isotropic encoding (csrc/render_core.cuh)
+
+
+def record_kind(gauss):
+    """sigma_kind argument of the kernels that read the packed records `gauss`"""
+    kind = {4: 1, 8: 3, 12: 9}[int(gauss.shape[1])]
+    return kind | (KIND_ISO_ENCODED if getattr(gauss, "iso_encoded", False) else 0)
 BIN_FLAG_DENSE_MARGIN = 1      # voge_bin_count flags: rounding margin with the dense-S constants (A/B aid)
 
 
@@ -377,7 +384,7 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
     if gauss is None:
         gauss = pack_gaussians(verts, sigmas, sigma_mode)
     B, N = int(R.shape[0]), int(gauss.shape[0])
-    kind = {4: 1, 8: 3, 12: 9}[int(gauss.shape[1])]
+    kind = record_kind(gauss)
     H, W = int(image_size[0]), int(image_size[1])
     TX, TY = (W + tile - 1) // tile, (H + tile - 1) // tile
     if flags is None:
@@ -398,7 +405,12 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
         # one host sync: total list entries + the item count at every view boundary (views can then be
         # processed in groups that bound the forward's scratch)
         per_view = TY * TX * S
-        host = torch.cat([offsets[0][-1:], offsets[1][::per_view]]).tolist()
+        iso_flag = getattr(gauss, "iso_flag", None)
+        host = torch.cat([offsets[0][-1:], offsets[1][::per_view]] + ([iso_flag.to(torch.int64)] if iso_flag is not None else [])).tolist()
+        if iso_flag is not None:
+            # the isotropic encoding is ambiguous for this scene (a non-encoded record has a negative S00): the caller
+            # re-packs plain records and bins again (the same host sync told us)
+            gauss.iso_bad = bool(host.pop())
         total, view_item_starts = int(host[0]), [int(v) for v in host[1:]]
         total_items = view_item_starts[-1]
         tile_list = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
@@ -411,15 +423,23 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
     return offsets[0], tile_list, rects, item_offsets
 
 
-def pack_gaussians(verts, sigmas, sigma_mode=0):
+def pack_gaussians(verts, sigmas, sigma_mode=0, iso_encode=False):
     """-> (N, 4 | 8 | 12) f32 records [x, y, z, S = 2 P ...] (16-byte aligned) read by the fused kernels; P = sigmas
-    (mode 0), inverse(sigmas) (mode 1, reference inverse_sigma=True) or tril(sigmas) tril(sigmas)^T (mode 2)."""
+    (mode 0), inverse(sigmas) (mode 1, reference inverse_sigma=True) or tril(sigmas) tril(sigmas)^T (mode 2).
+    iso_encode ((N,3,3) sigmas only): records whose S is exactly s I carry -s in the S00 slot, so a hit gathers 16
+    instead of 48 bytes (csrc/render_core.cuh: kKindIsoEncoded).  The result then has .iso_encoded = True and
+    .iso_flag, a device int32 that the kernel sets when the encoding is ambiguous (some other record has a negative
+    S00); bin_views reads it with its own host sync and sets .iso_bad, on which the caller packs plain records."""
     verts, sigmas = f32c(verts), f32c(sigmas)
     N, kind = int(verts.shape[0]), sigma_kind(sigmas)
+    iso_encode = bool(iso_encode) and kind == 9 and os.environ.get("VOGE_NO_ISO_ENCODING") != "1"
     with torch.cuda.device(verts.device):
         out = torch.empty((N, GAUSS_WIDTH[kind]), dtype=torch.float32, device=verts.device)
-        check(lib().voge_pack_gaussians(ptr(verts), ptr(sigmas), kind, int(sigma_mode), N, ptr(out), stream_of(verts)),
-              "pack_gaussians")
+        flag = torch.zeros((1,), dtype=torch.int32, device=verts.device) if iso_encode else None
+        check(lib().voge_pack_gaussians(ptr(verts), ptr(sigmas), kind, int(sigma_mode), N, ptr(out), ptr(flag),
+                                        stream_of(verts)), "pack_gaussians")
+    if iso_encode:
+        out.iso_encoded, out.iso_flag = True, flag
     return out
 
 
@@ -442,7 +462,7 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
     if gauss is None:
         gauss = pack_gaussians(verts, sigmas, sigma_mode)
     N, K = int(gauss.shape[0]), int(K)
-    skind = {4: 1, 8: 3, 12: 9}[int(gauss.shape[1])]
+    skind = record_kind(gauss)
     dev = gauss.device
     with torch.cuda.device(dev):
         idx = torch.empty((B, H, W, K), dtype=torch.int32, device=dev)
@@ -523,7 +543,7 @@ def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_
         g_rays = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev) if (need_rays and rays is not None) else None
         g_org = torch.zeros((B, 3), dtype=torch.float32, device=dev) if need_origins else None
         g_cam = torch.zeros((B, 16), dtype=torch.float32, device=dev) if (need_cam and rays is None) else None
-        check(lib().voge_render_backward_fused(ptr(gauss), kind, ptr(origins), ptr(rays),
+        check(lib().voge_render_backward_fused(ptr(gauss), record_kind(gauss), ptr(origins), ptr(rays),
                                                ptr(idx), ptr(valid), ptr(g_weight), ptr(weight), ptr(g_len_out),
                                                float(absorptivity), B, N, H, W, K, ptr(packed), _bwd_flags(need_sigma),
                                                ptr(g_rays), ptr(g_org), ptr(cam), ptr(g_cam), stream_of(verts)),
@@ -555,7 +575,7 @@ def render_backward_image(verts, sigmas, origins, rays, idx, valid, weight, grad
         g_rays = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev) if (need_rays and rays is not None) else None
         g_org = torch.zeros((B, 3), dtype=torch.float32, device=dev) if need_origins else None
         g_cam = torch.zeros((B, 16), dtype=torch.float32, device=dev) if (need_cam and rays is None) else None
-        check(lib().voge_render_backward_image(ptr(gauss), kind, ptr(origins), ptr(rays), ptr(cam), ptr(idx), ptr(valid),
+        check(lib().voge_render_backward_image(ptr(gauss), record_kind(gauss), ptr(origins), ptr(rays), ptr(cam), ptr(idx), ptr(valid),
                                                ptr(weight), ptr(grad_out), ptr(fwd_out), ptr(sat_code), ptr(attr4),
                                                ptr(background),
                                                float(mask_thr), C, float(absorptivity), B, N, H, W, K, ptr(packed),
@@ -574,6 +594,7 @@ def unpack_gradients(packed, gauss, sigmas, sigma_mode=0, need_sigma=True):
     with torch.cuda.device(packed.device):
         g_verts = torch.empty((N, 3), dtype=torch.float32, device=packed.device)
         g_sig = torch.empty_like(sigmas) if need_sigma else None
-        check(lib().voge_unpack_gradients(ptr(packed), ptr(gauss), ptr(sigmas), kind, int(sigma_mode), N, ptr(g_verts),
+        check(lib().voge_unpack_gradients(ptr(packed), ptr(gauss), ptr(sigmas), record_kind(gauss) if gauss is not None else kind,
+                                          int(sigma_mode), N, ptr(g_verts),
                                           ptr(g_sig), stream_of(packed)), "unpack_gradients")
     return g_verts, g_sig

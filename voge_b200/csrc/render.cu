@@ -26,6 +26,7 @@ namespace voge {
 struct BinArgs {
     const float* gauss;      // packed records (voge_pack_gaussians): [x, y, z, S = 2 P ...]
     int kind;
+    int enc;                 // kind-9 records carry the isotropic encoding (render_core.cuh: kKindIsoEncoded)
     const float* Rm;         // (B,3,3) row-vector convention X_view = X_world @ R + T
     const float* Tv;         // (B,3)
     const float* origins;    // (B,3) ray origins (camera centres) used for mu' = verts - origin
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
             float v0, v1, v2;
             if (a.kind == 1) load_gauss<1>(a.gauss, g, v0, v1, v2, S);
             else if (a.kind == 3) load_gauss<3>(a.gauss, g, v0, v1, v2, S);
-            else load_gauss<9>(a.gauss, g, v0, v1, v2, S);
+            else load_gauss<9>(a.gauss, g, v0, v1, v2, S, a.enc != 0);
             mu[0] = __fsub_rn(v0, c0); mu[1] = __fsub_rn(v1, c1); mu[2] = __fsub_rn(v2, c2);
         }
         // view space (X_v = mu' @ R since the origin is the camera centre)
@@ -296,7 +297,7 @@ constexpr int kMaxPairK = 112;   // two-threads-per-pixel backward up to this K 
 
 struct FusedBwdArgs {
     const float* gauss;      // packed records (voge_pack_gaussians)
-    int kind;
+    int kind;                // 1 | 3 | 9, or 9 | kKindIsoEncoded (split into kind / enc by launch_fused_backward)
     const float* origins;
     const float* rays;       // (B,H,W,3), or NULL: generated from `cam` (render_core.cuh: gen_ray)
     const float* cam;        // (B,16) per-view camera records, read when rays == NULL
@@ -324,6 +325,7 @@ struct FusedBwdArgs {
     float mask_thr;          // > 0: hard silhouette mask (Renderer.py:167-168)
     int C;
     float* grad_attr4;       // optional (N,4), zeroed by the caller: dL/d(attr)
+    int enc;                 // kind-9 records carry the isotropic encoding
 };
 
 // what geom_grad_accumulate needs of the kernel arguments (passed by value to out-of-line callers)
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
                 const int g = gv[j] - pack_off;
                 Hit h;
                 h.len = kEmptyLen; h.act = kEmptyLen; h.dsd = 0.f;
-                if (g >= 0 && g < a.N) h = exact_hit_packed<KIND>(a.gauss, g, c0, c1, c2, d0, d1, d2);
+                if (g >= 0 && g < a.N) h = exact_hit_packed<KIND>(a.gauss, g, c0, c1, c2, d0, d1, d2, a.enc != 0);
                 const float sk = sqrtf(h.dsd + 1e-10f);
                 s_ls[k * NT + tid] = make_float2(h.len, sk);
                 s_E[k * NT + tid] = expf(-h.act);
@@ -544,7 +546,7 @@ __global__ void __launch_bounds__(NT) render_bwd_fused_kernel(const FusedBwdArgs
             for (int q = 0; q < 9; ++q) S[q] = 0.f;
             if (g_ok) {
                 float v0, v1, v2;
-                load_gauss<KIND>(a.gauss, g, v0, v1, v2, S);
+                load_gauss<KIND>(a.gauss, g, v0, v1, v2, S, a.enc != 0);
                 m0 = __fsub_rn(v0, c0); m1 = __fsub_rn(v1, c1); m2 = __fsub_rn(v2, c2);
             }
             const float2 lsj = s_ls[j * NT + tid];
@@ -757,7 +759,7 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
                 const int g = gv[jj] - pack_off;
                 Hit h;
                 h.len = kEmptyLen; h.act = kEmptyLen; h.dsd = 0.f;
-                if (g >= 0 && g < a.N) h = exact_hit_packed<KIND>(a.gauss, g, c0, c1, c2, d0, d1, d2);
+                if (g >= 0 && g < a.N) h = exact_hit_packed<KIND>(a.gauss, g, c0, c1, c2, d0, d1, d2, a.enc != 0);
                 const float sk = sqrtf(h.dsd + 1e-10f);
                 s_ls[k * NP + col] = make_float2(h.len, sk);
                 s_E[k * NP + col] = expf(-h.act);
@@ -819,7 +821,7 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
             for (int q = 0; q < 9; ++q) S[q] = 0.f;
             if (g_ok) {
                 float v0, v1, v2;
-                load_gauss<KIND>(a.gauss, g, v0, v1, v2, S);
+                load_gauss<KIND>(a.gauss, g, v0, v1, v2, S, a.enc != 0);
                 m0 = __fsub_rn(v0, c0); m1 = __fsub_rn(v1, c1); m2 = __fsub_rn(v2, c2);
             }
             const float2 lsj = s_ls[j * NP + col];
@@ -912,7 +914,7 @@ extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
     if (grad_cam != nullptr && (rays != nullptr || cam == nullptr)) return (int)cudaErrorInvalidValue;
     FusedBwdArgs a{gauss, sigma_kind, origins, rays, cam, idx, valid, grad_weight, weight, grad_len_out, absorptivity,
                    B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins, grad_cam,
-                   nullptr, nullptr, nullptr, nullptr, nullptr, -1.f, 0, nullptr};
+                   nullptr, nullptr, nullptr, nullptr, nullptr, -1.f, 0, nullptr, 0};
     a.need_sigma = need_sigma & 1;
     return launch_fused_backward(a, false, need_sigma, (cudaStream_t)stream);
 }
@@ -932,14 +934,18 @@ extern "C" int voge_render_backward_image(const float* gauss, int sigma_kind, co
         return (int)cudaErrorInvalidValue;
     FusedBwdArgs a{gauss, sigma_kind, origins, rays, cam, idx, valid, nullptr, weight, nullptr, absorptivity,
                    B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins, grad_cam,
-                   grad_out, fwd_out, sat_code, attr4, background, mask_thr, C, grad_attr4};
+                   grad_out, fwd_out, sat_code, attr4, background, mask_thr, C, grad_attr4, 0};
     a.need_sigma = need_sigma & 1;
     return launch_fused_backward(a, true, need_sigma, (cudaStream_t)stream);
 }
 
 namespace voge {
 // flags: bit 0 = sigma gradients wanted
-static int launch_fused_backward(const FusedBwdArgs& a, bool image_mode, int flags, cudaStream_t s) {
+static int launch_fused_backward(const FusedBwdArgs& a_in, bool image_mode, int flags, cudaStream_t s) {
+    FusedBwdArgs a = a_in;
+    a.enc = (a.kind & kKindIsoEncoded) ? 1 : 0;
+    a.kind &= ~kKindIsoEncoded;
+    if (a.enc && a.kind != 9) return (int)cudaErrorInvalidValue;
     const int sigma_kind = a.kind, B = a.B, H = a.H, W = a.W, K = a.K;
     float* grad_rays = a.grad_rays; float* grad_origins = a.grad_origins; float* grad_cam = a.grad_cam;
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
@@ -1018,8 +1024,12 @@ __device__ __forceinline__ void sigma_to_S(int kind, int mode, const float* __re
     }
 }
 
+// iso_flag != NULL (kind 9): isotropic encoding (render_core.cuh: kKindIsoEncoded) -- a record whose S is exactly
+// s I, s > 0, is written with -s in the S00 slot; any OTHER record with the sign bit set in S00 (a non positive
+// definite input) makes the sign ambiguous and is reported through *iso_flag = 1: the caller then packs plain records.
 __global__ void __launch_bounds__(256) pack_gaussians_kernel(const float* __restrict__ verts, const float* __restrict__ sigmas,
-                                                             int kind, int mode, int N, float* __restrict__ out) {
+                                                             int kind, int mode, int N, float* __restrict__ out,
+                                                             int32_t* __restrict__ iso_flag) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
     const float x = verts[3 * (int64_t)g], y = verts[3 * (int64_t)g + 1], z = verts[3 * (int64_t)g + 2];
@@ -1032,6 +1042,13 @@ __global__ void __launch_bounds__(256) pack_gaussians_kernel(const float* __rest
         o[2 * (int64_t)g] = make_float4(x, y, z, S[0]);
         o[2 * (int64_t)g + 1] = make_float4(S[4], S[8], 0.f, 0.f);
     } else {
+        if (iso_flag != nullptr) {
+            const unsigned off = __float_as_uint(S[1]) | __float_as_uint(S[2]) | __float_as_uint(S[3]) |
+                                 __float_as_uint(S[5]) | __float_as_uint(S[6]) | __float_as_uint(S[7]);
+            const bool iso = off == 0u && S[4] == S[0] && S[8] == S[0] && S[0] > 0.f && S[0] < 3.0e38f;
+            if (iso) S[0] = -S[0];
+            else if (__float_as_uint(S[0]) >> 31) *iso_flag = 1;
+        }
         o[3 * (int64_t)g] = make_float4(x, y, z, S[0]);
         o[3 * (int64_t)g + 1] = make_float4(S[1], S[2], S[3], S[4]);
         o[3 * (int64_t)g + 2] = make_float4(S[5], S[6], S[7], S[8]);
@@ -1044,7 +1061,7 @@ __global__ void __launch_bounds__(256) pack_gaussians_kernel(const float* __rest
 //   mode 1:  dL/dSigma = -P^T (dL/dP) P^T   (P = S / 2 read back from the Gaussian's record)
 //   mode 2:  dL/dL     = tril((G + G^T) tril(L))
 __global__ void __launch_bounds__(256) unpack_gradients_kernel(const float* __restrict__ packed, const float* __restrict__ gauss,
-                                                               const float* __restrict__ sigmas, int kind, int mode, int N,
+                                                               const float* __restrict__ sigmas, int kind, int enc, int mode, int N,
                                                                float* __restrict__ g_verts, float* __restrict__ g_sigmas) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
@@ -1075,7 +1092,7 @@ __global__ void __launch_bounds__(256) unpack_gradients_kernel(const float* __re
             for (int i = 0; i < 9; ++i) o[i] = G[i];
         } else if (mode == 1) {
             float v0, v1, v2, S[9], P[9];
-            load_gauss<9>(gauss, g, v0, v1, v2, S);
+            load_gauss<9>(gauss, g, v0, v1, v2, S, enc != 0);
 #pragma unroll
             for (int i = 0; i < 9; ++i) P[i] = 0.5f * S[i];
             float T[9];   // T = P^T G
@@ -1120,12 +1137,13 @@ __global__ void __launch_bounds__(256) generate_rays_kernel(const float* __restr
 }  // namespace voge
 
 extern "C" int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int sigma_mode, int N,
-                                   float* out, voge_stream_t stream) {
+                                   float* out, int32_t* iso_flag, voge_stream_t stream) {
     using namespace voge;
     if (N <= 0) return 0;
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     if (sigma_mode < 0 || sigma_mode > 2 || (sigma_mode == 2 && sigma_kind != 9)) return (int)cudaErrorInvalidValue;
-    pack_gaussians_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(verts, sigmas, sigma_kind, sigma_mode, N, out);
+    if (iso_flag != nullptr && sigma_kind != 9) return (int)cudaErrorInvalidValue;
+    pack_gaussians_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(verts, sigmas, sigma_kind, sigma_mode, N, out, iso_flag);
     VOGE_LAUNCH_CHECK();
     return 0;
 }
@@ -1134,10 +1152,13 @@ extern "C" int voge_unpack_gradients(const float* grad_packed, const float* gaus
                                      int sigma_mode, int N, float* grad_verts, float* grad_sigmas, voge_stream_t stream) {
     using namespace voge;
     if (N <= 0) return 0;
+    const int enc = (sigma_kind & kKindIsoEncoded) ? 1 : 0;
+    sigma_kind &= ~kKindIsoEncoded;
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
+    if (enc && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     if (sigma_mode < 0 || sigma_mode > 2 || (sigma_mode == 2 && sigma_kind != 9)) return (int)cudaErrorInvalidValue;
-    unpack_gradients_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(grad_packed, gauss, sigmas, sigma_kind, sigma_mode,
-                                                                           N, grad_verts, grad_sigmas);
+    unpack_gradients_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(grad_packed, gauss, sigmas, sigma_kind, enc,
+                                                                           sigma_mode, N, grad_verts, grad_sigmas);
     VOGE_LAUNCH_CHECK();
     return 0;
 }
@@ -1161,8 +1182,12 @@ extern "C" int voge_bin_count(const float* gauss, int sigma_kind, const float* R
     using namespace voge;
     if (B <= 0 || N <= 0) return 0;
     if (tile <= 0 || tile > 16 || (use_ref_bins && (bin_size <= 0 || bin_size % tile != 0))) return (int)cudaErrorInvalidValue;
+    const int enc = (sigma_kind & kKindIsoEncoded) ? 1 : 0;
+    sigma_kind &= ~kKindIsoEncoded;
     if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
+    if (enc && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     BinArgs a;
+    a.enc = enc;
     a.gauss = gauss; a.kind = sigma_kind; a.Rm = Rm; a.Tv = Tv; a.origins = origins;
     a.focal = focal; a.principal = principal; a.B = B; a.N = N; a.H = H; a.W = W;
     a.neg_log_thr = -logf(thr); a.thr_act = thr_act; a.use_ref_bins = use_ref_bins; a.bin_size = bin_size;

@@ -106,8 +106,17 @@ struct GaussWidth {
     static constexpr int v = (KIND == 9) ? 12 : (KIND == 3 ? 8 : 4);
 };
 
+// Isotropic encoding of kind-9 records (sigma_kind | kKindIsoEncoded): a Gaussian whose S is exactly s I, s > 0
+// (every off-diagonal entry +0), carries -s in the S00 slot, so that its whole record is the first 16 bytes
+// [x, y, z, -s] and a hit gathers ONE sector instead of the 48-byte record (the scattered gathers bound the blend and
+// backward kernels).  The readers rebuild the same nine floats, i.e. the same bits go through exact_pair.
+// voge_pack_gaussians encodes only when no other record has the sign bit set in S00 (it reports such records and
+// the caller falls back to plain records), so the sign is unambiguous.
+constexpr int kKindIsoEncoded = 0x100;
+
 template <int KIND>
-__device__ __forceinline__ void load_gauss(const float* __restrict__ gp, int g, float& v0, float& v1, float& v2, float* S) {
+__device__ __forceinline__ void load_gauss(const float* __restrict__ gp, int g, float& v0, float& v1, float& v2, float* S,
+                                           bool enc = false) {
     const float4* p = reinterpret_cast<const float4*>(gp) + (int64_t)g * (GaussWidth<KIND>::v / 4);
     const float4 a = __ldg(p);
     v0 = a.x; v1 = a.y; v2 = a.z;
@@ -118,6 +127,10 @@ __device__ __forceinline__ void load_gauss(const float* __restrict__ gp, int g, 
         const float4 b = __ldg(p + 1);
         S[0] = a.w; S[4] = b.x; S[8] = b.y;
         S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
+    } else if (enc && a.w < 0.f) {
+        const float s = -a.w;
+        S[0] = s; S[4] = s; S[8] = s;
+        S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
     } else {
         const float4 b = __ldg(p + 1), c = __ldg(p + 2);
         S[0] = a.w; S[1] = b.x; S[2] = b.y; S[3] = b.z; S[4] = b.w; S[5] = c.x; S[6] = c.y; S[7] = c.z; S[8] = c.w;
@@ -126,9 +139,9 @@ __device__ __forceinline__ void load_gauss(const float* __restrict__ gp, int g, 
 
 template <int KIND>
 __device__ __forceinline__ Hit exact_hit_packed(const float* __restrict__ gp, int g, float c0, float c1, float c2,
-                                                float d0, float d1, float d2) {
+                                                float d0, float d1, float d2, bool enc = false) {
     float v0, v1, v2, S[9];
-    load_gauss<KIND>(gp, g, v0, v1, v2, S);
+    load_gauss<KIND>(gp, g, v0, v1, v2, S, enc);
     const float m0 = __fsub_rn(v0, c0), m1 = __fsub_rn(v1, c1), m2 = __fsub_rn(v2, c2);   // verts - ray_origin, Renderer.py:130
     if (KIND == 9) return exact_pair(m0, m1, m2, S, d0, d1, d2);
     return exact_pair_diag(m0, m1, m2, S[0], S[4], S[8], d0, d1, d2);

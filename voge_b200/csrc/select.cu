@@ -278,6 +278,7 @@ struct BlendArgs {
     float omega;
     int B, N, H, W, K;
     int view_base;                // as in SelectArgs
+    int enc;                      // kind-9 records carry the isotropic encoding (render_core.cuh: kKindIsoEncoded)
     float* out_weight;            // (B,H,W,K)
     float* out_len;               // (B,H,W,K), 1e10 padded
     float* out_act;               // optional (B,H,W,K)
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(NT) blend_weights_kernel(const BlendArgs a) {
             const int k = k0 + j;
             lv[j] = kEmptyLen; av[j] = kEmptyLen; dv[j] = 0.f;
             if (k < cnt) {
-                const Hit h = exact_hit_packed<KIND>(a.gauss, gv[j] - pack_off, c0, c1, c2, r0, r1, r2);
+                const Hit h = exact_hit_packed<KIND>(a.gauss, gv[j] - pack_off, c0, c1, c2, r0, r1, r2, a.enc != 0);
                 lv[j] = h.len; av[j] = h.act; dv[j] = h.dsd;
                 const float sk = sqrtf(h.dsd + 1e-10f);                              // Aggregation.py:49
                 s_ls[k * NT + tid] = make_float2(h.len, sk);
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(NT) blend_pair_kernel(const BlendArgs a) {
             for (int jj = 0; jj < 2; ++jj) {
                 const int k = k0 + sub + 2 * jj;
                 if (k < cnt) {
-                    const Hit h = exact_hit_packed<KIND>(a.gauss, gv[jj] - pack_off, c0, c1, c2, r0, r1, r2);
+                    const Hit h = exact_hit_packed<KIND>(a.gauss, gv[jj] - pack_off, c0, c1, c2, r0, r1, r2, a.enc != 0);
                     lv[jj] = h.len; av[jj] = h.act; dv[jj] = h.dsd;
                     const float sk = sqrtf(h.dsd + 1e-10f);                              // Aggregation.py:49
                     s_ls[k * NP + col] = make_float2(h.len, sk);
@@ -587,6 +588,9 @@ extern "C" int voge_blend_weights(const float* gauss, int sigma_kind, const floa
     a.gauss = gauss; a.origins = origins; a.rays = rays; a.cam = cam; a.idx = idx; a.valid = valid;
     a.omega = absorptivity; a.B = B; a.N = N; a.H = H; a.W = W; a.K = K; a.view_base = view_base;
     a.out_weight = out_weight; a.out_len = out_len; a.out_act = out_act; a.out_dsd = out_dsd;
+    a.enc = (sigma_kind & kKindIsoEncoded) ? 1 : 0;
+    sigma_kind &= ~kKindIsoEncoded;
+    if (a.enc && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     cudaStream_t s = (cudaStream_t)stream;
     if (sigma_kind == 1) return dispatch_blend<1>(a, s);
     if (sigma_kind == 3) return dispatch_blend<3>(a, s);

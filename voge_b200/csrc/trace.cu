@@ -37,6 +37,7 @@ struct TraceArgs {
     int64_t item_base;                 // subtracted from tile_item_offsets: first slot of this call's views in `hits`
     float thr_act;
     int B, N, H, W, tile, TX, TY;
+    int enc;                           // kind-9 records carry the isotropic encoding (render_core.cuh: kKindIsoEncoded)
     int32_t* counts;                   // out (B*TY*TX, NT): hits stored per pixel column (col = ly*tile + lx)
     int64_t* seg_base;                 // out (B*TY*TX, NT): first slot of the pixel's segment
     uint2* hits;                       // out (total items): (orderable len bits, local Gaussian index)
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
             const int g = __ldg(list + base + tid);
             const uint2 rc = a.rects[(int64_t)b * a.N + g];
             float v0, v1, v2, S[9];
-            load_gauss<KIND>(a.gauss, g, v0, v1, v2, S);
+            load_gauss<KIND>(a.gauss, g, v0, v1, v2, S, a.enc != 0);
             const float m0 = __fsub_rn(v0, c0), m1 = __fsub_rn(v1, c1), m2 = __fsub_rn(v2, c2);   // verts - ray_origin, Renderer.py:130
             const int xl = max((int)(rc.x & 0xffffu), px0), xh = min((int)(rc.x >> 16), pxe);
             const int yl = max((int)(rc.y & 0xffffu), py0), yh = min((int)(rc.y >> 16), pye);
@@ -339,6 +340,9 @@ extern "C" int voge_trace_hits(const float* gauss, int sigma_kind, const float* 
     a.thr_act = thr_act; a.B = B; a.N = N; a.H = H; a.W = W; a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
     a.counts = counts; a.seg_base = seg_base; a.hits = reinterpret_cast<uint2*>(hits);
     a.stats = reinterpret_cast<unsigned long long*>(stats);
+    a.enc = (sigma_kind & kKindIsoEncoded) ? 1 : 0;
+    sigma_kind &= ~kKindIsoEncoded;
+    if (a.enc && sigma_kind != 9) return (int)cudaErrorInvalidValue;
     cudaStream_t s = (cudaStream_t)stream;
     if (sigma_kind == 1) return dispatch_trace<1>(a, s);
     if (sigma_kind == 3) return dispatch_trace<3>(a, s);

@@ -38,11 +38,17 @@ class _RenderFused(torch.autograd.Function):
         thr_act = -math.log(thr + 1e-10)                       # RayTracing.py:85
         tile = choose_tile(bin_size, K, use_ref_bins)
         # (N, 4|8|12) aligned records shared by binning, forward and backward
-        gauss = _C.pack_gaussians(verts, sigmas, sigma_mode)
-        if holder is not None:
-            holder["gauss"] = gauss
+        # ((N,3,3) sigmas: isotropic Gaussians are stored in the first 16 bytes of their record, see _C.pack_gaussians)
+        gauss = _C.pack_gaussians(verts, sigmas, sigma_mode, iso_encode=True)
         offsets, tile_list, rects, item_offsets = _C.bin_views(None, None, R, T, origins, focal, principal, image_size,
                                                                thr, thr_act, use_ref_bins, bin_size, tile, gauss=gauss)
+        if getattr(gauss, "iso_bad", False):
+            # a non positive definite record makes the encoding ambiguous: plain records, binned again
+            gauss = _C.pack_gaussians(verts, sigmas, sigma_mode)
+            offsets, tile_list, rects, item_offsets = _C.bin_views(None, None, R, T, origins, focal, principal, image_size,
+                                                                   thr, thr_act, use_ref_bins, bin_size, tile, gauss=gauss)
+        if holder is not None:
+            holder["gauss"] = gauss
         idx, weight, tlen, valid, _, _ = _C.render_forward(None, None, origins, rays, offsets, tile_list, rects,
                                                            thr_act, absorptivity, K, tile, need_act=False,
                                                            item_offsets=item_offsets, gauss=gauss, cam=cam,
