@@ -137,7 +137,8 @@ class OpTimer:
 
 
 # ------------------------------------------------------------------------------------------------
-def build_workload(args, dev, first, count):
+def build_workload(args, dev, views):
+    """views: the orbit indices this rank renders (voge_b200.distributed.shard_view_indices)"""
     from voge_b200 import scenes
     from voge_b200.Meshes import GaussianMeshes
     from voge_b200.Renderer import GaussianRenderer, GaussianRenderSettings
@@ -146,12 +147,12 @@ def build_workload(args, dev, first, count):
     focal = 900.0 * args.hw / 1024.0
     settings = GaussianRenderSettings(image_size=(H, W), max_assign=args.k, thr_activation=0.01, absorptivity=1)
     renderers, targets = [], []
-    for c0 in range(0, count, args.chunk):
-        cc = min(args.chunk, count - c0)
+    for c0 in range(0, len(views), args.chunk):
+        chunk = views[c0:c0 + args.chunk]
         cams = scenes.orbit_cameras(args.views, dist=3.0, elev_amp=20.0, focal=focal, image_size=(H, W), device=dev,
-                                    first=first + c0, count=cc)
+                                    indices=chunk)
         renderers.append(GaussianRenderer(cams, settings).to(dev))
-        tg = [torch.rand(H, W, 3, generator=torch.Generator().manual_seed(1000 + first + c0 + i)) for i in range(cc)]
+        tg = [torch.rand(H, W, 3, generator=torch.Generator().manual_seed(1000 + v)) for v in chunk]
         targets.append(torch.stack(tg))
     gm = GaussianMeshes(verts, sig).to(dev)
     col = torch.nn.Parameter(colors.to(dev))
@@ -529,7 +530,7 @@ def run_small_config(args):
 
 def main():
     args = parse()
-    from voge_b200.distributed import barrier, init_from_env, max_over_ranks, shard_views
+    from voge_b200.distributed import barrier, init_from_env, max_over_ranks, shard_view_indices
     if args.impl != "reference" and args.config != "c5":
         run_small_config(args)
         return
@@ -544,8 +545,9 @@ def main():
     torch.cuda.set_device(dev)
     from voge_b200 import _C, _lib
     _lib.lib()
-    first, count = shard_views(args.views, rank, world)
-    wl = build_workload(args, dev, first, count)
+    my_views = shard_view_indices(args.views, rank, world)     # round-robin: every rank gets the same mix of cameras
+    count = len(my_views)
+    wl = build_workload(args, dev, my_views)
     H, W = wl["H"], wl["W"]
     rays_total = args.views * H * W
 
@@ -787,7 +789,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C5 synthetic scale sweep: %d Gaussians (10%% anisotropic, (N,3,3) sigmas), %dx%d, "
-                                   "%d views sharded by camera, K=%d, thr=0.01, fwd+bwd to verts/sigmas/colours"
+                                   "%d views sharded by camera (round-robin over the ranks), K=%d, thr=0.01, fwd+bwd to verts/sigmas/colours"
                                    % (args.n, H, W, args.views, args.k),
                        "views_per_rank": count, "views_per_call": min(args.chunk, count),
                        "l2": "no flush needed: each renderer call streams %.0f MB of fragments (+ %d MB targets), "

@@ -7,7 +7,16 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from voge_b200.distributed import shard_views
+from voge_b200.distributed import shard_view_indices, shard_views
+
+
+def test_shard_view_indices_round_robin():
+    for n in (1, 5, 8, 64, 65):
+        for world in (1, 2, 3, 8):
+            parts = [shard_view_indices(n, r, world) for r in range(world)]
+            assert sorted(v for p in parts for v in p) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert shard_view_indices(64, 3, 8) == [3, 11, 19, 27, 35, 43, 51, 59]
 
 
 def test_shard_views_partitions():

@@ -249,28 +249,34 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
             }
             n_eval += n_it;
             // phase 1: the kGroup pairs are evaluated back to back (independent FMA chains in flight together);
-            // slots past the end of the rectangle repeat its last pixel and are masked out
-            float ksk[kGroup], msk[kGroup];
+            // slots past the end of the rectangle repeat its last pixel and are masked out.  Both IEEE quotients of a
+            // pair -- msk^2 / ksk for act and msk / ksk = len (reference :190-193) -- are formed here, unconditionally:
+            // they share the refined reciprocal of ksk, and the hit phase below is then free of divergent arithmetic
+            unsigned lenb[kGroup];
             int cols[kGroup];
             unsigned hit = 0u;
 #pragma unroll
             for (int j = 0; j < kGroup; ++j) {
                 cols[j] = col;
                 const float d0 = s_ray[col], d1 = s_ray[NT + col], d2 = s_ray[2 * NT + col];
+                float ksk, msk;
                 if (KIND == 9) {
                     Prod9 pm;
 #pragma unroll
                     for (int q = 0; q < 9; ++q) pm.t[q] = t[q];
                     const Prod9 pd = exact_row_products(d0, d1, d2, S);
-                    ksk[j] = exact_contract(pd, d0, d1, d2);
-                    msk[j] = exact_contract(pm, d0, d1, d2);
+                    ksk = exact_contract(pd, d0, d1, d2);
+                    msk = exact_contract(pm, d0, d1, d2);
                 } else {
                     const float u0 = __fmul_rn(d0, S[0]), u1 = __fmul_rn(d1, S[4]), u2 = __fmul_rn(d2, S[8]);
-                    ksk[j] = __fmaf_rn(u2, d2, __fmaf_rn(u1, d1, __fmul_rn(u0, d0)));
-                    msk[j] = __fmaf_rn(t[8], d2, __fmaf_rn(t[4], d1, __fmul_rn(t[0], d0)));
+                    ksk = __fmaf_rn(u2, d2, __fmaf_rn(u1, d1, __fmul_rn(u0, d0)));
+                    msk = __fmaf_rn(t[8], d2, __fmaf_rn(t[4], d1, __fmul_rn(t[0], d0)));
                 }
-                const float act = __fsub_rn(msm, __fdiv_rn(__fmul_rn(msk[j], msk[j]), ksk[j]));
-                if (j < n_it && act < a.thr_act) hit |= 1u << j;
+                const float act = __fsub_rn(msm, __fdiv_rn(__fmul_rn(msk, msk), ksk));
+                const float len = __fdiv_rn(msk, ksk);
+                lenb[j] = orderable(len);
+                // reference :197: a hit enters the list only if len < 1e10 (the initial slot value); NaN never does
+                if (j < n_it && act < a.thr_act && len < kEmptyLen) hit |= 1u << j;
                 // next pixel of the rectangle (row-major)
                 if (j + 1 < n_it) {
                     ++col;
@@ -281,12 +287,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
 #pragma unroll
             for (int j = 0; j < kGroup; ++j) {
                 if (hit & (1u << j)) {
-                    // reference :197: a hit enters the list only if len < 1e10 (the initial slot value); NaN never does
-                    const float len = __fdiv_rn(msk[j], ksk[j]);
-                    if (len < kEmptyLen) {
-                        const int slot = atomicAdd(&s_cnt[cols[j]], 1);
-                        a.hits[tile_base + slot] = make_uint2(orderable(len), (unsigned)gg);
-                    }
+                    const int slot = atomicAdd(&s_cnt[cols[j]], 1);
+                    a.hits[tile_base + slot] = make_uint2(lenb[j], (unsigned)gg);
                 }
             }
         }

@@ -95,10 +95,11 @@ def synthetic_scene(n=1_000_000, seed=0, aniso_fraction=0.1, device="cpu"):
 
 
 def orbit_cameras(n_views, dist=3.0, elev_amp=20.0, focal=900.0, image_size=(1024, 1024), device="cpu",
-                  first=0, count=None):
-    """Views i = first .. first+count-1 of an n_views orbit: elev = elev_amp*sin(2 pi i/n), azim = 360 i/n."""
+                  first=0, count=None, indices=None):
+    """Views i = first .. first+count-1 (or the given `indices`) of an n_views orbit: elev = elev_amp*sin(2 pi i/n),
+    azim = 360 i/n."""
     count = n_views if count is None else count
-    i = torch.arange(first, first + count, dtype=torch.float32)
+    i = torch.arange(first, first + count, dtype=torch.float32) if indices is None else torch.tensor(list(indices), dtype=torch.float32)
     elev = elev_amp * torch.sin(2 * math.pi * i / n_views)
     azim = 360.0 * i / n_views
     R, T = look_at_view_transform(dist=dist, elev=elev, azim=azim, device=device)
