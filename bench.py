@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--hw", type=int, default=1024)
     ap.add_argument("--views", type=int, default=64)
-    ap.add_argument("--chunk", type=int, default=16, help="views rendered per renderer call (capped by the views of the rank)")
+    ap.add_argument("--chunk", type=int, default=64, help="views rendered per renderer call (capped by the views of the rank); the 64-view batch of C5 is ONE call at N=1 (21 GB of fragments + scratch out of 180 GB)")
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--config", default="c5", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="BASELINE.json configs[0..4]; c5 (default) is the configuration the metric is quoted on")
@@ -603,16 +603,20 @@ def main():
         h_verts, h_sig, h_col = pin(wl["verts_host"]), pin(wl["sig_host"]), pin(wl["colors_host"])
         h_targets = [pin(t) for t in wl["targets_host"]]
         h2d = sum(t.numel() * 4 for t in h_targets)
-        loss_host = torch.zeros(1).pin_memory()
+        loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+        loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        losses = []
 
         copy_stream = torch.cuda.Stream(device=dev)
         with torch.no_grad():     # model state lives on the device (as in a fitting loop); uploaded once, outside the timing
             wl["gm"].verts.copy_(h_verts); wl["gm"].sigmas.copy_(h_sig); wl["colors"].copy_(h_col)
 
-        def e2e_step():
+        def e2e_step(i):
             # the step's INPUTS (target images) come from pinned host memory on a copy stream, one event per chunk;
             # the compute stream waits for a chunk's targets right before the loss that consumes them, so the
-            # upload of chunk i overlaps the rendering of chunks <= i
+            # upload of chunk i overlaps the rendering of chunks <= i.  The step's RESULT (the loss) is copied to
+            # pinned host memory every step and read by the host one step later (as a training loop logs it), so the
+            # host keeps queueing work instead of draining the device once per step.
             main = torch.cuda.current_stream(dev)
             copy_stream.wait_stream(main)        # previous step must be done with the buffers we overwrite
             with torch.cuda.stream(copy_stream), torch.no_grad():
@@ -623,23 +627,35 @@ def main():
                     e = torch.cuda.Event(); e.record(copy_stream)
                     tdev.append(d); evs.append(e)
             total = fit_step(wl, tdev, args.views, wait_events=evs)
-            loss_host.copy_(total.reshape(1), non_blocking=True)
-            torch.cuda.synchronize()
-            return float(loss_host[0])
-        for _ in range(2):
-            e2e_step()
+            loss_host[i & 1].copy_(total.reshape(1), non_blocking=True)
+            loss_ready[i & 1].record(main)
+            if i > 0:
+                loss_ready[(i - 1) & 1].synchronize()
+                losses.append(float(loss_host[(i - 1) & 1][0]))
+
+        def e2e_drain(i_last):
+            loss_ready[i_last & 1].synchronize()
+            losses.append(float(loss_host[i_last & 1][0]))
+        for i in range(2):
+            e2e_step(i)
+        e2e_drain(1)
         barrier(); torch.cuda.synchronize()
+        del losses[:]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            e2e_step()
+        for i in range(args.steps):
+            e2e_step(i)
+        e2e_drain(args.steps - 1)
         e1.record()
         torch.cuda.synchronize(); barrier()
+        assert len(losses) == args.steps and all(math.isfinite(v) for v in losses)
         ms_e2e = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
         e2e = {"value": rays_total / (ms_e2e * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+               "losses_read_on_host": len(losses),
                "note": "per step: this rank's target images from pinned host memory (copy stream, one event per chunk, "
-                       "waited for right before the loss) + the loss read back; Gaussian parameters are device-resident "
+                       "waited for right before the loss) + the loss copied to pinned host memory and read by the host "
+                       "one step later (all reads inside the timed region); Gaussian parameters are device-resident "
                        "model state, uploaded once before the timed steps (they do not change between steps)"}
 
     if rank != 0:
@@ -691,13 +707,17 @@ def main():
         o = ops.get(sym)
         if not o or not o["launches"]:
             return None
+        # time per renderer CALL (the forward traces / selects a long batch in groups of views: several launches)
+        o = dict(o)
+        o["launches_per_call"] = o["launches"] / (args.steps * n_calls)
+        o["avg_ms"] = o["total_ms"] / (args.steps * n_calls)
         ach = work / (o["avg_ms"] * 1e-3) / unit_scale
         peak = peaks["fp32_tflops"] if bound == "fp32" else hbm_peak
         pk = pipes.get(sym) or {}
         e = {"kernel": label, "bound": bound, "achieved": ach, "peak": peak,
              "unit": "TFLOP/s" if bound == "fp32" else "GB/s", "frac": ach / peak,
              "traffic": (pk["dram_bytes_per_view"] * views_per_launch) if pk.get("dram_bytes_per_view") else None,
-             "avg_launch_ms": o["avg_ms"], "launches_timed": o["launches"],
+             "avg_launch_ms": o["avg_ms"], "launches_timed": o["launches"], "launches_per_call": o["launches_per_call"],
              "share_of_step": o["total_ms"] / max(ms_total, 1e-9), "algorithmic_work_per_launch": work, "work": note,
              # what the pipes actually did (ncu, % of peak) -- `frac` above is algorithmic work over time and, for the
              # kernels that cull or window their work, is NOT pipe efficiency
@@ -795,7 +815,7 @@ def main():
                        "l2": "no flush needed: each renderer call streams %.0f MB of fragments (+ %d MB targets), "
                              ">> 126 MB L2" % (frag_bytes / 1e6, min(args.chunk, count) * H * W * 12 // 10 ** 6)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(args.steps, 1), "clocks": clocks,
-            "loss": float(loss)}
+            "loss": float(loss), "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
     if world == 1 and not args.no_ref_gpu:
         # the bar that matters: the reference's OWN CUDA kernels + PyTorch aggregation on this GPU (one view, fwd+bwd)
         rg = ref_gpu_sample(wl, args, dev)
