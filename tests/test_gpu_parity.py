@@ -147,15 +147,17 @@ def test_merge_background_and_backward(oracle, C):
         assert torch.allclose(g_attr.cpu(), ar.grad, rtol=1e-4, atol=1e-5)
 
 
-def test_sample_ops(oracle, C):
+@pytest.mark.parametrize("shape", [(2, 9, 7, 5, 30, 4), (2, 40, 30, 8, 6, 3)])
+def test_sample_ops(oracle, C, shape):
+    """second shape: few vertices under many rays -> the run-aggregating kernel (sample_fwd_runs_kernel)"""
     g = torch.Generator().manual_seed(12)
-    B, H, W, K, N, Cc = 2, 9, 7, 5, 30, 4
+    B, H, W, K, N, Cc = shape
     idx = torch.randint(-1, N, (B, H, W, K), generator=g).int()
     w = torch.rand(B, H, W, K, generator=g)
     img = torch.rand(B, H, W, Cc, generator=g)
     f_o, s_o = oracle.sample(img, w, idx, N)
     f, s = C.sample_voge(img.to(DEV), w.to(DEV), idx.to(DEV), N)
-    assert np.allclose(f.cpu().numpy(), f_o, rtol=1e-5, atol=1e-6) and np.allclose(s.cpu().numpy(), s_o, rtol=1e-5)
+    assert np.allclose(f.cpu().numpy(), f_o, rtol=2e-5, atol=1e-6) and np.allclose(s.cpu().numpy(), s_o, rtol=2e-5)
     # dense-matrix spec of Documentation.md:94-100
     dense = torch.zeros(B * H * W, N + 1)
     dense.scatter_add_(1, (idx.view(-1, K).long() + 1), w.view(-1, K))

@@ -154,10 +154,22 @@ class GaussianRenderer(nn.Module):
     def _forward_fused(self, verts, sigmas, rays, origins):
         st = self.render_settings
         map_size = st['image_size']
-        R, T, focal, principal, cam_origins = self._camera_tensors(map_size)
+        # The camera-derived tensors ((B,.) only, but a dozen tiny launches) are rebuilt only when a camera tensor was
+        # replaced or written to; cameras that require grad always take the differentiable route.
+        tensors = self._camera_key_tensors()
+        frozen = not any(t.requires_grad for t in tensors)
+        key = self._camera_key(map_size) if frozen else None
+        cached = getattr(self, '_fused_cam_cache', None)
+        if frozen and cached is not None and cached[0] == key:
+            R, T, focal, principal, cam_origins, cam_rec = cached[2]
+        else:
+            R, T, focal, principal, cam_origins = self._camera_tensors(map_size)
+            cam_rec = _C.make_cam(R, focal, principal)
+            if frozen:
+                self._fused_cam_cache = (key, list(tensors), (R, T, focal, principal, cam_origins, cam_rec))
         if rays is None:
             # closed-form camera: rays are generated inside the kernels from the (B,16) camera records
-            cam, origins = _C.make_cam(R, focal, principal), cam_origins
+            cam, origins = cam_rec, cam_origins
         else:
             cam = None
         M = st['max_point_per_bin']

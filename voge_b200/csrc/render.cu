@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__
 // (so neither act nor dsd is ever written to HBM by the forward), the blend is differentiated
 // analytically inside the depth window where the erf is not saturated, and the chain rule of
 // ray_trace_voge.cu:324-330 is applied straight into the (N,.) parameter gradients.
-constexpr int kMaxPairK = 112;   // two-threads-per-pixel backward up to this K (16 K bytes of shared memory per pixel)
+constexpr int kMaxPairK = 112;   // two-threads-per-pixel backward up to this K (20 K bytes of shared memory per pixel)
 
 struct FusedBwdArgs {
     const float* gauss;      // packed records (voge_pack_gaussians)
@@ -630,6 +630,7 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
     float2* s_ls = reinterpret_cast<float2*>(smem_raw);   // (len, s = sqrt(dsd + 1e-10))
     float* s_E = reinterpret_cast<float*>(s_ls + A);      // exp(-act)
     float* s_wg = s_E + A;                                // w_m * dL/dw_m
+    int* s_g = reinterpret_cast<int*>(s_wg + A);          // local Gaussian index of the slot (-1: none): pass 2 needs no second trip to the index rows
     const int tid = threadIdx.x;
     const int lane = tid & 31, sub = lane & 1, col = tid >> 1;
     const unsigned pair_mask = 3u << (lane & 30);
@@ -763,6 +764,7 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
                 const float sk = sqrtf(h.dsd + 1e-10f);
                 s_ls[k * NP + col] = make_float2(h.len, sk);
                 s_E[k * NP + col] = expf(-h.act);
+                s_g[k * NP + col] = (g >= 0 && g < a.N) ? g : -1;
                 s_min = fminf(s_min, sk);
                 if (a.weight != nullptr) {
                     const float wg = wv[jj] * gwv[jj];
@@ -809,13 +811,10 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
     {
         int lo_j = 0, hi_j = -1;
         float pref = 0.f;                 // sum of gD_m over m <= hi_j
-        int4 ix4 = make_int4(-1, -1, -1, -1);
         for (int j = sub; j < cnt; j += 2) {
             // the Gaussian's record is fetched first: the gathers overlap with the window loop below
-            if (vec && (j & 3) == sub) ix4 = *reinterpret_cast<const int4*>(i_idx + (j & ~3));
-            const int gp = vec ? ((j & 2) ? ((j & 1) ? ix4.w : ix4.z) : ((j & 1) ? ix4.y : ix4.x)) : i_idx[j];
-            const int g = gp - pack_off;
-            const bool g_ok = g >= 0 && g < a.N;
+            const int g = s_g[j * NP + col];
+            const bool g_ok = g >= 0;
             float S[9], m0 = 0.f, m1 = 0.f, m2 = 0.f;
 #pragma unroll
             for (int q = 0; q < 9; ++q) S[q] = 0.f;
@@ -953,7 +952,7 @@ static int launch_fused_backward(const FusedBwdArgs& a_in, bool image_mode, int 
     auto launch = [&](auto kernel, int nt, int per_pixel) -> int {
         // per_pixel = 2: two threads per pixel, 4x4 pixel blocks per warp; 1: 8x4 blocks
         const int64_t warps = per_pixel == 2 ? (int64_t)B * cdiv(W, 4) * cdiv(H, 4) : (int64_t)B * cdiv(W, 8) * cdiv(H, 4);
-        const size_t smem = (size_t)K * (nt / per_pixel) * 16;
+        const size_t smem = (size_t)K * (nt / per_pixel) * (per_pixel == 2 ? 20 : 16);
         if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
         VOGE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t grid = (warps * 32 + nt - 1) / nt;
