@@ -79,8 +79,8 @@ static int check_pair(std::mt19937& rng, int samples) {
     return bad;
 }
 
-// Four lanes per pixel (not in the kernel yet: the next step of DESIGN.md section 8): S slots per lane, slot 4 i + q
-// in lane q.  Round 1 merges lanes (0,1) and (2,3) as in select_pair; round 2 takes min / max against the reversed
+// Four lanes per pixel (select_quad of select.cu, S = 32: segments of 65 .. 128 hits; the kernel keeps only the
+// lower half, lanes 0 and 1): S slots per lane, slot 4 i + q in lane q.  Round 1 merges lanes (0,1) and (2,3) as in select_pair; round 2 takes min / max against the reversed
 // sequence of the other pair (partner lane q ^ 3), then one cross-lane compare-exchange stage inside each pair
 // (partner q ^ 1, same register) and a bitonic merge per lane.  Lane q ends with ranks q S .. q S + S - 1.
 template <int S>
@@ -139,7 +139,7 @@ int main() {
     bad += check_sort<20>(rng, 3000) + check_sort<7>(rng, 3000);
     bad += check_bitonic<8>() + check_bitonic<16>() + check_bitonic<32>();
     bad += check_pair<8>(rng, 20000) + check_pair<16>(rng, 20000) + check_pair<32>(rng, 20000);
-    bad += check_quad<8>(rng, 10000) + check_quad<16>(rng, 10000);
+    bad += check_quad<8>(rng, 10000) + check_quad<16>(rng, 10000) + check_quad<32>(rng, 10000);
     static_assert(odd_even_count(16) == 63 && odd_even_count(32) == 191 && odd_even_count(64) == 543, "comparator counts");
     {   // fold_index
         const int ds[] = {1, 2, 3, 7, 1000, 35947, 1000000, 999983, 1 << 20, (1 << 30) + 7, 2147483647};

@@ -288,9 +288,9 @@ def test_forward_pipeline_dense_ties_and_single_kernel(K, hw):
 @pytest.mark.parametrize("K,hw,scale", [(20, (64, 64), 0.08), (40, (64, 64), 0.08), (60, (48, 80), 0.05), (25, (40, 56), 0.12),
                                         (64, (64, 64), 0.05)])
 def test_select_topk_hit_count_classes(K, hw, scale):
-    """select_topk over every per-pixel hit-count class -- one lane per pixel (<= 16 / <= 32 hits), two lanes per
-    pixel (33..64, ranks 32.. written by the second lane when K > 32), warp-cooperative and per-lane exact
-    selection (> 64 hits, tied lens) -- for K below / at / above 32 and K % 4 != 0: bit-identical index lists
+    """select_topk over every per-pixel hit-count class -- two lanes per pixel with 8 / 16 / 32 slots each (<= 64 hits,
+    ranks 32.. written by the second lane when K > 32), four lanes per pixel (65..128 hits, K <= 63), warp-cooperative
+    and per-lane exact selection (more hits, K = 64, tied lens) -- for K below / at / above 32 and K % 4 != 0: bit-identical index lists
     to the op-by-op chain (pixel-major fine kernel with the reference's insertion rule)."""
     from voge_b200 import _C
     from voge_b200.cameras import camera_params
@@ -322,6 +322,11 @@ def test_select_topk_hit_count_classes(K, hw, scale):
     classes = [int(((wmax >= lo) & (wmax <= hi)).sum()) for lo, hi in ((1, 16), (17, 32), (33, 64), (65, 10 ** 9))]
     assert classes[2] > 0 and classes[3] > 0 and (classes[0] > 0 or classes[1] > 0), classes
     assert int(stats[2]) > 0
+    # 65 .. 128 hits: four lanes per pixel (select_quad, K <= 63); more: the exact-key selection
+    cpix = dbg["counts"]
+    n_quad, n_more = int(((cpix > 64) & (cpix <= 128)).sum()), int((cpix > 128).sum())
+    print("[select classes K=%d] pixels with 65..128 hits: %d, with more: %d, exact-key selections: %d" % (K, n_quad, n_more, int(stats[2])))
+    assert n_quad > 0
     # selected lists are ascending in (len, idx) and padded consistently
     idx, ln, valid = p[0], p[2], p[3]
     kk = torch.arange(K, device=DEV).view(1, 1, 1, K)

@@ -102,6 +102,94 @@ __device__ __forceinline__ bool select_pair(const uint2* __restrict__ hs, int c,
     return true;
 }
 
+// FOUR adjacent lanes per pixel, 32 slots each: segments of 65 .. 128 hits (mesh-converted scenes with K = 40 .. 60:
+// 8 % of the covered pixels of the RenderBunny-sized C2 scene), K <= 63.  Lane q takes the slots 4 i + q (the quad's
+// four 8-byte loads are adjacent); every lane sorts its 32, the pairs (0,1) and (2,3) merge to two sorted runs of
+// 64 as in select_pair, the pair (0,1) then keeps min(A[i], B[63 - i]) -- the 64 smallest of the 128, a bitonic
+// sequence -- and a half-cleaner across its two lanes plus a bitonic merge per lane sort them.  Composites carry 7
+// slot bits, so the lens may span 2^25 float steps.  Returns false (in all four lanes) where they are not exact.
+__device__ __noinline__ bool select_quad(const uint2* __restrict__ hs, int c, int K, int pack_off, int q,
+                                            unsigned quad_mask, unsigned* __restrict__ s_y, int lane,
+                                            int32_t* __restrict__ o_idx) {
+    constexpr int S = 32;
+    unsigned r[S];
+    unsigned omin = 0xffffffffu, omax = 0u;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        r[i] = 0xffffffffu;
+        if (4 * i + q < c) {
+            const uint2 h = __ldg(&hs[4 * i + q]);
+            r[i] = h.x;
+            s_y[i * 32 + lane] = h.y;          // slot 4 i + q lives in the column of the lane that loaded it
+            omin = min(omin, r[i]);
+            omax = max(omax, r[i]);
+        }
+    }
+    omin = min(omin, __shfl_xor_sync(quad_mask, omin, 1)); omin = min(omin, __shfl_xor_sync(quad_mask, omin, 2));
+    omax = max(omax, __shfl_xor_sync(quad_mask, omax, 1)); omax = max(omax, __shfl_xor_sync(quad_mask, omax, 2));
+    if (omax - omin >= 0x1ffffffu) return false;
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+        if (4 * i + q < c) r[i] = ((r[i] - omin) << 7) | (unsigned)(4 * i + q);
+    sort_network<S>(r);
+    const int sub = q & 1;
+    // pairs (0,1) and (2,3): sorted runs of 64 (lane sub = 0: ranks 0..31 of its pair, sub = 1: ranks 32..63)
+#pragma unroll
+    for (int x = 0; x < S / 2; ++x) {
+        const unsigned t1 = __shfl_xor_sync(quad_mask, r[S - 1 - x], 1), t2 = __shfl_xor_sync(quad_mask, r[x], 1);
+        r[x] = sub ? max(r[x], t1) : min(r[x], t1);
+        r[S - 1 - x] = sub ? max(r[S - 1 - x], t2) : min(r[S - 1 - x], t2);
+    }
+    bitonic_merge<S>(r);
+    // A = pair (0,1), B = pair (2,3): lane 0 register x = A[x] meets B[63 - x] = lane 3 register 31 - x, lane 1
+    // register x = A[32 + x] meets B[31 - x] = lane 2 register 31 - x; the other pair's result is not needed
+#pragma unroll
+    for (int x = 0; x < S; ++x) {
+        const unsigned t = __shfl_xor_sync(quad_mask, r[S - 1 - x], 3);
+        r[x] = min(r[x], t);
+    }
+    // half-cleaner across the lanes of pair (0,1), then a bitonic merge per lane
+#pragma unroll
+    for (int x = 0; x < S; ++x) {
+        const unsigned t = __shfl_xor_sync(quad_mask, r[x], 1);
+        r[x] = sub ? max(r[x], t) : min(r[x], t);
+    }
+    bitonic_merge<S>(r);
+    // lanes 0 / 1 hold ranks 0..31 / 32..63; a tie is two neighbouring ranks with equal len bits
+    const int j0 = sub * S;
+    const unsigned below = __shfl_xor_sync(quad_mask, r[S - 1], 1);
+    bool tie = sub && ((r[0] ^ below) < 128u);
+#pragma unroll
+    for (int i = 1; i < S; ++i) tie = tie || ((r[i] ^ r[i - 1]) < 128u);
+    tie = tie && q < 2;
+    tie = __shfl_xor_sync(quad_mask, (int)tie, 1) || tie;
+    tie = __shfl_xor_sync(quad_mask, (int)tie, 2) || tie;
+    if (tie) return false;
+    __syncwarp(quad_mask);                                      // the other lanes' index columns are read below
+    if (q < 2) {
+        const bool vec = (K & 3) == 0;
+#pragma unroll
+        for (int i0 = 0; i0 < S; i0 += 4) {
+            if (j0 + i0 < K) {
+                int v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned slot = r[i0 + j] & 127u;
+                    v[j] = (j0 + i0 + j < K) ? pack_off + (int)s_y[(slot >> 2) * 32 + ((lane & 28) | (int)(slot & 3u))] : -1;
+                }
+                if (vec) {
+                    *reinterpret_cast<int4*>(o_idx + j0 + i0) = make_int4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j0 + i0 + j < K) o_idx[j0 + i0 + j] = v[j];
+                }
+            }
+        }
+    }
+    return true;
+}
+
 // exact selection with the full (len, idx) keys: K passes, each extracting the smallest key above the
 // previous one (keys are unique: a Gaussian hits a pixel at most once).  O(K c) loads, any c.
 __device__ __noinline__ void select_exact(const uint2* __restrict__ hs, int c, int K, int pack_off,
@@ -238,7 +326,32 @@ __global__ void __launch_bounds__(NT, 1024 / NT) select_topk_kernel(const Select
         }
         done = !(((lane < 16 ? failed[0] : failed[1]) >> (2 * (lane & 15))) & 1u);
     }
-    // pixels the networks could not finish (more than 64 hits, tied lens, lens spanning > 8 binades): a few
+    if (__ballot_sync(0xffffffffu, !done) == 0u) return;
+    // pixels of 65 .. 128 hits: four lanes each, eight pixels per pass
+    if (a.K <= 63) {
+        const SelPix me = select_pixel<TNT>(a, tile_id, ti0 + lane);
+        unsigned want = __ballot_sync(0xffffffffu, !done && me.c > 64 && me.c <= 128);
+        if (want != 0u) {
+            const int q = lane & 3;
+            const unsigned quad_mask = 15u << (lane & 28);
+#pragma unroll 1
+            for (int pass = 0; pass < 4; ++pass) {
+                if (((want >> (8 * pass)) & 0xffu) == 0u) continue;
+                const int p = pass * 8 + (lane >> 2);
+                bool ok = true;
+                if ((want >> p) & 1u) {
+                    const SelPix px = select_pixel<TNT>(a, tile_id, ti0 + p);
+                    ok = select_quad(px.hs, px.c, a.K, pack_off, q, quad_mask, s_y, lane, a.out_idx + px.ray * a.K);
+                } else {
+                    ok = false;
+                }
+                const unsigned fin = __ballot_sync(0xffffffffu, ok);     // bit of lane 4 (p % 8) set: pixel p finished
+                if (pass == (lane >> 3) && ((fin >> (4 * (lane & 7))) & 1u)) done = true;
+                __syncwarp();                                            // the next pass overwrites the index columns
+            }
+        }
+    }
+    // pixels the networks could not finish (more than 128 hits, tied lens, lens spanning > 8 binades): a few
     // per warp are selected by the whole warp, many (a warp inside a very dense region) by their own lanes
     unsigned slow = __ballot_sync(0xffffffffu, !done);
     if (slow == 0u) return;
