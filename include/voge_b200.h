@@ -214,7 +214,8 @@ int voge_knn_mean_dist(const float* points, int N, int n_nearest, float thr_max,
  *   shape, ZEROED) accumulates the rectangle area inside each tile (the tile's number of ITEMS, trace.cu).
  *   flags: bit 0 = use the dense-S rounding constants for every Gaussian (default: count the non-zero entries
  *   of S, DESIGN.md "culling margins").
- * voge_bin_fill: scatters Gaussian indices into tile_list using tile_offsets (B*TY*TX*S+1, int64,
+ * voge_bin_fill: scatters 16-byte entries (Gaussian index, rectangle x, rectangle y, 0) into tile_list (total, 4) int32
+ *   using tile_offsets (B*TY*TX*S+1, int64,
  *   exclusive scan of tile_counts; the S segments of a tile are adjacent); cursor (B*TY*TX*S) int32 must be
  *   ZEROED by the caller.                                                                                  */
 #define VOGE_KIND_ISO_ENCODED 0x100
