@@ -209,15 +209,15 @@ int voge_knn_mean_dist(const float* points, int N, int n_nearest, float thr_max,
  *   RayTracing.py:33-57 + rasterize_coarse.cu:20-42,:116-130 at `bin_size` px, if use_ref_bins]
  *   AND [conservative projected-ellipsoid bound]; tiles are `tile` x `tile` px (tile <= 16, divides
  *   bin_size).  rects (B,N,2) uint32 out = conservative PIXEL rectangle x0|x1<<16, y0|y1<<16 (inclusive,
- *   empty if x0 > x1); tile_counts (B,TY,TX,S) int32, S = voge_bin_sub() counters per tile (entry n is counted in
- *   counter n % S: L2 serialises atomics on one address), must be ZEROED by the caller; tile_items (optional, same
- *   shape, ZEROED) accumulates the rectangle area inside each tile (the tile's number of ITEMS, trace.cu).
+ *   empty if x0 > x1); tile_counters (B,TY,TX,S) uint64, S = voge_bin_sub() list segments per tile (entry n is
+ *   counted in segment n % S: L2 serialises atomics on one address), must be ZEROED by the caller: the low word
+ *   counts the segment's list entries, the high word accumulates their rectangle areas inside the tile (the tile's
+ *   number of ITEMS, trace.cu) -- one 64-bit reduction per (entry, tile) serves both.
  *   flags: bit 0 = use the dense-S rounding constants for every Gaussian (default: count the non-zero entries
  *   of S, DESIGN.md "culling margins").
- * voge_bin_fill: scatters 16-byte entries (Gaussian index, rectangle x, rectangle y, 0) into tile_list (total, 4) int32
- *   using tile_offsets (B*TY*TX*S+1, int64,
- *   exclusive scan of tile_counts; the S segments of a tile are adjacent); cursor (B*TY*TX*S) int32 must be
- *   ZEROED by the caller.                                                                                  */
+ * voge_bin_fill: scatters 16-byte entries (Gaussian index, rectangle x, rectangle y, 0) into tile_list (total, 4) int32;
+ *   cursor (B*TY*TX*S) uint64 must hold the segments' offsets (exclusive scan of the entry counts; the S segments of
+ *   a tile are adjacent) and is advanced: one atomic yields an entry's position.                           */
 #define VOGE_KIND_ISO_ENCODED 0x100
 int voge_bin_sub(void);   /* counters / list segments per tile (S below) */
 int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int sigma_mode, int N,
@@ -228,9 +228,9 @@ int voge_generate_rays(const float* cam, int B, int H, int W, float* rays, voge_
 int voge_bin_count(const float* gauss, int sigma_kind, const float* R,
                    const float* T, const float* origins, const float* focal, const float* principal,
                    int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins,
-                   int bin_size, int tile, int flags, uint32_t* rects, int32_t* tile_counts, int32_t* tile_items,
+                   int bin_size, int tile, int flags, uint32_t* rects, uint64_t* tile_counters,
                    voge_stream_t stream);
-int voge_bin_fill(const uint32_t* rects, const int64_t* tile_offsets, int32_t* cursor, int B, int N,
+int voge_bin_fill(const uint32_t* rects, uint64_t* cursor, int B, int N,
                   int H, int W, int tile, int32_t* tile_list, voge_stream_t stream);
 /* ---- forward pipeline of the fused renderer (csrc/trace.cu, csrc/select.cu) ----------------------------
  *   voge_trace_hits: every item (tile-list entry x pixel of its rectangle inside the tile) is evaluated with

@@ -392,16 +392,16 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
     dev = gauss.device
     with torch.cuda.device(dev):
         rects = torch.empty((B, N, 2), dtype=torch.int32, device=dev)
-        # row 0: list entries per tile, row 1: items (rectangle pixels) per tile; one leading zero column so
-        # that the inclusive scan is the exclusive offset table
+        # one 64-bit counter per list segment (low word: list entries, high word: items = rectangle pixels), filled by
+        # ONE reduction per (entry, tile); a leading zero row so that the inclusive scans are the exclusive offsets
         S = int(lib().voge_bin_sub())
-        counts = torch.zeros((2, B * TY * TX * S + 1), dtype=torch.int32, device=dev)
+        counters = torch.zeros((B * TY * TX * S + 1, 2), dtype=torch.int32, device=dev)
         check(lib().voge_bin_count(ptr(gauss), kind, ptr(R), ptr(T), ptr(origins),
                                    ptr(focal), ptr(principal), B, N, H, W, float(thr), float(thr_act),
                                    int(bool(use_ref_bins)), int(bin_size), int(tile), int(flags), ptr(rects),
-                                   ptr(counts[0, 1:]), ptr(counts[1, 1:]), stream_of(gauss)), "bin_count")
+                                   ptr(counters[1:]), stream_of(gauss)), "bin_count")
         # two 1-D scans (cub DeviceScan); a (2, n) scan along dim 1 runs one thread block per row
-        offsets = (torch.cumsum(counts[0], 0, dtype=torch.int64), torch.cumsum(counts[1], 0, dtype=torch.int64))
+        offsets = (torch.cumsum(counters[:, 0], 0, dtype=torch.int64), torch.cumsum(counters[:, 1], 0, dtype=torch.int64))
         # one host sync: total list entries + the item count at every view boundary (views can then be
         # processed in groups that bound the forward's scratch)
         per_view = TY * TX * S
@@ -414,8 +414,8 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
         total, view_item_starts = int(host[0]), [int(v) for v in host[1:]]
         total_items = view_item_starts[-1]
         tile_list = torch.empty((max(total, 1), 4), dtype=torch.int32, device=dev)
-        cursor = torch.zeros((B * TY * TX * S,), dtype=torch.int32, device=dev)
-        check(lib().voge_bin_fill(ptr(rects), ptr(offsets[0]), ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
+        cursor = offsets[0][:-1].clone()      # every segment's cursor starts at its offset: one atomic yields the position
+        check(lib().voge_bin_fill(ptr(rects), ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
                                   stream_of(gauss)), "bin_fill")
     item_offsets = offsets[1]
     item_offsets.total_items = total_items

@@ -37,8 +37,8 @@ struct BinArgs {
     int use_ref_bins, bin_size, BH, BW, tile, TX, TY;
     int zero_aware_margin;   // 1: rounding margin counts the non-zero entries of S (default); 0: dense-S constants
     uint2* rects;            // (B,N): x = x0 | x1 << 16, y = y0 | y1 << 16 in PIXELS (inclusive); empty if x0 > x1
-    int32_t* tile_counts;    // (B, TY*TX)
-    int32_t* tile_items;     // optional (B, TY*TX): sum over the tile's entries of the rectangle area inside the tile
+    unsigned long long* tile_counters;   // (B, TY*TX, kBinSub) one 64-bit counter per list segment: low word = list entries,
+                                         // high word = items (sum over the entries of the rectangle area inside the tile)
 };
 
 __device__ __forceinline__ float edge_min(int i, int bin, int S1, int S2, float half) {
@@ -258,21 +258,19 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
         } else {
             rc = make_uint2((unsigned)x0 | ((unsigned)x1 << 16), (unsigned)y0 | ((unsigned)y1 << 16));
             const int tx0 = x0 / a.tile, tx1 = x1 / a.tile, ty0 = y0 / a.tile, ty1 = y1 / a.tile;
-            int32_t* cnt = a.tile_counts + (int64_t)b * a.TX * a.TY * kBinSub + (g & (kBinSub - 1));
-            int32_t* itm = a.tile_items != nullptr ? a.tile_items + (int64_t)b * a.TX * a.TY * kBinSub + (g & (kBinSub - 1)) : nullptr;
+            // ONE 64-bit reduction per (entry, tile) counts the entry and its items (both counters share the request)
+            unsigned long long* cnt = a.tile_counters + (int64_t)b * a.TX * a.TY * kBinSub + (g & (kBinSub - 1));
             for (int ty = ty0; ty <= ty1; ++ty)
-                for (int tx = tx0; tx <= tx1; ++tx) {
-                    atomicAdd(cnt + (ty * a.TX + tx) * kBinSub, 1);
-                    if (itm != nullptr) atomicAdd(itm + (ty * a.TX + tx) * kBinSub, rect_area_in_tile(rc, tx, ty, a.tile));
-                }
+                for (int tx = tx0; tx <= tx1; ++tx)
+                    atomicAdd(cnt + (ty * a.TX + tx) * kBinSub,
+                              1ull | ((unsigned long long)(unsigned)rect_area_in_tile(rc, tx, ty, a.tile) << 32));
         }
         a.rects[(int64_t)b * a.N + g] = rc;
     }
 }
 
 __global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__ rects,
-                                                       const int64_t* __restrict__ tile_offsets,
-                                                       int32_t* __restrict__ cursor, int B, int N, int TX, int TY,
+                                                       unsigned long long* __restrict__ cursor, int B, int N, int TX, int TY,
                                                        int tile, uint4* __restrict__ tile_list) {
     const int b = blockIdx.y;
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
@@ -282,10 +280,11 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) {
                 const int64_t t = (((int64_t)b * TY + ty) * TX + tx) * kBinSub + (g & (kBinSub - 1));
-                const int slot = atomicAdd(cursor + t, 1);
+                // the cursor starts at the segment's offset: one atomic yields the list position
+                const unsigned long long pos = atomicAdd(cursor + t, 1ull);
                 // the entry carries the rectangle: the trace reads list and rectangles with coalesced 16-byte loads
                 // instead of gathering rects[g] per candidate (twice)
-                tile_list[tile_offsets[t] + slot] = make_uint4((unsigned)g, rc.x, rc.y, 0u);
+                tile_list[pos] = make_uint4((unsigned)g, rc.x, rc.y, 0u);
             }
     }
 }
@@ -1178,7 +1177,7 @@ extern "C" int voge_bin_sub(void) { return voge::kBinSub; }
 extern "C" int voge_bin_count(const float* gauss, int sigma_kind, const float* Rm,
                               const float* Tv, const float* origins, const float* focal, const float* principal,
                               int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins, int bin_size,
-                              int tile, int flags, uint32_t* rects, int32_t* tile_counts, int32_t* tile_items,
+                              int tile, int flags, uint32_t* rects, uint64_t* tile_counters,
                               voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || N <= 0) return 0;
@@ -1196,20 +1195,22 @@ extern "C" int voge_bin_count(const float* gauss, int sigma_kind, const float* R
     a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
     a.zero_aware_margin = (flags & 1) ? 0 : 1;
     if (a.TX > 65535 || a.TY > 65535) return (int)cudaErrorInvalidValue;
-    a.rects = reinterpret_cast<uint2*>(rects); a.tile_counts = tile_counts; a.tile_items = tile_items;
+    a.rects = reinterpret_cast<uint2*>(rects); a.tile_counters = reinterpret_cast<unsigned long long*>(tile_counters);
     dim3 grid(cdiv(N, 256), B);   // one Gaussian per thread: the dependent load -> atomic -> store chain is pure latency
     bin_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     VOGE_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int voge_bin_fill(const uint32_t* rects, const int64_t* tile_offsets, int32_t* cursor, int B, int N,
+extern "C" int voge_bin_fill(const uint32_t* rects, uint64_t* cursor, int B, int N,
                              int H, int W, int tile, int32_t* tile_list, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || N <= 0) return 0;
     dim3 grid(cdiv(N, 256), B);   // one Gaussian per thread: the dependent load -> atomic -> store chain is pure latency
-    bin_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(rects), tile_offsets, cursor,
-                                                             B, N, cdiv(W, tile), cdiv(H, tile), tile, reinterpret_cast<uint4*>(tile_list));
+    bin_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(rects),
+                                                             reinterpret_cast<unsigned long long*>(cursor),
+                                                             B, N, cdiv(W, tile), cdiv(H, tile), tile,
+                                                             reinterpret_cast<uint4*>(tile_list));
     VOGE_LAUNCH_CHECK();
     return 0;
 }
