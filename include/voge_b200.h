@@ -184,9 +184,12 @@ int voge_knn_mean_dist(const float* points, int N, int n_nearest, float thr_max,
  *   1  P = inverse(sigmas) (covariances, inverse_sigma = True: `2 * torch.inverse(sigmas)`)
  *   2  P = tril(sigmas) tril(sigmas)^T (Cholesky factor: `to_sym`, demo/EfficientCuboidViaOptimization.py:17-18;
  *      sigma_kind 9 only)
- * voge_pack_gaussians writes one 16-byte-aligned record per Gaussian, out (N, 4 | 8 | 12) floats for
- * sigma_kind 1 | 3 | 9 = [x,y,z,S00] | [x,y,z,S00, S11,S22,0,0] | [x,y,z, S00..S22]; every other kernel of
- * the path reads these records (`gauss`).  voge_unpack_gradients is the matching gradient epilogue: it
+ * voge_pack_gaussians writes one aligned record per Gaussian, out (N, 4 | 8 | 16) floats for
+ * sigma_kind 1 | 3 | 9 = [x,y,z,S00] | [x,y,z,S00, S11,S22,0,0] | [x,y,z,S00, attribute row (4), S01,S02,S10,S11, S12..S22];
+ * every other kernel of the path reads these records (`gauss`).  The attribute row of a kind-9 record (64 bytes) is
+ * written by voge_pack_attr (attr (N, C <= 4) -> zero-padded attr4 (N,4), optional, and / or the records' second 16
+ * bytes, optional): voge_render_backward_image then fetches geometry + attribute of a hit with one 256-bit request
+ * (flag bit 1 of its need_sigma argument).  voge_unpack_gradients is the matching gradient epilogue: it
  * splits the packed gradient records of voge_render_backward_fused into grad_verts (N,3) and grad_sigmas
  * (shaped like sigmas, NULL to skip) and applies the chain rule of sigma_mode (mode 1: -P^T G P^T; mode 2:
  * tril((G + G^T) tril(L))) -- replaces autograd through torch.inverse / to_sym.
@@ -222,6 +225,7 @@ int voge_knn_mean_dist(const float* points, int N, int n_nearest, float thr_max,
 int voge_bin_sub(void);   /* counters / list segments per tile (S below) */
 int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int sigma_mode, int N,
                         float* out, int32_t* iso_flag, voge_stream_t stream);
+int voge_pack_attr(const float* attr, int C, int N, float* attr4, float* gauss16, voge_stream_t stream);
 int voge_unpack_gradients(const float* grad_packed, const float* gauss, const float* sigmas, int sigma_kind,
                           int sigma_mode, int N, float* grad_verts, float* grad_sigmas, voge_stream_t stream);
 int voge_generate_rays(const float* cam, int B, int H, int W, float* rays, voge_stream_t stream);
@@ -293,7 +297,8 @@ int voge_render_backward_fused(const float* gauss, int sigma_kind,
  * background (C) or NULL (plain interpolate_attr); mask_thr as voge_merge_final; weight = the forward's out_weight
  * (required); sat_code (B,H,W) optional = voge_merge_final's clamp code of the same forward (else the kernel rebuilds the
  * un-clamped composite of saturated pixels).  dL/dw_k is formed in registers (no (B,H,W,K) weight-gradient round trip through HBM) and dL/d(attr) is
- * reduced by the same kernel into grad_attr4 (N,4), optional, ZEROED by the caller.  Everything else as
+ * reduced by the same kernel into grad_attr4 (N,4), optional, ZEROED by the caller.  need_sigma: bit 0 = sigma
+ * gradients wanted, bit 1 = the attribute rows live in the kind-9 records (voge_pack_attr).  Everything else as
  * voge_render_backward_fused.                                                                               */
 int voge_render_backward_image(const float* gauss, int sigma_kind, const float* origins, const float* rays,
                                const float* cam, const int32_t* idx, const int64_t* valid_num,

@@ -270,13 +270,19 @@ def aggregation_backward(sel_act, sel_len, sel_dsd, grad_weight, absorptivity):
     return g_act, g_len, g_dsd
 
 
-def pad_attr4(attr):
-    """(n, C <= 4) attribute table -> (n, 4) zero-padded rows (one 16-byte gather per hit in the kernels)."""
+def pad_attr4(attr, gauss=None):
+    """(n, C <= 4) attribute table -> (n, 4) zero-padded rows (one 16-byte gather per hit in the kernels).  gauss: a
+    kind-9 record table (n, 16) of the fused renderer -- the rows are also written into the second 16 bytes of its
+    records (voge_pack_attr), where the image-mode backward fetches them together with the geometry."""
     attr = f32c(attr)
-    if attr.shape[1] == 4:
+    n, C = int(attr.shape[0]), int(attr.shape[1])
+    in_rec = gauss is not None and int(gauss.shape[1]) == 16 and int(gauss.shape[0]) == n
+    if C == 4 and not in_rec:
         return attr
-    out = torch.zeros((attr.shape[0], 4), dtype=torch.float32, device=attr.device)
-    out[:, :attr.shape[1]] = attr
+    with torch.cuda.device(attr.device):
+        out = attr if C == 4 else torch.empty((n, 4), dtype=torch.float32, device=attr.device)
+        check(lib().voge_pack_attr(ptr(attr), C, n, ptr(out) if C != 4 else None, ptr(gauss) if in_rec else None,
+                                   stream_of(attr)), "pack_attr")
     return out
 
 
@@ -345,13 +351,14 @@ def sigma_kind(sigmas):
 
 
 SIGMA_MODES = {"direct": 0, "inverse": 1, "cholesky": 2}
-GAUSS_WIDTH = {1: 4, 3: 8, 9: 12}
+GAUSS_WIDTH = {1: 4, 3: 8, 9: 16}      # floats per record (kind 9: 64 bytes, the second 16 hold the attribute row)
+GRAD_WIDTH = {1: 4, 3: 8, 9: 12}       # floats per packed gradient record
 KIND_ISO_ENCODED = 0x100       # sigma_kind flag: kind-9 records with the isotropic encoding (csrc/render_core.cuh)
 
 
 def record_kind(gauss):
     """sigma_kind argument of the kernels that read the packed records `gauss`"""
-    kind = {4: 1, 8: 3, 12: 9}[int(gauss.shape[1])]
+    kind = {4: 1, 8: 3, 16: 9}[int(gauss.shape[1])]
     return kind | (KIND_ISO_ENCODED if getattr(gauss, "iso_encoded", False) else 0)
 BIN_FLAG_DENSE_MARGIN = 1      # voge_bin_count flags: rounding margin with the dense-S constants (A/B aid)
 
@@ -539,7 +546,7 @@ def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_
     with torch.cuda.device(dev):
         if gauss is None:
             gauss = pack_gaussians(verts, sigmas, sigma_mode)
-        packed = torch.zeros((N, GAUSS_WIDTH[kind]), dtype=torch.float32, device=dev)
+        packed = torch.zeros((N, GRAD_WIDTH[kind]), dtype=torch.float32, device=dev)
         g_rays = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev) if (need_rays and rays is not None) else None
         g_org = torch.zeros((B, 3), dtype=torch.float32, device=dev) if need_origins else None
         g_cam = torch.zeros((B, 16), dtype=torch.float32, device=dev) if (need_cam and rays is None) else None
@@ -554,7 +561,8 @@ def render_backward_fused(verts, sigmas, origins, rays, idx, valid, g_weight, g_
 
 def render_backward_image(verts, sigmas, origins, rays, idx, valid, weight, grad_out, fwd_out, attr4, background,
                           mask_thr, absorptivity, sat_code=None, need_sigma=True, need_attr=True, need_rays=False, need_origins=False,
-                          gauss=None, cam=None, need_cam=False, sigma_mode=0, n_channels=3, need_geometry=True):
+                          gauss=None, cam=None, need_cam=False, sigma_mode=0, n_channels=3, need_geometry=True,
+                          attr_in_records=False):
     """Fused backward with merge_final's backward folded in (voge_render_backward_image): the gradient of the
     composited image -> (g_verts, g_sigmas | None, g_attr (N,C) | None, g_rays | None, g_origins | None, g_cam | None)."""
     verts, sigmas, origins = f32c(verts), f32c(sigmas), f32c(origins)
@@ -570,7 +578,7 @@ def render_backward_image(verts, sigmas, origins, rays, idx, valid, weight, grad
     with torch.cuda.device(dev):
         if gauss is None:
             gauss = pack_gaussians(verts, sigmas, sigma_mode)
-        packed = torch.zeros((N, GAUSS_WIDTH[kind]), dtype=torch.float32, device=dev)
+        packed = torch.zeros((N, GRAD_WIDTH[kind]), dtype=torch.float32, device=dev)
         g_attr4 = torch.zeros((N, 4), dtype=torch.float32, device=dev) if need_attr else None
         g_rays = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev) if (need_rays and rays is not None) else None
         g_org = torch.zeros((B, 3), dtype=torch.float32, device=dev) if need_origins else None
@@ -579,7 +587,8 @@ def render_backward_image(verts, sigmas, origins, rays, idx, valid, weight, grad
                                                ptr(weight), ptr(grad_out), ptr(fwd_out), ptr(sat_code), ptr(attr4),
                                                ptr(background),
                                                float(mask_thr), C, float(absorptivity), B, N, H, W, K, ptr(packed),
-                                               _bwd_flags(need_sigma), ptr(g_attr4), ptr(g_rays), ptr(g_org), ptr(g_cam),
+                                               _bwd_flags(need_sigma) | (2 if (attr_in_records and int(gauss.shape[1]) == 16) else 0),
+                                               ptr(g_attr4), ptr(g_rays), ptr(g_org), ptr(g_cam),
                                                stream_of(verts)), "render_backward_image")
         g_verts, g_sig = unpack_gradients(packed, gauss, sigmas, sigma_mode, need_sigma) if need_geometry else (None, None)
     g_attr = g_attr4[:, :C].contiguous() if need_attr else None

@@ -43,6 +43,7 @@ SIGNATURES = {
     "voge_bin_fill": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "voge_trace_threads": (_I, [_I]),
     "voge_pack_gaussians": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "voge_pack_attr": (_I, [_P, _I, _I, _P, _P, _P]),
     "voge_unpack_gradients": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "voge_generate_rays": (_I, [_P, _I, _I, _I, _P, _P]),
     "voge_trace_hits": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _L, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -327,6 +327,7 @@ struct FusedBwdArgs {
     int C;
     float* grad_attr4;       // optional (N,4), zeroed by the caller: dL/d(attr)
     int enc;                 // kind-9 records carry the isotropic encoding
+    int attr_in_rec;         // image mode, kind 9: the attribute rows live in the records (voge_pack_attr): one request fetches both
 };
 
 // what geom_grad_accumulate needs of the kernel arguments (passed by value to out-of-line callers)
@@ -737,7 +738,9 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
                 }
             }
         }
-        if (IMG) {
+        // kind-9 tables with the attribute rows in the records: geometry + attribute of a slot arrive with one request
+        const bool rec_attr = IMG && KIND == 9 && a.attr_in_rec != 0;
+        if (IMG && !rec_attr) {
             // the attribute rows of this thread's two slots: dL/dw from the image gradient, dL/d(attr) reduced here
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
@@ -761,7 +764,21 @@ __global__ void __launch_bounds__(NT, (CAM ? 4 : 8)) render_bwd_pair_kernel(cons
                 const int g = gv[jj] - pack_off;
                 Hit h;
                 h.len = kEmptyLen; h.act = kEmptyLen; h.dsd = 0.f;
-                if (g >= 0 && g < a.N) h = exact_hit_packed<KIND>(a.gauss, g, c0, c1, c2, d0, d1, d2, a.enc != 0);
+                if (rec_attr) gwv[jj] = -gB;
+                if (g >= 0 && g < a.N) {
+                    if (rec_attr) {
+                        float v0, v1, v2, S[9];
+                        float4 av;
+                        load_gauss_attr9(a.gauss, g, v0, v1, v2, S, av, a.enc != 0);
+                        gwv[jj] = fmaf(go[3], av.w, fmaf(go[2], av.z, fmaf(go[1], av.y, go[0] * av.x))) - gB;
+                        if (a.grad_attr4 != nullptr && wv[jj] != 0.f)
+                            atomicAdd(reinterpret_cast<float4*>(a.grad_attr4) + g,
+                                      make_float4(wv[jj] * go[0], wv[jj] * go[1], wv[jj] * go[2], wv[jj] * go[3]));
+                        h = exact_pair(__fsub_rn(v0, c0), __fsub_rn(v1, c1), __fsub_rn(v2, c2), S, d0, d1, d2);
+                    } else {
+                        h = exact_hit_packed<KIND>(a.gauss, g, c0, c1, c2, d0, d1, d2, a.enc != 0);
+                    }
+                }
                 const float sk = sqrtf(h.dsd + 1e-10f);
                 s_ls[k * NP + col] = make_float2(h.len, sk);
                 s_E[k * NP + col] = expf(-h.act);
@@ -914,7 +931,7 @@ extern "C" int voge_render_backward_fused(const float* gauss, int sigma_kind,
     if (grad_cam != nullptr && (rays != nullptr || cam == nullptr)) return (int)cudaErrorInvalidValue;
     FusedBwdArgs a{gauss, sigma_kind, origins, rays, cam, idx, valid, grad_weight, weight, grad_len_out, absorptivity,
                    B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins, grad_cam,
-                   nullptr, nullptr, nullptr, nullptr, nullptr, -1.f, 0, nullptr, 0};
+                   nullptr, nullptr, nullptr, nullptr, nullptr, -1.f, 0, nullptr, 0, 0};
     a.need_sigma = need_sigma & 1;
     return launch_fused_backward(a, false, need_sigma, (cudaStream_t)stream);
 }
@@ -934,8 +951,9 @@ extern "C" int voge_render_backward_image(const float* gauss, int sigma_kind, co
         return (int)cudaErrorInvalidValue;
     FusedBwdArgs a{gauss, sigma_kind, origins, rays, cam, idx, valid, nullptr, weight, nullptr, absorptivity,
                    B, N, H, W, K, grad_packed, need_sigma, grad_rays, grad_origins, grad_cam,
-                   grad_out, fwd_out, sat_code, attr4, background, mask_thr, C, grad_attr4, 0};
+                   grad_out, fwd_out, sat_code, attr4, background, mask_thr, C, grad_attr4, 0, 0};
     a.need_sigma = need_sigma & 1;
+    a.attr_in_rec = (need_sigma & 2) ? 1 : 0;
     return launch_fused_backward(a, true, need_sigma, (cudaStream_t)stream);
 }
 
@@ -1049,9 +1067,10 @@ __global__ void __launch_bounds__(256) pack_gaussians_kernel(const float* __rest
             if (iso) S[0] = -S[0];
             else if (__float_as_uint(S[0]) >> 31) *iso_flag = 1;
         }
-        o[3 * (int64_t)g] = make_float4(x, y, z, S[0]);
-        o[3 * (int64_t)g + 1] = make_float4(S[1], S[2], S[3], S[4]);
-        o[3 * (int64_t)g + 2] = make_float4(S[5], S[6], S[7], S[8]);
+        o[4 * (int64_t)g] = make_float4(x, y, z, S[0]);
+        o[4 * (int64_t)g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);          // attribute row, voge_pack_attr
+        o[4 * (int64_t)g + 2] = make_float4(S[1], S[2], S[3], S[4]);
+        o[4 * (int64_t)g + 3] = make_float4(S[5], S[6], S[7], S[8]);
     }
 }
 
@@ -1168,6 +1187,30 @@ extern "C" int voge_generate_rays(const float* cam, int B, int H, int W, float* 
     const int64_t total = (int64_t)B * H * W;
     if (total <= 0) return 0;
     generate_rays_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cam, B, H, W, rays);
+    VOGE_LAUNCH_CHECK();
+    return 0;
+}
+
+namespace voge {
+// attribute rows (N, C <= 4) -> zero-padded (N,4) table (one 16-byte gather per hit in the gather-blend kernels) and,
+// for a kind-9 record table, the second 16 bytes of every record (render_core.cuh)
+__global__ void __launch_bounds__(256) pack_attr_kernel(const float* __restrict__ attr, int C, int N,
+                                                        float* __restrict__ attr4, float* __restrict__ gauss16) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) v[c] = attr[(int64_t)g * C + c];
+    const float4 q = make_float4(v[0], v[1], v[2], v[3]);
+    if (attr4 != nullptr) reinterpret_cast<float4*>(attr4)[g] = q;
+    if (gauss16 != nullptr) reinterpret_cast<float4*>(gauss16)[4 * (int64_t)g + 1] = q;
+}
+}  // namespace voge
+
+extern "C" int voge_pack_attr(const float* attr, int C, int N, float* attr4, float* gauss16, voge_stream_t stream) {
+    using namespace voge;
+    if (N <= 0) return 0;
+    if (C < 1 || C > 4) return (int)cudaErrorInvalidValue;
+    pack_attr_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(attr, C, N, attr4, gauss16);
     VOGE_LAUNCH_CHECK();
     return 0;
 }

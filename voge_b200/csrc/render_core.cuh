@@ -97,14 +97,24 @@ __host__ __device__ __forceinline__ int rect_area_in_tile(uint2 rc, int tx, int 
 }
 
 // ---- packed per-Gaussian records (voge_pack_gaussians) ------------------------------------------------
-// One 16-byte-aligned record per Gaussian, [x, y, z | S = 2 sigma ...]: kind 1 -> 4 floats (x,y,z,s),
-// kind 3 -> 8 floats (x,y,z,s0 | s1,s2,-,-), kind 9 -> 12 floats (x,y,z,S00 | S01..S11 | S12..S22).  A hit then
-// costs 1 / 2 / 3 vector loads instead of 4 / 6 / 12 scalar ones (every lane of a warp gathers a different
-// Gaussian, so each load instruction is one L1 tag lookup per lane).
+// One aligned record per Gaussian, [x, y, z | S = 2 sigma ...]: kind 1 -> 4 floats (x,y,z,s), kind 3 -> 8 floats
+// (x,y,z,s0 | s1,s2,-,-), kind 9 -> 16 floats = 64 bytes (x,y,z,S00 | attribute row | S01,S02,S10,S11 | S12..S22).  A hit
+// then costs 1 / 2 / 3 vector loads instead of 4 / 6 / 12 scalar ones (every lane of a warp gathers a different
+// Gaussian, so each load instruction is one L1 tag lookup per lane).  The second 16 bytes of a kind-9 record hold the
+// Gaussian's ATTRIBUTE row (colour; written by voge_pack_attr when an image is composited from the fragments): the
+// image-mode backward fetches geometry + attribute of an isotropic Gaussian with ONE 32-byte request (sm_100's
+// 256-bit ld.global.v8.f32) instead of two gathers into two tables.
 template <int KIND>
 struct GaussWidth {
-    static constexpr int v = (KIND == 9) ? 12 : (KIND == 3 ? 8 : 4);
+    static constexpr int v = (KIND == 9) ? 16 : (KIND == 3 ? 8 : 4);
 };
+
+// 256-bit read-only load (LDG.E.ENL2.256.CONSTANT, sm_100+): p must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const float* __restrict__ p, float4& lo, float4& hi) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
 
 // Isotropic encoding of kind-9 records (sigma_kind | kKindIsoEncoded): a Gaussian whose S is exactly s I, s > 0
 // (every off-diagonal entry +0), carries -s in the S00 slot, so that its whole record is the first 16 bytes
@@ -132,7 +142,25 @@ __device__ __forceinline__ void load_gauss(const float* __restrict__ gp, int g, 
         S[0] = s; S[4] = s; S[8] = s;
         S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
     } else {
-        const float4 b = __ldg(p + 1), c = __ldg(p + 2);
+        const float4 b = __ldg(p + 2), c = __ldg(p + 3);
+        S[0] = a.w; S[1] = b.x; S[2] = b.y; S[3] = b.z; S[4] = b.w; S[5] = c.x; S[6] = c.y; S[7] = c.z; S[8] = c.w;
+    }
+}
+
+// kind-9 record + the attribute row stored in it: one 256-bit request for an isotropic Gaussian, two for a dense one
+__device__ __forceinline__ void load_gauss_attr9(const float* __restrict__ gp, int g, float& v0, float& v1, float& v2,
+                                                 float* S, float4& attr, bool enc) {
+    const float* p = gp + (int64_t)g * 16;
+    float4 a;
+    ldg256(p, a, attr);
+    v0 = a.x; v1 = a.y; v2 = a.z;
+    if (enc && a.w < 0.f) {
+        const float s = -a.w;
+        S[0] = s; S[4] = s; S[8] = s;
+        S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
+    } else {
+        float4 b, c;
+        ldg256(p + 8, b, c);
         S[0] = a.w; S[1] = b.x; S[2] = b.y; S[3] = b.z; S[4] = b.w; S[5] = c.x; S[6] = c.y; S[7] = c.z; S[8] = c.w;
     }
 }

@@ -89,7 +89,7 @@ class FusedSource(object):
     the renderer's backward).  Attached to Fragments as `_fused_src`; it is honoured only while the fragment
     tensors are the very objects the renderer returned."""
     __slots__ = ("verts", "sigmas", "origins", "rays", "cam", "gauss", "sigma_mode", "absorptivity", "weight", "idx",
-                 "valid", "n_points", "K")
+                 "valid", "n_points", "K", "attr_stamp")
 
     def matches(self, weight, idx, valid):
         return weight is self.weight and idx is self.idx and valid is self.valid
@@ -120,7 +120,11 @@ class _RenderImage(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, attr, verts, sigmas, origins, rays, cam, background, src, mask_thr, idx_mod, zero_padding=False):
-        attr4 = _C.pad_attr4(attr)
+        # kind-9 record tables keep the attribute rows in the records' second 16 bytes (one request per hit fetches
+        # geometry + attribute in the backward); the stamp tells the backward whether they are still THIS call's rows
+        attr4 = _C.pad_attr4(attr, gauss=src.gauss)
+        src.attr_stamp = getattr(src, "attr_stamp", 0) + 1
+        ctx.attr_stamp = src.attr_stamp
         out, code = _C.merge_final_forward(attr, src.weight.detach(), src.idx, src.valid, background, mask_thr, idx_mod,
                                            attr4=attr4, want_sat_code=True, zero_padding=zero_padding)
         ctx.save_for_backward(verts, sigmas, origins, rays, cam, attr4, out, background, code)
@@ -136,7 +140,7 @@ class _RenderImage(torch.autograd.Function):
             verts, sigmas, origins, rays, src.idx, src.valid, src.weight.detach(), grad_out.contiguous(), out, attr4,
             background, ctx.mask_thr, src.absorptivity, sat_code=code, need_sigma=need[2], need_attr=need[0], need_rays=need[4],
             need_origins=need[3], gauss=src.gauss, cam=cam, need_cam=need[5], sigma_mode=src.sigma_mode,
-            n_channels=ctx.C)
+            n_channels=ctx.C, attr_in_records=(ctx.attr_stamp == src.attr_stamp))
         return g_attr, g_verts, g_sig, g_org, g_rays, g_cam, None, None, None, None, None
 
 
