@@ -218,7 +218,9 @@ int voge_knn_mean_dist(const float* points, int N, int n_nearest, float thr_max,
  *   number of ITEMS, trace.cu) -- one 64-bit reduction per (entry, tile) serves both.
  *   flags: bit 0 = use the dense-S rounding constants for every Gaussian (default: count the non-zero entries
  *   of S, DESIGN.md "culling margins").
- * voge_bin_fill: scatters 16-byte entries (Gaussian index, rectangle x, rectangle y, 0) into tile_list (total, 4) int32;
+ * voge_bin_fill: scatters 32-byte entries (Gaussian index, rectangle x, rectangle y, 0 | first 16 bytes of the Gaussian's
+ *   record) into tile_list (total, 8) int32 -- the trace then reads its candidates with coalesced loads and gathers only the
+ *   rest of non-isotropic records;
  *   cursor (B*TY*TX*S) uint64 must hold the segments' offsets (exclusive scan of the entry counts; the S segments of
  *   a tile are adjacent) and is advanced: one atomic yields an entry's position.                           */
 #define VOGE_KIND_ISO_ENCODED 0x100
@@ -234,7 +236,7 @@ int voge_bin_count(const float* gauss, int sigma_kind, const float* R,
                    int B, int N, int H, int W, float thr, float thr_act, int use_ref_bins,
                    int bin_size, int tile, int flags, uint32_t* rects, uint64_t* tile_counters,
                    voge_stream_t stream);
-int voge_bin_fill(const uint32_t* rects, uint64_t* cursor, int B, int N,
+int voge_bin_fill(const uint32_t* rects, const float* gauss, int sigma_kind, uint64_t* cursor, int B, int N,
                   int H, int W, int tile, int32_t* tile_list, voge_stream_t stream);
 /* ---- forward pipeline of the fused renderer (csrc/trace.cu, csrc/select.cu) ----------------------------
  *   voge_trace_hits: every item (tile-list entry x pixel of its rectangle inside the tile) is evaluated with

@@ -384,7 +384,7 @@ def generate_rays(cam, image_size):
 
 def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act, use_ref_bins, bin_size,
               tile, gauss=None, sigma_mode=0, flags=None):
-    """-> (tile_offsets (B*TY*TX*S+1,) int64, tile_list (total, 4) int32 = (index, rectangle x, rectangle y, 0), rects (B,N,2) int32,
+    """-> (tile_offsets (B*TY*TX*S+1,) int64, tile_list (total, 8) int32 = (index, rectangle x, rectangle y, 0 | first 16 bytes of the record), rects (B,N,2) int32,
     tile_item_offsets (B*TY*TX*S+1,) int64 with .total_items), S = voge_bin_sub() list segments per tile.
     One host sync (the two totals)."""
     R, T, origins, focal, principal = f32c(R), f32c(T), f32c(origins), f32c(focal), f32c(principal)
@@ -420,9 +420,9 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
             gauss.iso_bad = bool(host.pop())
         total, view_item_starts = int(host[0]), [int(v) for v in host[1:]]
         total_items = view_item_starts[-1]
-        tile_list = torch.empty((max(total, 1), 4), dtype=torch.int32, device=dev)
+        tile_list = torch.empty((max(total, 1), 8), dtype=torch.int32, device=dev)
         cursor = offsets[0][:-1].clone()      # every segment's cursor starts at its offset: one atomic yields the position
-        check(lib().voge_bin_fill(ptr(rects), ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
+        check(lib().voge_bin_fill(ptr(rects), ptr(gauss), kind, ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
                                   stream_of(gauss)), "bin_fill")
     item_offsets = offsets[1]
     item_offsets.total_items = total_items

@@ -40,7 +40,7 @@ SIGNATURES = {
     "voge_knn_mean_dist": (_I, [_P, _I, _I, _F, _P, _P]),
     "voge_bin_sub": (_I, []),
     "voge_bin_count": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _I, _P, _P, _P]),
-    "voge_bin_fill": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "voge_bin_fill": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "voge_trace_threads": (_I, [_I]),
     "voge_pack_gaussians": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "voge_pack_attr": (_I, [_P, _I, _I, _P, _P, _P]),

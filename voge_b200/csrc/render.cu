@@ -269,22 +269,26 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__ rects,
-                                                       unsigned long long* __restrict__ cursor, int B, int N, int TX, int TY,
-                                                       int tile, uint4* __restrict__ tile_list) {
+__global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__ rects, const float* __restrict__ gauss,
+                                                       int rec_f4, unsigned long long* __restrict__ cursor, int B, int N,
+                                                       int TX, int TY, int tile, uint4* __restrict__ tile_list) {
     const int b = blockIdx.y;
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
         const uint2 rc = rects[(int64_t)b * N + g];
         if ((rc.x & 0xffff) > (rc.x >> 16)) continue;
+        // A 32-byte entry carries the rectangle and the first 16 bytes of the record, [x, y, z, S00 | -s]: the trace reads
+        // its candidates with coalesced loads only -- no rects[g] gather (twice per candidate before) and no record
+        // gather for isotropic Gaussians (the whole record of kind 1 and of an encoded kind-9 one)
+        const float4 head = __ldg(reinterpret_cast<const float4*>(gauss) + (int64_t)g * rec_f4);
+        const uint4 e0 = make_uint4((unsigned)g, rc.x, rc.y, 0u);
+        const uint4 e1 = make_uint4(__float_as_uint(head.x), __float_as_uint(head.y), __float_as_uint(head.z), __float_as_uint(head.w));
         const int tx0 = (rc.x & 0xffff) / tile, tx1 = (rc.x >> 16) / tile, ty0 = (rc.y & 0xffff) / tile, ty1 = (rc.y >> 16) / tile;
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) {
                 const int64_t t = (((int64_t)b * TY + ty) * TX + tx) * kBinSub + (g & (kBinSub - 1));
                 // the cursor starts at the segment's offset: one atomic yields the list position
                 const unsigned long long pos = atomicAdd(cursor + t, 1ull);
-                // the entry carries the rectangle: the trace reads list and rectangles with coalesced 16-byte loads
-                // instead of gathering rects[g] per candidate (twice)
-                tile_list[pos] = make_uint4((unsigned)g, rc.x, rc.y, 0u);
+                stg256(tile_list + 2 * pos, e0, e1);      // one 32-byte request
             }
     }
 }
@@ -1245,12 +1249,15 @@ extern "C" int voge_bin_count(const float* gauss, int sigma_kind, const float* R
     return 0;
 }
 
-extern "C" int voge_bin_fill(const uint32_t* rects, uint64_t* cursor, int B, int N,
+extern "C" int voge_bin_fill(const uint32_t* rects, const float* gauss, int sigma_kind, uint64_t* cursor, int B, int N,
                              int H, int W, int tile, int32_t* tile_list, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || N <= 0) return 0;
+    sigma_kind &= ~kKindIsoEncoded;
+    if (sigma_kind != 1 && sigma_kind != 3 && sigma_kind != 9) return (int)cudaErrorInvalidValue;
+    const int rec_f4 = sigma_kind == 9 ? 4 : (sigma_kind == 3 ? 2 : 1);
     dim3 grid(cdiv(N, 256), B);   // one Gaussian per thread: the dependent load -> atomic -> store chain is pure latency
-    bin_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(rects),
+    bin_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(rects), gauss, rec_f4,
                                                              reinterpret_cast<unsigned long long*>(cursor),
                                                              B, N, cdiv(W, tile), cdiv(H, tile), tile,
                                                              reinterpret_cast<uint4*>(tile_list));

@@ -147,6 +147,39 @@ __device__ __forceinline__ void load_gauss(const float* __restrict__ gp, int g, 
     }
 }
 
+// 256-bit store (STG.E.ENL2.256, sm_100+): p must be 32-byte aligned
+__device__ __forceinline__ void stg256(void* p, const uint4 lo, const uint4 hi) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+}
+__device__ __forceinline__ void ldg256u(const void* __restrict__ p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+
+// the rest of a record whose first 16 bytes `a` = [x, y, z, S00 | -s] are already at hand (trace.cu: they travel in the
+// tile-list entry): nothing for kind 1 and for an isotropically encoded kind-9 record, one gather otherwise
+template <int KIND>
+__device__ __forceinline__ void finish_gauss(const float* __restrict__ gp, int g, const float4 a, float* S, bool enc) {
+    if (KIND == 1) {
+        S[0] = a.w; S[4] = a.w; S[8] = a.w;
+        S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
+    } else if (KIND == 3) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(gp) + (int64_t)g * 2 + 1);
+        S[0] = a.w; S[4] = b.x; S[8] = b.y;
+        S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
+    } else if (enc && a.w < 0.f) {
+        const float s = -a.w;
+        S[0] = s; S[4] = s; S[8] = s;
+        S[1] = S[2] = S[3] = S[5] = S[6] = S[7] = 0.f;
+    } else {
+        float4 b, c;
+        ldg256(gp + (int64_t)g * 16 + 8, b, c);
+        S[0] = a.w; S[1] = b.x; S[2] = b.y; S[3] = b.z; S[4] = b.w; S[5] = c.x; S[6] = c.y; S[7] = c.z; S[8] = c.w;
+    }
+}
+
 // kind-9 record + the attribute row stored in it: one 256-bit request for an isotropic Gaussian, two for a dense one
 __device__ __forceinline__ void load_gauss_attr9(const float* __restrict__ gp, int g, float& v0, float& v1, float& v2,
                                                  float* S, float4& attr, bool enc) {

@@ -31,7 +31,7 @@ struct TraceArgs {
     const float* rays;                 // (B,H,W,3), or NULL: generated from `cam` (render_core.cuh: gen_ray)
     const float* cam;                  // (B,16) per-view camera records, read when rays == NULL
     const int64_t* tile_offsets;       // (B*TY*TX*kBinSub + 1) into tile_list
-    const uint4* tile_list;            // (local Gaussian index, rectangle x, rectangle y, -) per entry, from voge_bin_fill
+    const uint4* tile_list;            // 32-byte entries (local Gaussian index, rectangle x, rectangle y, - | first 16 bytes of the record), voge_bin_fill
     const uint2* rects;                // (B,N) conservative pixel rectangles from bin_count_kernel
     const int64_t* tile_item_offsets;  // (B*TY*TX*kBinSub + 1) exclusive scan of tile_items
     int64_t item_base;                 // subtracted from tile_item_offsets: first slot of this call's views in `hits`
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
 
     const int64_t beg = a.tile_offsets[tile_id * kBinSub];
     const int n = (int)(a.tile_offsets[(tile_id + 1) * kBinSub] - beg);
-    const uint4* list = a.tile_list + beg;
+    const uint4* list = a.tile_list + 2 * beg;
     const int warp = tid >> 5, lane = tid & 31;
     const int px0 = tx * tile, py0 = ty * tile;
     const int pxe = min(px0 + tile, a.W) - 1, pye = min(py0 + tile, a.H) - 1;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
 
     // ---- pre-pass: how many rectangles cover each pixel (2D difference array + prefix sums) ----
     for (int i = tid; i < n; i += NT) {
-        const uint4 ent = __ldg(list + i);
+        const uint4 ent = __ldg(list + 2 * i);
         const uint2 rc = make_uint2(ent.y, ent.z);
         const int xl = max((int)(rc.x & 0xffffu), px0) - px0, xh = min((int)(rc.x >> 16), pxe) - px0;
         const int yl = max((int)(rc.y & 0xffffu), py0) - py0, yh = min((int)(rc.y >> 16), pye) - py0;
@@ -167,11 +167,13 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
         int area = 0, ng = 0;          // items, item groups
         int pack = kDead;
         if (base + tid < n) {
-            const uint4 ent = __ldg(list + base + tid);
+            uint4 ent, hd;
+            ldg256u(list + 2 * (base + tid), ent, hd);
             const int g = (int)ent.x;
             const uint2 rc = make_uint2(ent.y, ent.z);
-            float v0, v1, v2, S[9];
-            load_gauss<KIND>(a.gauss, g, v0, v1, v2, S, a.enc != 0);
+            const float v0 = __uint_as_float(hd.x), v1 = __uint_as_float(hd.y), v2 = __uint_as_float(hd.z);
+            float S[9];
+            finish_gauss<KIND>(a.gauss, g, make_float4(v0, v1, v2, __uint_as_float(hd.w)), S, a.enc != 0);
             const float m0 = __fsub_rn(v0, c0), m1 = __fsub_rn(v1, c1), m2 = __fsub_rn(v2, c2);   // verts - ray_origin, Renderer.py:130
             const int xl = max((int)(rc.x & 0xffffu), px0), xh = min((int)(rc.x >> 16), pxe);
             const int yl = max((int)(rc.y & 0xffffu), py0), yh = min((int)(rc.y >> 16), pye);
