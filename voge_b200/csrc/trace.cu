@@ -158,6 +158,11 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     __syncthreads();   // the records alias s_diff / s_rowp
     unsigned n_eval = 0;
 
+    // the list entries of a chunk are requested before the item loop of the previous one (coalesced 32-byte loads):
+    // a chunk's set-up then starts with its candidates at hand
+    uint4 ent, hd;
+    ent = make_uint4(0u, 1u, 0u, 0u); hd = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < n) ldg256u(list + 2 * tid, ent, hd);
     for (int base = 0, buf = 0; base < n; buf ^= 1) {
         float* s_rec = s_rec_all + (size_t)buf * NT * REC;
         int2* s_meta = s_meta_all + buf * (NT + 2);
@@ -167,8 +172,6 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
         int area = 0, ng = 0;          // items, item groups
         int pack = kDead;
         if (base + tid < n) {
-            uint4 ent, hd;
-            ldg256u(list + 2 * (base + tid), ent, hd);
             const int g = (int)ent.x;
             const uint2 rc = make_uint2(ent.y, ent.z);
             const float v0 = __uint_as_float(hd.x), v1 = __uint_as_float(hd.y), v2 = __uint_as_float(hd.z);
@@ -222,6 +225,10 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
         }
         const int taken = __syncthreads_count(take);
         const int total = s_meta[taken].x & 0xffff; // first group of the first candidate left out = groups taken
+        {
+            const int nb = base + max(taken, 1) + tid;      // this thread's candidate of the next chunk
+            if (nb < n) ldg256u(list + 2 * nb, ent, hd);
+        }
 
         // ---- items: blocks of 32 consecutive groups, round-robin over the warps; a lane keeps the record of
         // its group's candidate in registers for the kGroup pixels ----
