@@ -222,7 +222,15 @@ int voge_knn_mean_dist(const float* points, int N, int n_nearest, float thr_max,
  *   record) into tile_list (total, 8) int32 -- the trace then reads its candidates with coalesced loads and gathers only the
  *   rest of non-isotropic records;
  *   cursor (B*TY*TX*S) uint64 must hold the segments' offsets (exclusive scan of the entry counts; the S segments of
- *   a tile are adjacent) and is advanced: one atomic yields an entry's position.                           */
+ *   a tile are adjacent) and is advanced: one atomic yields an entry's position.
+ *
+ * Speculative scratch (no host round trip between voge_bin_count and the rest of the forward): a caller that sizes
+ *   tile_list and hits from a PREVIOUS call's totals passes those sizes as list_capacity (entries) / hits_capacity
+ *   (slots); voge_bin_fill then drops entries past the capacity and voge_trace_hits skips (counts = 0) every tile
+ *   whose list or segment area would cross one, so nothing is read or written out of bounds.  The caller reads
+ *   the true totals (last elements of the two scans) asynchronously and must repeat the call with exact sizes
+ *   when they exceed the capacities.  <= 0: the buffers have their exact sizes.  item_base < 0 in
+ *   voge_trace_hits: the kernel reads it from tile_item_offsets[0] (the group's first tile).                */
 #define VOGE_KIND_ISO_ENCODED 0x100
 int voge_bin_sub(void);   /* counters / list segments per tile (S below) */
 int voge_pack_gaussians(const float* verts, const float* sigmas, int sigma_kind, int sigma_mode, int N,
@@ -237,7 +245,7 @@ int voge_bin_count(const float* gauss, int sigma_kind, const float* R,
                    int bin_size, int tile, int flags, uint32_t* rects, uint64_t* tile_counters,
                    voge_stream_t stream);
 int voge_bin_fill(const uint32_t* rects, const float* gauss, int sigma_kind, uint64_t* cursor, int B, int N,
-                  int H, int W, int tile, int32_t* tile_list, voge_stream_t stream);
+                  int H, int W, int tile, int32_t* tile_list, int64_t list_capacity, voge_stream_t stream);
 /* ---- forward pipeline of the fused renderer (csrc/trace.cu, csrc/select.cu) ----------------------------
  *   voge_trace_hits: every item (tile-list entry x pixel of its rectangle inside the tile) is evaluated with
  *       the reference's arithmetic (ray_trace_voge.cu:188-193); hits (act < thr_act, len < 1e10, :197) are
@@ -261,7 +269,7 @@ int voge_trace_hits(const float* gauss, int sigma_kind, const float* origins,
                     const float* rays, const float* cam, const int64_t* tile_offsets, const int32_t* tile_list,
                     const uint32_t* rects, const int64_t* tile_item_offsets, int64_t item_base, float thr_act,
                     int B, int N, int H, int W, int tile, int32_t* counts, int64_t* seg_base, uint32_t* hits,
-                    uint64_t* stats, voge_stream_t stream);
+                    int64_t list_capacity, int64_t hits_capacity, uint64_t* stats, voge_stream_t stream);
 int voge_select_topk(const int32_t* counts, const int64_t* seg_base, const uint32_t* hits,
                      int view_base, int B, int N, int H, int W, int K, int tile,
                      int32_t* out_idx, int64_t* out_valid, uint64_t* stats, voge_stream_t stream);

@@ -613,3 +613,59 @@ def test_two_rank_nccl_gradients_equal_single_rank(tmp_path):
         err = float((a - b).abs().max() / b.abs().max())
         print("[2-rank NCCL] d%s: max|allreduced - single| / max %.2e" % (name, err))
         assert err < 2e-5 and float(b.abs().max()) > 0
+
+
+def test_speculative_binning_matches_exact(monkeypatch):
+    """Second and later calls of a shape size tile_list / the hit segments from the previous call's totals and queue
+    the whole forward without a host round trip (_C.BinPlan); the totals are validated afterwards.  Fragments must be
+    bit-identical to the exact pass (a) when the plan holds, (b) when the capacities are too small (the kernels skip
+    what does not fit, the renderer repeats the call with exact sizes), (c) when the scene outgrows the slack,
+    (d) when the views are traced in several groups."""
+    from voge_b200 import _C
+    from voge_b200.Meshes import GaussianMeshes
+    sc = small_scene(seed=17, n=500, views=3, K=10)
+    H, W = sc["image_size"]
+    r = _renderer(sc["R"], sc["T"], sc["focal"], sc["principal"], (H, W), 10, M=500)
+
+    def render(sig_scale=1.0):
+        gm = GaussianMeshes(sc["verts"].clone(), sc["sigmas"].clone() * sig_scale).to(DEV)
+        f = r(gm)
+        return [t.clone() for t in (f.vert_index, f.vert_weight, f.vert_hit_length, f.valid_num)]
+
+    def same(a, b):
+        return all(torch.equal(x, y) for x, y in zip(a, b))
+
+    validated = []
+    orig_valid = _C.bins_valid
+    monkeypatch.setattr(_C, "bins_valid", lambda io: (validated.append((hasattr(io, "spec"), orig_valid(io))), validated[-1][1])[1])
+    _C._bin_plans.clear()
+    exact = render()
+    assert validated == [(False, True)] and len(_C._bin_plans) == 1
+    spec = render()                                                    # (a)
+    assert validated[-1] == (True, True) and same(exact, spec)
+    assert int(exact[3].sum()) > 1000
+    (key, plan), = _C._bin_plans.items()
+    plan.list_cap = 7                                                  # (b) tile list too small
+    assert same(exact, render()) and validated[-1] == (True, False)
+    _C._bin_plans[key].view_items = 5                                  # (b) hit segments too small
+    assert same(exact, render()) and validated[-1] == (True, False)
+    assert same(exact, render()) and validated[-1] == (True, True)     # the plan was refreshed from the true totals
+    monkeypatch.setenv("VOGE_NO_SPECULATION", "1")
+    big_exact = render(0.3)                                            # (c) every Gaussian ~1.8x wider
+    assert validated[-1] == (False, True)
+    monkeypatch.delenv("VOGE_NO_SPECULATION")
+    _C._bin_plans.clear()
+    render()
+    big = render(0.3)
+    assert validated[-1] == (True, False) and same(big_exact, big)
+    # (d) several groups of views per call: scratch budget of ~1.2 views
+    _C._bin_plans.clear()
+    render()
+    (key, plan), = _C._bin_plans.items()
+    monkeypatch.setattr(_C, "MAX_GROUP_ITEMS", int(plan.view_items * 1.2))
+    _C._bin_plans.clear()
+    g_exact = render()
+    g_spec = render()
+    assert validated[-1] == (True, True) and same(exact, g_exact) and same(exact, g_spec)
+    (key, plan), = _C._bin_plans.items()
+    assert len(plan.groups(3, _C.MAX_GROUP_ITEMS)) == 3

@@ -382,11 +382,61 @@ def generate_rays(cam, image_size):
     return rays
 
 
+class BinPlan(object):
+    """Scratch sizes carried from one renderer call to the next of the same shape (speculative binning).
+
+    bin_views needs two totals that only the device knows after voge_bin_count -- the tile-list entries and the
+    items (hit slots) per view -- to size tile_list and the hit segments.  Reading them back costs a host round
+    trip in the middle of the forward (the launch queue drains).  With a plan the scratch is
+    sized from the PREVIOUS call (+ 12.5 %), every launch of the forward is queued without waiting, the kernels
+    never step outside the capacities (include/voge_b200.h "Speculative scratch"), and the true totals arrive
+    through a pinned buffer that the host checks after the last launch (bins_valid): the GPU is busy with the
+    queued kernels while the host waits for an event that completed long ago.  A violated capacity (the scene
+    grew by more than the slack) repeats the call with exact sizes."""
+    SLACK_NUM, SLACK_DEN = 9, 8
+    __slots__ = ("list_cap", "view_items", "hits_cap", "pinned", "done")
+
+    def __init__(self, total_entries, max_view_items):
+        self.pinned = self.done = None
+        self.update(total_entries, max_view_items)
+
+    def update(self, total_entries, max_view_items):
+        self.list_cap = int(total_entries) * self.SLACK_NUM // self.SLACK_DEN + 1024
+        self.view_items = int(max_view_items) * self.SLACK_NUM // self.SLACK_DEN + 4096
+        self.hits_cap = 0
+
+    def mailbox(self, n):
+        """The plan's own pinned buffer + event for the totals, allocated once: a fresh pinned tensor per call goes
+        through the caching host allocator, whose blocks become reusable only after an event recorded when they are
+        FREED (behind everything queued by then) -- with the GPU a step behind that means a cudaHostAlloc per call."""
+        if self.pinned is None or int(self.pinned.numel()) != n:
+            self.pinned = torch.empty((n,), dtype=torch.int64, pin_memory=True)
+            self.done = torch.cuda.Event()
+        return self.pinned, self.done
+
+    def groups(self, B, max_group_items):
+        """Views per trace / select launch so that a group's items fit the scratch budget, from the largest view of the
+        previous call (independent of the order of the cameras)."""
+        per = max(1, min(B, int(max_group_items) // max(self.view_items, 1)))
+        self.hits_cap = per * self.view_items
+        return [(b0, min(b0 + per, B)) for b0 in range(0, B, per)]
+
+
+_bin_plans = {}
+MAX_GROUP_ITEMS = 1 << 29      # 8 bytes of hit scratch per item
+
+
+def speculation_enabled():
+    return os.environ.get("VOGE_NO_SPECULATION") != "1"
+
+
 def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, thr_act, use_ref_bins, bin_size,
-              tile, gauss=None, sigma_mode=0, flags=None):
+              tile, gauss=None, sigma_mode=0, flags=None, speculate=False, max_group_items=None):
     """-> (tile_offsets (B*TY*TX*S+1,) int64, tile_list (total, 8) int32 = (index, rectangle x, rectangle y, 0 | first 16 bytes of the record), rects (B,N,2) int32,
     tile_item_offsets (B*TY*TX*S+1,) int64 with .total_items), S = voge_bin_sub() list segments per tile.
-    One host sync (the two totals)."""
+    One host sync (the two totals) -- or none with speculate=True once a call of the same shape has left a BinPlan:
+    the result then carries `.spec` and the caller must check bins_valid(item_offsets) after queueing the forward
+    and repeat with speculate=False when it returns False."""
     R, T, origins, focal, principal = f32c(R), f32c(T), f32c(origins), f32c(focal), f32c(principal)
     if gauss is None:
         gauss = pack_gaussians(verts, sigmas, sigma_mode)
@@ -397,6 +447,10 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
     if flags is None:
         flags = BIN_FLAG_DENSE_MARGIN if os.environ.get("VOGE_DENSE_MARGIN") == "1" else 0
     dev = gauss.device
+    max_group_items = MAX_GROUP_ITEMS if max_group_items is None else int(max_group_items)
+    key = (dev.index, B, N, H, W, int(tile), bool(use_ref_bins), int(bin_size), kind, int(max_group_items),
+           bool(getattr(gauss, "iso_encoded", False)))
+    plan = _bin_plans.get(key) if (speculate and speculation_enabled()) else None
     with torch.cuda.device(dev):
         rects = torch.empty((B, N, 2), dtype=torch.int32, device=dev)
         # one 64-bit counter per list segment (low word: list entries, high word: items = rectangle pixels), filled by
@@ -409,25 +463,62 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
                                    ptr(counters[1:]), stream_of(gauss)), "bin_count")
         # two 1-D scans (cub DeviceScan); a (2, n) scan along dim 1 runs one thread block per row
         offsets = (torch.cumsum(counters[:, 0], 0, dtype=torch.int64), torch.cumsum(counters[:, 1], 0, dtype=torch.int64))
-        # one host sync: total list entries + the item count at every view boundary (views can then be
-        # processed in groups that bound the forward's scratch)
+        # the totals the host needs: list entries + the item count at every view boundary (views can then be
+        # processed in groups that bound the forward's scratch) + the isotropic encoding's ambiguity flag
         per_view = TY * TX * S
         iso_flag = getattr(gauss, "iso_flag", None)
-        host = torch.cat([offsets[0][-1:], offsets[1][::per_view]] + ([iso_flag.to(torch.int64)] if iso_flag is not None else [])).tolist()
-        if iso_flag is not None:
-            # the isotropic encoding is ambiguous for this scene (a non-encoded record has a negative S00): the caller
-            # re-packs plain records and bins again (the same host sync told us)
-            gauss.iso_bad = bool(host.pop())
-        total, view_item_starts = int(host[0]), [int(v) for v in host[1:]]
-        total_items = view_item_starts[-1]
-        tile_list = torch.empty((max(total, 1), 8), dtype=torch.int32, device=dev)
+        totals = torch.cat([offsets[0][-1:], offsets[1][::per_view]] + ([iso_flag.to(torch.int64)] if iso_flag is not None else []))
+        item_offsets = offsets[1]
+        if plan is None:
+            host = totals.tolist()             # the one host sync of the exact path
+            if iso_flag is not None:
+                # the isotropic encoding is ambiguous for this scene (a non-encoded record has a negative S00): the
+                # caller re-packs plain records and bins again (the same host sync told us)
+                gauss.iso_bad = bool(host.pop())
+            total, view_item_starts = int(host[0]), [int(v) for v in host[1:]]
+            vmax = max(b - a for a, b in zip(view_item_starts[:-1], view_item_starts[1:]))
+            if key in _bin_plans:
+                _bin_plans[key].update(total, vmax)
+            else:
+                _bin_plans[key] = BinPlan(total, vmax)
+            list_cap = 0
+            tile_list = torch.empty((max(total, 1), 8), dtype=torch.int32, device=dev)
+            item_offsets.total_items = view_item_starts[-1]
+            item_offsets.view_item_starts = view_item_starts      # B + 1 host ints
+        else:
+            pinned, done = plan.mailbox(int(totals.numel()))
+            pinned.copy_(totals, non_blocking=True)
+            done.record()
+            list_cap = plan.list_cap
+            tile_list = torch.empty((list_cap, 8), dtype=torch.int32, device=dev)
+            item_offsets.spec = {"key": key, "plan": plan, "groups": plan.groups(B, max_group_items), "pinned": pinned,
+                                 "done": done, "has_iso_flag": iso_flag is not None, "gauss": gauss}
         cursor = offsets[0][:-1].clone()      # every segment's cursor starts at its offset: one atomic yields the position
         check(lib().voge_bin_fill(ptr(rects), ptr(gauss), kind, ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
-                                  stream_of(gauss)), "bin_fill")
-    item_offsets = offsets[1]
-    item_offsets.total_items = total_items
-    item_offsets.view_item_starts = view_item_starts      # B + 1 host ints
+                                  int(list_cap), stream_of(gauss)), "bin_fill")
     return offsets[0], tile_list, rects, item_offsets
+
+
+def bins_valid(item_offsets):
+    """True if the scratch of a speculative bin_views (and of the render_forward that followed) held everything.
+    Waits for the totals' copy (queued right after the scans, i.e. long finished while the forward's kernels run),
+    refreshes the shape's BinPlan from the true totals either way, and sets gauss.iso_bad like the exact path."""
+    spec = getattr(item_offsets, "spec", None)
+    if spec is None:
+        return True
+    spec["done"].synchronize()
+    host = spec["pinned"].tolist()
+    iso_bad = bool(host.pop()) if spec["has_iso_flag"] else False
+    spec["gauss"].iso_bad = iso_bad
+    total, starts = int(host[0]), [int(v) for v in host[1:]]
+    plan = spec["plan"]
+    ok = total <= plan.list_cap and all(starts[b1] - starts[b0] <= plan.hits_cap for b0, b1 in spec["groups"])
+    if iso_bad:
+        _bin_plans.pop(spec["key"], None)      # such a scene keeps to the exact pass (which re-packs plain records)
+    else:
+        plan.update(total, max(b - a for a, b in zip(starts[:-1], starts[1:])))
+    item_offsets.total_items, item_offsets.view_item_starts = starts[-1], starts
+    return ok and not iso_bad
 
 
 def pack_gaussians(verts, sigmas, sigma_mode=0, iso_encode=False):
@@ -451,7 +542,7 @@ def pack_gaussians(verts, sigmas, sigma_mode=0, iso_encode=False):
 
 
 def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects, thr_act, absorptivity, K, tile,
-                   need_act=True, stats=None, item_offsets=None, gauss=None, max_group_items=1 << 29, debug=None,
+                   need_act=True, stats=None, item_offsets=None, gauss=None, max_group_items=None, debug=None,
                    cam=None, image_size=None, sigma_mode=0):
     """Fragments of the fused renderer: trace_hits -> select_topk -> blend_weights over the tile lists of
     bin_views (item_offsets = its fourth result); no per-pixel capacity limit; the views are traced in groups of
@@ -466,6 +557,7 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
         B, H, W = int(cam.shape[0]), int(image_size[0]), int(image_size[1])
     if item_offsets is None:
         raise RuntimeError("voge_b200.render_forward: item_offsets (bin_views' fourth result) is required")
+    max_group_items = MAX_GROUP_ITEMS if max_group_items is None else int(max_group_items)
     if gauss is None:
         gauss = pack_gaussians(verts, sigmas, sigma_mode)
     N, K = int(gauss.shape[0]), int(K)
@@ -483,7 +575,14 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
         S = int(lib().voge_bin_sub())
         tiles_per_view = (int(tile_offsets.numel()) - 1) // S // max(B, 1)
         starts = getattr(item_offsets, "view_item_starts", None)
-        if starts is None:
+        spec = getattr(item_offsets, "spec", None)
+        list_cap = hits_cap = 0
+        if spec is not None:
+            # speculative scratch (bin_views(speculate=True)): groups and capacities from the shape's BinPlan, the
+            # kernels read the group's item base from the device and skip what does not fit; the caller validates
+            groups, hits_cap, list_cap = spec["groups"], int(spec["plan"].hits_cap), int(spec["plan"].list_cap)
+            starts = None
+        elif starts is None:
             starts = [0] * B + [int(item_offsets.total_items)]
             groups = [(0, B)]
         else:
@@ -495,7 +594,7 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
                     b1 += 1
                 groups.append((b0, b1))
                 b0 = b1
-        cap = max(max(starts[b1] - starts[b0] for b0, b1 in groups), 1)
+        cap = max(max(starts[b1] - starts[b0] for b0, b1 in groups), 1) if starts is not None else max(hits_cap, 1)
         counts = torch.empty((B * tiles_per_view * nt,), dtype=torch.int32, device=dev)
         seg_base = torch.empty((B * tiles_per_view * nt,), dtype=torch.int64, device=dev)
         hits = torch.empty((cap, 2), dtype=torch.int32, device=dev)
@@ -510,8 +609,10 @@ def render_forward(verts, sigmas, origins, rays, tile_offsets, tile_list, rects,
             check(lib().voge_trace_hits(ptr(gauss), skind, ptr(origins[b0:b1]),
                                         ptr(rays[b0:b1]) if rays is not None else None,
                                         ptr(cam[b0:b1]) if cam is not None else None, ptr(t_off),
-                                        ptr(tile_list), ptr(rects[b0:b1]), ptr(i_off), int(starts[b0]), float(thr_act),
-                                        nb, N, H, W, int(tile), ptr(c_g), ptr(s_g), ptr(hits), ptr(stats), st),
+                                        ptr(tile_list), ptr(rects[b0:b1]), ptr(i_off),
+                                        int(starts[b0]) if starts is not None else -1, float(thr_act),
+                                        nb, N, H, W, int(tile), ptr(c_g), ptr(s_g), ptr(hits), list_cap, hits_cap,
+                                        ptr(stats), st),
                   "trace_hits")
             check(lib().voge_select_topk(ptr(c_g), ptr(s_g), ptr(hits), b0, nb, N, H, W, K, int(tile),
                                          ptr(idx[b0:b1]), ptr(valid[b0:b1]), ptr(stats), st), "select_topk")

@@ -40,13 +40,13 @@ SIGNATURES = {
     "voge_knn_mean_dist": (_I, [_P, _I, _I, _F, _P, _P]),
     "voge_bin_sub": (_I, []),
     "voge_bin_count": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _I, _P, _P, _P]),
-    "voge_bin_fill": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "voge_bin_fill": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "voge_trace_threads": (_I, [_I]),
     "voge_pack_gaussians": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "voge_pack_attr": (_I, [_P, _I, _I, _P, _P, _P]),
     "voge_unpack_gradients": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "voge_generate_rays": (_I, [_P, _I, _I, _I, _P, _P]),
-    "voge_trace_hits": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _L, _F, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "voge_trace_hits": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _L, _F, _I, _I, _I, _I, _I, _P, _P, _P, _L, _L, _P, _P]),
     "voge_select_topk": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "voge_blend_weights": (_I, [_P, _I, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "voge_render_backward_fused": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _I, _P, _I, _P, _P,

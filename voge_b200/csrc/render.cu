@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
 
 __global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__ rects, const float* __restrict__ gauss,
                                                        int rec_f4, unsigned long long* __restrict__ cursor, int B, int N,
-                                                       int TX, int TY, int tile, uint4* __restrict__ tile_list) {
+                                                       int TX, int TY, int tile, uint4* __restrict__ tile_list,
+                                                       unsigned long long list_capacity) {
     const int b = blockIdx.y;
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < N; g += gridDim.x * blockDim.x) {
         const uint2 rc = rects[(int64_t)b * N + g];
@@ -288,7 +289,8 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const uint2* __restrict__
                 const int64_t t = (((int64_t)b * TY + ty) * TX + tx) * kBinSub + (g & (kBinSub - 1));
                 // the cursor starts at the segment's offset: one atomic yields the list position
                 const unsigned long long pos = atomicAdd(cursor + t, 1ull);
-                stg256(tile_list + 2 * pos, e0, e1);      // one 32-byte request
+                // speculative capacity (sized from the previous call, validated by the host afterwards): never write past it
+                if (pos < list_capacity) stg256(tile_list + 2 * pos, e0, e1);      // one 32-byte request
             }
     }
 }
@@ -1250,7 +1252,7 @@ extern "C" int voge_bin_count(const float* gauss, int sigma_kind, const float* R
 }
 
 extern "C" int voge_bin_fill(const uint32_t* rects, const float* gauss, int sigma_kind, uint64_t* cursor, int B, int N,
-                             int H, int W, int tile, int32_t* tile_list, voge_stream_t stream) {
+                             int H, int W, int tile, int32_t* tile_list, int64_t list_capacity, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || N <= 0) return 0;
     sigma_kind &= ~kKindIsoEncoded;
@@ -1260,7 +1262,8 @@ extern "C" int voge_bin_fill(const uint32_t* rects, const float* gauss, int sigm
     bin_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(rects), gauss, rec_f4,
                                                              reinterpret_cast<unsigned long long*>(cursor),
                                                              B, N, cdiv(W, tile), cdiv(H, tile), tile,
-                                                             reinterpret_cast<uint4*>(tile_list));
+                                                             reinterpret_cast<uint4*>(tile_list),
+                                                             list_capacity > 0 ? (unsigned long long)list_capacity : ~0ull);
     VOGE_LAUNCH_CHECK();
     return 0;
 }

@@ -34,7 +34,9 @@ struct TraceArgs {
     const uint4* tile_list;            // 32-byte entries (local Gaussian index, rectangle x, rectangle y, - | first 16 bytes of the record), voge_bin_fill
     const uint2* rects;                // (B,N) conservative pixel rectangles from bin_count_kernel
     const int64_t* tile_item_offsets;  // (B*TY*TX*kBinSub + 1) exclusive scan of tile_items
-    int64_t item_base;                 // subtracted from tile_item_offsets: first slot of this call's views in `hits`
+    int64_t item_base;                 // subtracted from tile_item_offsets: first slot of this call's views in `hits`; < 0: tile_item_offsets[0]
+    int64_t list_capacity;             // entries allocated in tile_list / slots allocated in hits when the caller sized them
+    int64_t hits_capacity;             // speculatively (<= 0: exact sizes): a tile that would cross either is skipped
     float thr_act;
     int B, N, H, W, tile, TX, TY;
     int enc;                           // kind-9 records carry the isotropic encoding (render_core.cuh: kKindIsoEncoded)
@@ -117,7 +119,17 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     for (int i = tid; i < 17 * 17; i += NT) s_diff[i] = 0;
 
     const int64_t beg = a.tile_offsets[tile_id * kBinSub];
-    const int n = (int)(a.tile_offsets[(tile_id + 1) * kBinSub] - beg);
+    const int64_t end = a.tile_offsets[(tile_id + 1) * kBinSub];
+    const int n = (int)(end - beg);
+    const int64_t item_base = a.item_base >= 0 ? a.item_base : a.tile_item_offsets[0];
+    if ((a.list_capacity > 0 && end > a.list_capacity) ||
+        (a.hits_capacity > 0 && a.tile_item_offsets[(tile_id + 1) * kBinSub] - item_base > a.hits_capacity)) {
+        // the caller's speculative scratch is too small for this tile: nothing is read or written outside it, the
+        // host sees the true totals and repeats the call with exact sizes (voge_b200/_C.py: BinPlan)
+        a.counts[tile_id * NT + tid] = 0;
+        a.seg_base[tile_id * NT + tid] = 0;
+        return;
+    }
     const uint4* list = a.tile_list + 2 * beg;
     const int warp = tid >> 5, lane = tid & 31;
     const int px0 = tx * tile, py0 = ty * tile;
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     int cover = 0;
     if (tid < tile * tile)
         for (int y = 0; y <= ly; ++y) cover += s_rowp[y * 16 + lx];
-    const int64_t tile_base = a.tile_item_offsets[tile_id * kBinSub] - a.item_base;
+    const int64_t tile_base = a.tile_item_offsets[tile_id * kBinSub] - item_base;
     {
         const int2 sc = block_scan<NT>(cover, s_wsum, lane, warp);
         s_base[tid] = sc.x - cover;
@@ -342,14 +354,14 @@ extern "C" int voge_trace_hits(const float* gauss, int sigma_kind, const float* 
                                const float* rays, const float* cam, const int64_t* tile_offsets, const int32_t* tile_list,
                                const uint32_t* rects, const int64_t* tile_item_offsets, int64_t item_base, float thr_act, int B, int N,
                                int H, int W, int tile, int32_t* counts, int64_t* seg_base, uint32_t* hits,
-                               uint64_t* stats, voge_stream_t stream) {
+                               int64_t list_capacity, int64_t hits_capacity, uint64_t* stats, voge_stream_t stream) {
     using namespace voge;
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     TraceArgs a;
     if (rays == nullptr && cam == nullptr) return (int)cudaErrorInvalidValue;
     a.gauss = gauss; a.origins = origins; a.rays = rays; a.cam = cam; a.tile_offsets = tile_offsets;
     a.tile_list = reinterpret_cast<const uint4*>(tile_list); a.rects = reinterpret_cast<const uint2*>(rects); a.tile_item_offsets = tile_item_offsets;
-    a.item_base = item_base;
+    a.item_base = item_base; a.list_capacity = list_capacity; a.hits_capacity = hits_capacity;
     a.thr_act = thr_act; a.B = B; a.N = N; a.H = H; a.W = W; a.tile = tile; a.TX = cdiv(W, tile); a.TY = cdiv(H, tile);
     a.counts = counts; a.seg_base = seg_base; a.hits = reinterpret_cast<uint2*>(hits);
     a.stats = reinterpret_cast<unsigned long long*>(stats);
