@@ -468,7 +468,8 @@ def run_small_config(args):
     opt = torch.optim.SGD([gm.verts, gm.sigmas, col], lr=0.8 * 1e-4, momentum=0.9) if optim else None
     target = torch.rand(max(count, 1), H, W, 3, generator=g).to(dev)
 
-    def step():
+    def core():
+        # the part of the step that a CUDA graph can hold: renderer forward, composite, loss, fused backward
         bucket.zero()
         out = None
         if renderer is not None:
@@ -485,10 +486,17 @@ def run_small_config(args):
                     if sample:
                         feat, wsum = sample_features(frag, img, n_vert=verts.shape[0])
                         out = out + feat.mean()
+        return out
+
+    def tail():
         if backward:
             bucket.allreduce()
         if opt is not None:
             opt.step()
+
+    def step():
+        out = core()
+        tail()
         return out
     for _ in range(max(args.warmup, 3)):
         step()
@@ -503,6 +511,7 @@ def run_small_config(args):
     torch.cuda.synchronize(); barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     ms_step = max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    launches_eager = int(_lib.launch_count - l0)
     # per-op breakdown (untimed extra steps with CUDA events around every C-ABI call)
     timer = OpTimer()
     _lib.kernel_timer = timer
@@ -512,13 +521,42 @@ def run_small_config(args):
     torch.cuda.synchronize()
     timer.enabled = False
     ops = {k: round(v["total_ms"] / 3, 4) for k, v in timer.summary().items()}
+    # the same step with core() replayed from ONE CUDA graph (voge_b200.graphs.GraphedStep; the all-reduce and the
+    # optimizer stay outside): what the launch-bound configurations cost once the host is out of the way
+    graphed = None
+    _lib.kernel_timer = None
+    loss_eager = float(out.detach()) if out is not None else None
+    out = None          # drop the eager autograd graph (its AccumulateGrad nodes live on the default stream)
+    if renderer is not None and os.environ.get("VOGE_BENCH_NO_GRAPH") != "1":
+        from voge_b200.graphs import GraphedStep
+        gs = GraphedStep(core, device=dev)
+
+        def gstep():
+            out = gs()
+            tail()
+            return out
+        for _ in range(max(args.warmup, 3)):
+            gstep()
+        torch.cuda.synchronize(); barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tg = time.perf_counter()
+        g0.record()
+        for _ in range(args.steps):
+            gout = gstep()
+        g1.record()
+        torch.cuda.synchronize(); barrier()
+        graphed = {"ms_per_step": max_over_ranks(g0.elapsed_time(g1), dev) / args.steps,
+                   "host_wall_ms_per_step": (time.perf_counter() - tg) * 1e3 / args.steps,
+                   "kernel_launches_per_replay": int(gs.launches_per_replay), "recaptures": int(gs.recaptures),
+                   "validated_every_replay": True,
+                   "loss_eager": loss_eager, "loss_graphed": float(gout) if gout is not None else None}
     if rank == 0:
         line = {"metric": ("fwd+bwd" if backward else "fwd") + " Mrays/s", "value": views * H * W / (ms_step * 1e-3) / 1e6,
                 "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "host_wall_ms_per_step": wall_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": {"workload": desc, "views_per_rank": count},
-                "gpu_launches": int(_lib.launch_count - l0), "gpu_launches_per_step": int(_lib.launch_count - l0) // max(args.steps, 1),
-                "roofline": None, "cpu_baseline": None, "e2e": None, "op_breakdown_ms_per_step": ops,
+                "gpu_launches": launches_eager, "gpu_launches_per_step": launches_eager // max(args.steps, 1),
+                "roofline": None, "cpu_baseline": None, "e2e": None, "op_breakdown_ms_per_step": ops, "graphed": graphed,
                 "note": "informational line for BASELINE.json configs[%d]; small scenes are bound by kernel launches and "
                         "the one host sync of the binning, not by a pipe" % (int(cfg[1]) - 1)}
         print(json.dumps(line))

@@ -669,3 +669,61 @@ def test_speculative_binning_matches_exact(monkeypatch):
     assert validated[-1] == (True, True) and same(exact, g_exact) and same(exact, g_spec)
     (key, plan), = _C._bin_plans.items()
     assert len(plan.groups(3, _C.MAX_GROUP_ITEMS)) == 3
+
+
+def test_graphed_step_matches_eager():
+    """voge_b200.graphs.GraphedStep: forward + composite + loss + fused backward replayed from ONE CUDA graph must give
+    the eager step's loss and gradients; when the scene outgrows the capacities baked into the graph the device-side
+    check must trigger a re-capture (results again those of the eager step)."""
+    from voge_b200 import _C, _lib
+    from voge_b200.distributed import GradientBucket
+    from voge_b200.graphs import GraphedStep
+    from voge_b200.Meshes import GaussianMeshes
+    from voge_b200.Renderer import to_white_background
+    sc = small_scene(seed=23, n=600, views=2, K=12)
+    H, W = sc["image_size"]
+    r = _renderer(sc["R"], sc["T"], sc["focal"], sc["principal"], (H, W), 12, M=600)
+    gm = GaussianMeshes(sc["verts"].clone(), sc["sigmas"].clone()).to(DEV)
+    col = torch.nn.Parameter(sc["colors"].clone().to(DEV))
+    bucket = GradientBucket([gm.verts, gm.sigmas, col])
+    tgt = torch.rand(2, H, W, 3, generator=torch.Generator().manual_seed(5)).to(DEV)
+
+    def step():
+        bucket.zero()
+        frag = r(gm)
+        img = to_white_background(frag, col)
+        loss = ((img - tgt) ** 2).mean()
+        loss.backward()
+        return loss
+
+    def eager():
+        loss = float(step().detach())
+        return loss, bucket.flat.clone()
+
+    _C._bin_plans.clear()
+    l_ref, g_ref = eager()
+    gs = GraphedStep(step, device=DEV)
+    assert gs.launches_per_replay >= 8, gs.launches_per_replay
+    n0 = _lib.launch_count
+    for _ in range(3):
+        loss = gs()
+    assert _lib.launch_count - n0 == 3 * gs.launches_per_replay and gs.recaptures == 0
+    err = float((bucket.flat - g_ref).abs().max() / g_ref.abs().max())
+    print("[graphed step] loss eager %.8f graphed %.8f, max|dgrad|/max %.2e" % (l_ref, float(loss), err))
+    assert abs(float(loss) - l_ref) <= 1e-6 * abs(l_ref) and err < 5e-6
+    # parameters updated in place are seen by the replay
+    with torch.no_grad():
+        gm.verts.add_(0.01)
+    l2, g2 = eager()
+    loss = gs()
+    assert abs(float(loss) - l2) <= 1e-6 * abs(l2) and float((bucket.flat - g2).abs().max() / g2.abs().max()) < 5e-6
+    assert abs(l2 - l_ref) > 1e-7
+    # the scene outgrows the graph's scratch: every Gaussian ~1.8x wider
+    with torch.no_grad():
+        gm.sigmas.mul_(0.3)
+    loss = gs()
+    assert gs.recaptures == 1
+    l3, g3 = eager()
+    assert abs(float(loss) - l3) <= 1e-6 * abs(l3) and float((bucket.flat - g3).abs().max() / g3.abs().max()) < 5e-6
+    loss = gs()
+    assert gs.recaptures == 1 and abs(float(loss) - l3) <= 1e-6 * abs(l3)

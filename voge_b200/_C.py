@@ -424,6 +424,10 @@ class BinPlan(object):
 
 _bin_plans = {}
 MAX_GROUP_ITEMS = 1 << 29      # 8 bytes of hit scratch per item
+# Set by voge_b200.graphs.GraphedStep while a step is captured into a CUDA graph: the host can not wait inside a
+# capture, so the capacity check runs on the device (a sticky violation flag that the graph's owner reads after a
+# replay) and a shape without a BinPlan is an error (run the step eagerly once before capturing).
+capture_state = None
 
 
 def speculation_enabled():
@@ -451,6 +455,9 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
     key = (dev.index, B, N, H, W, int(tile), bool(use_ref_bins), int(bin_size), kind, int(max_group_items),
            bool(getattr(gauss, "iso_encoded", False)))
     plan = _bin_plans.get(key) if (speculate and speculation_enabled()) else None
+    if capture_state is not None and plan is None:
+        raise RuntimeError("voge_b200: a renderer call of a new shape inside a CUDA-graph capture (no BinPlan yet, or "
+                           "speculation disabled): run the step eagerly at least once before capturing it")
     with torch.cuda.device(dev):
         rects = torch.empty((B, N, 2), dtype=torch.int32, device=dev)
         # one 64-bit counter per list segment (low word: list entries, high word: items = rectangle pixels), filled by
@@ -486,12 +493,23 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
             item_offsets.total_items = view_item_starts[-1]
             item_offsets.view_item_starts = view_item_starts      # B + 1 host ints
         else:
-            pinned, done = plan.mailbox(int(totals.numel()))
-            pinned.copy_(totals, non_blocking=True)
-            done.record()
+            groups = plan.groups(B, max_group_items)
             list_cap = plan.list_cap
+            if capture_state is None:
+                pinned, done = plan.mailbox(int(totals.numel()))
+                pinned.copy_(totals, non_blocking=True)
+                done.record()
+            else:
+                # inside a graph capture: the same check as bins_valid, evaluated by the device on every replay
+                # (a group holds at most hits_cap / view_items views, so the largest view bounds every group)
+                pinned = done = None
+                starts = totals[1:B + 2]
+                bad = (totals[0] > list_cap) | ((starts[1:] - starts[:-1]).max() > plan.view_items)
+                if iso_flag is not None:
+                    bad = bad | (totals[-1] != 0)
+                capture_state.violation.logical_or_(bad)
             tile_list = torch.empty((list_cap, 8), dtype=torch.int32, device=dev)
-            item_offsets.spec = {"key": key, "plan": plan, "groups": plan.groups(B, max_group_items), "pinned": pinned,
+            item_offsets.spec = {"key": key, "plan": plan, "groups": groups, "pinned": pinned,
                                  "done": done, "has_iso_flag": iso_flag is not None, "gauss": gauss}
         cursor = offsets[0][:-1].clone()      # every segment's cursor starts at its offset: one atomic yields the position
         check(lib().voge_bin_fill(ptr(rects), ptr(gauss), kind, ptr(cursor), B, N, H, W, int(tile), ptr(tile_list),
@@ -506,6 +524,8 @@ def bins_valid(item_offsets):
     spec = getattr(item_offsets, "spec", None)
     if spec is None:
         return True
+    if spec["done"] is None:
+        return True        # captured into a CUDA graph: validated on the device (capture_state.violation)
     spec["done"].synchronize()
     host = spec["pinned"].tolist()
     iso_bad = bool(host.pop()) if spec["has_iso_flag"] else False
