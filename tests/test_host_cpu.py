@@ -139,3 +139,23 @@ def test_batchifier_helpers():
     got = Batchifier(8, batch_args="point_v", target_dims=0, tbar=True)(nn)(point_v=pts.unsqueeze(1), point_t=pts.unsqueeze(0))
     assert torch.allclose(want, got)
     assert Reshaper((2, 3), 0)([torch.ones(4, 5), torch.ones(2, 5)]).shape == (2, 3, 5)
+
+
+def test_bin_plan_capacities_and_groups():
+    """_C.BinPlan (speculative binning): capacities = previous totals + 12.5 % (+ a floor), the views of a call are
+    split into equal groups whose capacity fits the scratch budget, every view lands in exactly one group."""
+    from voge_b200 import _C
+    p = _C.BinPlan(1_000_000, 57_600_000)
+    assert p.list_cap == 1_000_000 * 9 // 8 + 1024 and p.view_items == 57_600_000 * 9 // 8 + 4096
+    g = p.groups(64, 1 << 29)
+    assert g[0] == (0, 8) and g[-1] == (56, 64) and len(g) == 8
+    assert p.hits_cap == 8 * p.view_items <= (1 << 29)
+    assert [b for a, b in g[:-1]] == [a for a, b in g[1:]]                  # contiguous, no gaps
+    # a single view larger than the budget still forms a group (as in the exact pass)
+    g1 = p.groups(3, 1000)
+    assert g1 == [(0, 1), (1, 2), (2, 3)] and p.hits_cap == p.view_items
+    # few views: one group, capacity = views x largest view
+    p2 = _C.BinPlan(10, 100)
+    assert p2.groups(5, 1 << 29) == [(0, 5)] and p2.hits_cap == 5 * p2.view_items
+    p2.update(2000, 3000)
+    assert p2.list_cap == 2000 * 9 // 8 + 1024 and p2.view_items == 3000 * 9 // 8 + 4096

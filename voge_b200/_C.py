@@ -455,6 +455,9 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
     key = (dev.index, B, N, H, W, int(tile), bool(use_ref_bins), int(bin_size), kind, int(max_group_items),
            bool(getattr(gauss, "iso_encoded", False)))
     plan = _bin_plans.get(key) if (speculate and speculation_enabled()) else None
+    if capture_state is None and torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("voge_b200: the renderer was called inside a CUDA-graph capture it does not know about; "
+                           "capture the step with voge_b200.graphs.GraphedStep (its capacity check runs on the device)")
     if capture_state is not None and plan is None:
         raise RuntimeError("voge_b200: a renderer call of a new shape inside a CUDA-graph capture (no BinPlan yet, or "
                            "speculation disabled): run the step eagerly at least once before capturing it")

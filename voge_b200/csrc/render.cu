@@ -82,11 +82,18 @@ __device__ __forceinline__ void ref_bin_range(float lo, float hi, int nb, int bi
 // product rounding nor a partial-sum rounding.  With n = number of non-zero entries of S every form passes through at
 // most 1 + n roundings (10 for a dense S, 4 for a diagonal / isotropic one stored as 3x3 or as a compact kind), so the
 // constants 10 / 20 / 10 above become (1 + n) / 2 (1 + n) / (1 + n): the margin of a diagonal Gaussian shrinks to 0.43x.
-__device__ __forceinline__ bool gaussian_margin(const float* mu, const float* S, float thr_act, bool zero_aware, float& margin) {
-    const float m0 = mu[0], m1 = mu[1], m2 = mu[2];
-    const float q0 = m0 * S[0] + m1 * S[3] + m2 * S[6];
-    const float q1 = m0 * S[1] + m1 * S[4] + m2 * S[7];
-    const float q2 = m0 * S[2] + m1 * S[5] + m2 * S[8];
+// The S-only part (eigenvalues of the symmetric part, Us, the rounding count) is evaluated once per Gaussian and call;
+// the part that depends on mu = verts - camera centre once per view (bin_count_kernel loops over the views).
+struct MarginS {
+    bool ok;       // positive definite, second-order terms negligible
+    float il;      // 1 / lambda_min(sym S)
+    float Us;      // >= || |S| ||_2
+    float g1;      // roundings per 9-term form: 10, or 1 + nnz(S)
+};
+
+__device__ __forceinline__ MarginS gaussian_margin_s(const float* S, bool zero_aware) {
+    MarginS r;
+    r.ok = false; r.il = 0.f; r.Us = 0.f; r.g1 = 10.f;
     const float a = S[0], b = S[4], c = S[8];
     const float s01 = 0.5f * (S[1] + S[3]), s02 = 0.5f * (S[2] + S[6]), s12 = 0.5f * (S[5] + S[7]);
     // smallest / largest eigenvalue of the symmetric part (closed form, Smith 1961)
@@ -102,15 +109,38 @@ __device__ __forceinline__ bool gaussian_margin(const float* mu, const float* S,
             const float p = sqrtf((aa * aa + bb * bb + cc * cc + 2.f * p1) * (1.f / 6.f));
             const float ip = 1.f / p;
             const float b00 = aa * ip, b11 = bb * ip, b22 = cc * ip, b01 = s01 * ip, b02 = s02 * ip, b12 = s12 * ip;
-            float r = 0.5f * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
-            r = fminf(1.f, fmaxf(-1.f, r));
-            const float phi = acosf(r) * (1.f / 3.f);
+            float rr = 0.5f * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+            rr = fminf(1.f, fmaxf(-1.f, rr));
+            const float phi = acosf(rr) * (1.f / 3.f);
             lmax = qq + 2.f * p * cosf(phi);
             lmin = qq + 2.f * p * cosf(phi + 2.0943951023931953f);
         }
         lmin -= 1e-5f * fabsf(lmax);   // rounding of the closed form itself
     }
-    if (!(lmin > 0.f)) return false;
+    if (!(lmin > 0.f)) return r;
+    const float r0 = fabsf(S[0]) + fabsf(S[1]) + fabsf(S[2]), r1 = fabsf(S[3]) + fabsf(S[4]) + fabsf(S[5]),
+                r2 = fabsf(S[6]) + fabsf(S[7]) + fabsf(S[8]);
+    const float k0 = fabsf(S[0]) + fabsf(S[3]) + fabsf(S[6]), k1 = fabsf(S[1]) + fabsf(S[4]) + fabsf(S[7]),
+                k2 = fabsf(S[2]) + fabsf(S[5]) + fabsf(S[8]);
+    r.Us = fmaxf(fmaxf(fmaxf(r0, r1), r2), fmaxf(fmaxf(k0, k1), k2));
+    r.il = 1.f / lmin;
+    if (!(r.Us * r.il < 1.6e4f)) return r;                       // g10 Us / l < 1e-2: second-order terms negligible
+    if (zero_aware) {
+        int nnz = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) nnz += (S[i] != 0.f) ? 1 : 0;
+        r.g1 = (float)(1 + nnz);
+    }
+    r.ok = true;
+    return r;
+}
+
+__device__ __forceinline__ bool gaussian_margin(const float* mu, const float* S, float thr_act, const MarginS& ms, float& margin) {
+    if (!ms.ok) return false;
+    const float m0 = mu[0], m1 = mu[1], m2 = mu[2];
+    const float q0 = m0 * S[0] + m1 * S[3] + m2 * S[6];
+    const float q1 = m0 * S[1] + m1 * S[4] + m2 * S[7];
+    const float q2 = m0 * S[2] + m1 * S[5] + m2 * S[8];
     const float am0 = fabsf(m0), am1 = fabsf(m1), am2 = fabsf(m2);
     const float c0 = am0 * fabsf(S[0]) + am1 * fabsf(S[3]) + am2 * fabsf(S[6]);   // (|S|^T |mu|)_j
     const float c1 = am0 * fabsf(S[1]) + am1 * fabsf(S[4]) + am2 * fabsf(S[7]);
@@ -118,44 +148,48 @@ __device__ __forceinline__ bool gaussian_margin(const float* mu, const float* S,
     const float Tmm = c0 * am0 + c1 * am1 + c2 * am2;
     const float Um2 = sqrtf(c0 * c0 + c1 * c1 + c2 * c2);
     const float Qn = sqrtf(q0 * q0 + q1 * q1 + q2 * q2);
-    const float r0 = fabsf(S[0]) + fabsf(S[1]) + fabsf(S[2]), r1 = fabsf(S[3]) + fabsf(S[4]) + fabsf(S[5]),
-                r2 = fabsf(S[6]) + fabsf(S[7]) + fabsf(S[8]);
-    const float k0 = fabsf(S[0]) + fabsf(S[3]) + fabsf(S[6]), k1 = fabsf(S[1]) + fabsf(S[4]) + fabsf(S[7]),
-                k2 = fabsf(S[2]) + fabsf(S[5]) + fabsf(S[8]);
-    const float Us = fmaxf(fmaxf(fmaxf(r0, r1), r2), fmaxf(fmaxf(k0, k1), k2));
-    const float il = 1.f / lmin;
-    if (!(Us * il < 1.6e4f)) return false;                       // g10 Us / l < 1e-2: second-order terms negligible
-    float g1 = 10.f;
-    if (zero_aware) {
-        int nnz = 0;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) nnz += (S[i] != 0.f) ? 1 : 0;
-        g1 = (float)(1 + nnz);
-    }
+    const float il = ms.il, Us = ms.Us, g1 = ms.g1;
     const float bound = g1 * Tmm + 2.f * g1 * Qn * Um2 * il + g1 * Us * (Qn * il) * (Qn * il) + 2.1f * Qn * Qn * il +
                         2.f * fabsf(thr_act);
     margin = 7.4505806e-8f * 1.003f * bound;                     // 1.25 x 2^-24 (x rays within 1e-3 of unit length)
     return margin >= 0.f && margin < 3.0e38f;
 }
 
+// One thread per Gaussian; the thread walks the views b = blockIdx.y, blockIdx.y + gridDim.y, ... of the call: the record is
+// loaded once and everything that depends on S alone -- the eigenvalues / norms of the rounding margin, the symmetry tests,
+// the adjugate of the tangent bound -- is evaluated once per Gaussian instead of once per (view, Gaussian).
 __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
-    const int b = blockIdx.y;
-    const float* R = a.Rm + 9 * b;
-    const float fx = a.focal[2 * b], fy = a.focal[2 * b + 1];
-    const float px = a.principal[2 * b], py = a.principal[2 * b + 1];
-    const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
     const float sc = 0.5f * (float)min(a.H, a.W);
     const float half_x = __fdiv_rn(ndc_range(a.W, a.H) / 2.0f, (float)a.W);
     const float half_y = __fdiv_rn(ndc_range(a.H, a.W) / 2.0f, (float)a.H);
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < a.N; g += gridDim.x * blockDim.x) {
-        float mu[3], S[9];
-        {
-            float v0, v1, v2;
-            if (a.kind == 1) load_gauss<1>(a.gauss, g, v0, v1, v2, S);
-            else if (a.kind == 3) load_gauss<3>(a.gauss, g, v0, v1, v2, S);
-            else load_gauss<9>(a.gauss, g, v0, v1, v2, S, a.enc != 0);
-            mu[0] = __fsub_rn(v0, c0); mu[1] = __fsub_rn(v1, c1); mu[2] = __fsub_rn(v2, c2);
-        }
+        float S[9], v0, v1, v2;
+        if (a.kind == 1) load_gauss<1>(a.gauss, g, v0, v1, v2, S);
+        else if (a.kind == 3) load_gauss<3>(a.gauss, g, v0, v1, v2, S);
+        else load_gauss<9>(a.gauss, g, v0, v1, v2, S, a.enc != 0);
+        // ---- S only ----
+        const float as01 = fabsf(S[1] - S[3]), as02 = fabsf(S[2] - S[6]), as12 = fabsf(S[5] - S[7]);
+        const bool sym_exact = (as01 == 0.f) && (as02 == 0.f) && (as12 == 0.f);
+        const bool sym_near = as01 <= 9.5367e-7f * (fabsf(S[1]) + fabsf(S[3])) &&
+                              as02 <= 9.5367e-7f * (fabsf(S[2]) + fabsf(S[6])) &&
+                              as12 <= 9.5367e-7f * (fabsf(S[5]) + fabsf(S[7]));
+        MarginS ms;
+        ms.ok = false;
+        if (sym_near) ms = gaussian_margin_s(S, a.zero_aware_margin != 0);
+        // inverse of the symmetric part (adjugate / det)
+        const float a00 = S[0], a11 = S[4], a22 = S[8];
+        const float a01 = 0.5f * (S[1] + S[3]), a02 = 0.5f * (S[2] + S[6]), a12 = 0.5f * (S[5] + S[7]);
+        const float j00 = a11 * a22 - a12 * a12, j01 = a02 * a12 - a01 * a22, j02 = a01 * a12 - a02 * a11;
+        const float j11 = a00 * a22 - a02 * a02, j12 = a01 * a02 - a00 * a12, j22 = a00 * a11 - a01 * a01;
+        const float det = a00 * j00 + a01 * j01 + a02 * j02;
+        const float J[9] = {j00, j01, j02, j01, j11, j12, j02, j12, j22};
+      for (int b = blockIdx.y; b < a.B; b += gridDim.y) {
+        const float* R = a.Rm + 9 * b;
+        const float fx = a.focal[2 * b], fy = a.focal[2 * b + 1];
+        const float px = a.principal[2 * b], py = a.principal[2 * b + 1];
+        const float c0 = a.origins[3 * b], c1 = a.origins[3 * b + 1], c2 = a.origins[3 * b + 2];
+        float mu[3];
+        mu[0] = __fsub_rn(v0, c0); mu[1] = __fsub_rn(v1, c1); mu[2] = __fsub_rn(v2, c2);
         // view space (X_v = mu' @ R since the origin is the camera centre)
         const float xv = mu[0] * R[0] + mu[1] * R[3] + mu[2] * R[6];
         const float yv = mu[0] * R[1] + mu[1] * R[4] + mu[2] * R[7];
@@ -199,23 +233,11 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
         // it is applied to (numerically) symmetric S only; fp32-level asymmetry (|S_ij - S_ji| <=
         // 2^-20 (|S_ij|+|S_ji|), e.g. from R D R^T products) is absorbed by doubling the margin.
         float margin;
-        const float as01 = fabsf(S[1] - S[3]), as02 = fabsf(S[2] - S[6]), as12 = fabsf(S[5] - S[7]);
-        const bool sym_exact = (as01 == 0.f) && (as02 == 0.f) && (as12 == 0.f);
-        const bool sym_near = as01 <= 9.5367e-7f * (fabsf(S[1]) + fabsf(S[3])) &&
-                              as02 <= 9.5367e-7f * (fabsf(S[2]) + fabsf(S[6])) &&
-                              as12 <= 9.5367e-7f * (fabsf(S[5]) + fabsf(S[7]));
-        if (!empty && zv > 0.f && sym_near && gaussian_margin(mu, S, a.thr_act, a.zero_aware_margin != 0, margin)) {
+        if (!empty && zv > 0.f && sym_near && gaussian_margin(mu, S, a.thr_act, ms, margin)) {
             if (!sym_exact) margin *= 2.f;
-            const float a00 = S[0], a11 = S[4], a22 = S[8];
-            const float a01 = 0.5f * (S[1] + S[3]), a02 = 0.5f * (S[2] + S[6]), a12 = 0.5f * (S[5] + S[7]);
-            // inverse of the symmetric part (adjugate / det)
-            const float j00 = a11 * a22 - a12 * a12, j01 = a02 * a12 - a01 * a22, j02 = a01 * a12 - a02 * a11;
-            const float j11 = a00 * a22 - a02 * a02, j12 = a01 * a02 - a00 * a12, j22 = a00 * a11 - a01 * a01;
-            const float det = a00 * j00 + a01 * j01 + a02 * j02;
             const float t = (a.thr_act + margin) * 1.0001f / det;
             // Q = t * R^T J R ; need Q00 Q11 Q22 Q02 Q12
             float JR[3][3];
-            const float J[9] = {j00, j01, j02, j01, j11, j12, j02, j12, j22};
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -266,6 +288,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
                               1ull | ((unsigned long long)(unsigned)rect_area_in_tile(rc, tx, ty, a.tile) << 32));
         }
         a.rects[(int64_t)b * a.N + g] = rc;
+      }
     }
 }
 
@@ -1245,7 +1268,10 @@ extern "C" int voge_bin_count(const float* gauss, int sigma_kind, const float* R
     a.zero_aware_margin = (flags & 1) ? 0 : 1;
     if (a.TX > 65535 || a.TY > 65535) return (int)cudaErrorInvalidValue;
     a.rects = reinterpret_cast<uint2*>(rects); a.tile_counters = reinterpret_cast<unsigned long long*>(tile_counters);
-    dim3 grid(cdiv(N, 256), B);   // one Gaussian per thread: the dependent load -> atomic -> store chain is pure latency
+    // one Gaussian per thread, walking B / grid.y views: as few view slices as still fill the machine (~4 waves of blocks)
+    const int bx = cdiv(N, 256);
+    const int by = min(B, max(1, cdiv(4 * 148 * 8, bx)));
+    dim3 grid(bx, by);
     bin_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     VOGE_LAUNCH_CHECK();
     return 0;
