@@ -158,7 +158,7 @@ __device__ __forceinline__ bool gaussian_margin(const float* mu, const float* S,
 // One thread per Gaussian; the thread walks the views b = blockIdx.y, blockIdx.y + gridDim.y, ... of the call: the record is
 // loaded once and everything that depends on S alone -- the eigenvalues / norms of the rounding margin, the symmetry tests,
 // the adjugate of the tangent bound -- is evaluated once per Gaussian instead of once per (view, Gaussian).
-__global__ void __launch_bounds__(256) bin_count_kernel(const BinArgs a) {
+__global__ void __launch_bounds__(256, 4) bin_count_kernel(const BinArgs a) {
     const float sc = 0.5f * (float)min(a.H, a.W);
     const float half_x = __fdiv_rn(ndc_range(a.W, a.H) / 2.0f, (float)a.W);
     const float half_y = __fdiv_rn(ndc_range(a.H, a.W) / 2.0f, (float)a.H);
