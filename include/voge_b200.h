@@ -265,6 +265,11 @@ int voge_bin_fill(const uint32_t* rects, const float* gauss, int sigma_kind, uin
  *   stats optional 4 x uint64 ([0] items evaluated, [2] pixels selected with the exact 64-bit keys), zeroed
  *   by the caller.                                                                                         */
 int voge_trace_threads(int tile);
+/* Segment alignment: voge_trace_hits starts every pixel's segment on a 32-byte boundary when the tile's area has room for
+ * the rounding (3 slots per pixel + 3 per tile).  A caller that wants it initialises the ITEM half (high word) of each of
+ * the S counters of a tile with voge_bin_item_slack() before voge_bin_count (instead of 0); without that room the
+ * plain layout is used -- both are correct, the aligned one moves ~18 % fewer sectors through trace and selection.  */
+int voge_bin_item_slack(void);
 int voge_trace_hits(const float* gauss, int sigma_kind, const float* origins,
                     const float* rays, const float* cam, const int64_t* tile_offsets, const int32_t* tile_list,
                     const uint32_t* rects, const int64_t* tile_item_offsets, int64_t item_base, float thr_act,

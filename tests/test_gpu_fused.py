@@ -280,7 +280,7 @@ def test_forward_pipeline_dense_ties_and_single_kernel(K, hw):
                           max_group_items=1)
     for x, y in zip(p, g):
         assert torch.equal(x, y)
-    assert int(stats[0]) == ioff.total_items > 0          # every item evaluated exactly once
+    assert int(stats[0]) == ioff.total_items - ioff.slack_items > 0          # every item evaluated exactly once
     assert int(stats[2]) > 0                              # the exact-key selection was exercised
     assert int(p[3].max()) == K
 

@@ -56,7 +56,7 @@ with torch.no_grad():
     torch.cuda.synchronize()
     st = stats.tolist()
     print("per view: tile entries %.3fM  items %.2fM (alloc %.2fM)  exact-select pixels %d  hits %.2fM" % (
-        tl.shape[0] / V / 1e6, st[0] / V / 1e6, ioff.total_items / V / 1e6, st[2] // V, int((out[0] >= 0).sum()) / V / 1e6))
+        tl.shape[0] / V / 1e6, st[0] / V / 1e6, (ioff.total_items - getattr(ioff, 'slack_items', 0)) / V / 1e6, st[2] // V, int((out[0] >= 0).sum()) / V / 1e6))
     if os.environ.get("TILESTATS"):
         # hits per (Gaussian, tile): how much a per-tile Gaussian-major gradient reduction could aggregate
         idx = out[0]

@@ -467,6 +467,11 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
         # ONE reduction per (entry, tile); a leading zero row so that the inclusive scans are the exclusive offsets
         S = int(lib().voge_bin_sub())
         counters = torch.zeros((B * TY * TX * S + 1, 2), dtype=torch.int32, device=dev)
+        slack_items = 0
+        if os.environ.get("VOGE_NO_SEGMENT_ALIGN") != "1":
+            # room for 32-byte aligned pixel segments (include/voge_b200.h "Segment alignment")
+            counters[1:, 1] = int(lib().voge_bin_item_slack())
+            slack_items = int(lib().voge_bin_item_slack()) * B * TY * TX * S
         check(lib().voge_bin_count(ptr(gauss), kind, ptr(R), ptr(T), ptr(origins),
                                    ptr(focal), ptr(principal), B, N, H, W, float(thr), float(thr_act),
                                    int(bool(use_ref_bins)), int(bin_size), int(tile), int(flags), ptr(rects),
@@ -479,6 +484,7 @@ def bin_views(verts, sigmas, R, T, origins, focal, principal, image_size, thr, t
         iso_flag = getattr(gauss, "iso_flag", None)
         totals = torch.cat([offsets[0][-1:], offsets[1][::per_view]] + ([iso_flag.to(torch.int64)] if iso_flag is not None else []))
         item_offsets = offsets[1]
+        item_offsets.slack_items = slack_items      # slots in the totals that are alignment room, not items
         if plan is None:
             host = totals.tolist()             # the one host sync of the exact path
             if iso_flag is not None:

@@ -42,6 +42,7 @@ SIGNATURES = {
     "voge_bin_count": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _I, _I, _I, _P, _P, _P]),
     "voge_bin_fill": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "voge_trace_threads": (_I, [_I]),
+    "voge_bin_item_slack": (_I, []),
     "voge_pack_gaussians": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "voge_pack_attr": (_I, [_P, _I, _I, _P, _P, _P]),
     "voge_unpack_gradients": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
@@ -70,7 +71,7 @@ class _Handle(object):
     def __getattr__(self, name):
         fn = getattr(self._h, name)
         kt = kernel_timer
-        if kt is None or not kt.enabled or name in ("voge_error_string", "voge_version", "voge_trace_threads", "voge_bin_sub"):
+        if kt is None or not kt.enabled or name in ("voge_error_string", "voge_version", "voge_trace_threads", "voge_bin_sub", "voge_bin_item_slack"):
             return fn
 
         def timed(*args):

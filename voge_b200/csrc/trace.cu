@@ -160,12 +160,24 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     int cover = 0;
     if (tid < tile * tile)
         for (int y = 0; y <= ly; ++y) cover += s_rowp[y * 16 + lx];
-    const int64_t tile_base = a.tile_item_offsets[tile_id * kBinSub] - item_base;
+    // Segments start on 32-byte boundaries (4 slots): a sector of `hits` then belongs to ONE pixel, so the selection reads
+    // ceil(hits / 4) sectors per pixel instead of one more on average, and the trace's partial-sector writes shrink alike.
+    // The rounding needs up to 3 slots per pixel + 3 per tile, which the caller adds to the tile's item count before
+    // the scan (voge_bin_item_slack); a tile whose area has no such room keeps the plain layout.
+    const int64_t tile_off = a.tile_item_offsets[tile_id * kBinSub] - item_base;
+    int64_t tile_base = (tile_off + 3) & ~(int64_t)3;
     {
-        const int2 sc = block_scan<NT>(cover, s_wsum, lane, warp);
-        s_base[tid] = sc.x - cover;
-        s_cnt[tid] = sc.x - cover;       // the slot counter starts at the segment base: one atomic yields the slot
-        a.seg_base[tile_id * NT + tid] = tile_base + (sc.x - cover);
+        int cov = (cover + 3) & ~3;
+        int2 sc = block_scan<NT>(cov, s_wsum, lane, warp);
+        if (tile_base + sc.y > a.tile_item_offsets[(tile_id + 1) * kBinSub] - item_base) {
+            __syncthreads();             // the scan scratch is read by every thread before it is rewritten
+            tile_base = tile_off;
+            cov = cover;
+            sc = block_scan<NT>(cov, s_wsum, lane, warp);
+        }
+        s_base[tid] = sc.x - cov;
+        s_cnt[tid] = sc.x - cov;         // the slot counter starts at the segment base: one atomic yields the slot
+        a.seg_base[tile_id * NT + tid] = tile_base + (sc.x - cov);
     }
     __syncthreads();   // the records alias s_diff / s_rowp
     unsigned n_eval = 0;
@@ -349,6 +361,9 @@ static int dispatch_trace(const TraceArgs& a, cudaStream_t s) {
 }  // namespace voge
 
 extern "C" int voge_trace_threads(int tile) { return voge::tile_threads(tile); }
+
+// 3 slots per pixel of the largest tile (256) + 3 for the tile's own alignment, spread over the kBinSub item counters
+extern "C" int voge_bin_item_slack(void) { return (3 * 256 + 3 + voge::kBinSub - 1) / voge::kBinSub; }
 
 extern "C" int voge_trace_hits(const float* gauss, int sigma_kind, const float* origins,
                                const float* rays, const float* cam, const int64_t* tile_offsets, const int32_t* tile_list,
