@@ -52,6 +52,7 @@ struct RecFloats {
     static constexpr int v = (KIND == 9) ? 20 : 8;
 };
 
+constexpr int kSegAlign = 4;                   // pixel segments start on multiples of this many 8-byte slots
 constexpr int kGroup = 4;                      // consecutive items of one candidate evaluated by one lane
 constexpr int kGroupBudget = 4096;             // item groups per chunk (bounds the block tables)
 constexpr int kMaxBlocks = kGroupBudget / 32;
@@ -165,9 +166,9 @@ __global__ void __launch_bounds__(NT, (NT == 256 ? 4 : (NT == 128 ? 6 : 8))) tra
     // The rounding needs up to 3 slots per pixel + 3 per tile, which the caller adds to the tile's item count before
     // the scan (voge_bin_item_slack); a tile whose area has no such room keeps the plain layout.
     const int64_t tile_off = a.tile_item_offsets[tile_id * kBinSub] - item_base;
-    int64_t tile_base = (tile_off + 3) & ~(int64_t)3;
+    int64_t tile_base = (tile_off + (kSegAlign - 1)) & ~(int64_t)(kSegAlign - 1);
     {
-        int cov = (cover + 3) & ~3;
+        int cov = (cover + (kSegAlign - 1)) & ~(kSegAlign - 1);
         int2 sc = block_scan<NT>(cov, s_wsum, lane, warp);
         if (tile_base + sc.y > a.tile_item_offsets[(tile_id + 1) * kBinSub] - item_base) {
             __syncthreads();             // the scan scratch is read by every thread before it is rewritten
@@ -363,7 +364,7 @@ static int dispatch_trace(const TraceArgs& a, cudaStream_t s) {
 extern "C" int voge_trace_threads(int tile) { return voge::tile_threads(tile); }
 
 // 3 slots per pixel of the largest tile (256) + 3 for the tile's own alignment, spread over the kBinSub item counters
-extern "C" int voge_bin_item_slack(void) { return (3 * 256 + 3 + voge::kBinSub - 1) / voge::kBinSub; }
+extern "C" int voge_bin_item_slack(void) { return ((voge::kSegAlign - 1) * 257 + voge::kBinSub - 1) / voge::kBinSub; }
 
 extern "C" int voge_trace_hits(const float* gauss, int sigma_kind, const float* origins,
                                const float* rays, const float* cam, const int64_t* tile_offsets, const int32_t* tile_list,
